@@ -1,0 +1,203 @@
+/*
+ * nabla_cuda.h — C ABI of libnabla_cuda.so, the B200 (sm_100a) backend for the array-valued
+ * reverse sweep of invenia/Nabla.jl.
+ *
+ * Callable identically from Julia `ccall` (julia/NablaCUDA.jl) and Python `ctypes`
+ * (nabla.jl_b200/_lib.py).  Plain pointers and sizes only.  Every function returns an int32 status
+ * (NB_OK == 0), never throws or aborts; `nb_last_error(ctx)` gives the message.  One `nb_ctx` per
+ * host thread / reverse sweep; all device work is enqueued asynchronously on the ctx stream and is
+ * ordered by it (the reference sweep is strictly sequential: src/core.jl:160-166).
+ *
+ * Arrays follow Julia: COLUMN-MAJOR, dense, shape[0] is the contiguous dimension, ndim <= 4,
+ * ndim == 0 is a device-resident scalar.  An operand whose extent in a dimension is 1 (or whose
+ * ndim is smaller) while the result's is larger is broadcast along it, exactly like
+ * `Broadcast.combine_axes` (src/sensitivities/functional/functional.jl:60).
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the reference
+ * checkout).
+ */
+#ifndef NABLA_CUDA_H
+#define NABLA_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NB_ABI_VERSION 1
+#define NB_MAX_DIMS 4
+#define NB_MAX_ARGS 6      /* operands of one broadcast call (the reference caps map at 10) */
+#define NB_MAX_INSTR 32    /* instructions of one scalar program */
+#define NB_MAX_CONSTS 16
+
+typedef struct nb_ctx nb_ctx;
+typedef struct nb_prog nb_prog;
+typedef struct nb_graph nb_graph;
+
+typedef enum nb_status {
+  NB_OK = 0,
+  NB_ERR_INVALID = 1,      /* bad argument (Julia side raises ArgumentError) */
+  NB_ERR_CUDA = 2,         /* CUDA runtime/driver error */
+  NB_ERR_OOM = 3,
+  NB_ERR_UNSUPPORTED = 4,  /* no rule for this op on the device (Julia side raises MethodError) */
+  NB_ERR_COMM = 5,         /* NCCL error or NCCL not loadable */
+  NB_ERR_SHAPE = 6         /* DimensionMismatch */
+} nb_status;
+
+typedef enum nb_dtype { NB_F32 = 0, NB_F64 = 1 } nb_dtype;
+
+/* GEMM arithmetic for Float32 operands (Float64 always runs exact FP64 FMA on the DMMA path). */
+typedef enum nb_math_mode {
+  NB_MATH_DEFAULT = 0,  /* f32: 3xTF32 on tcgen05 (meets rtol 1e-4); f64: DMMA */
+  NB_MATH_TF32 = 1,     /* f32: single-pass TF32 on tcgen05 */
+  NB_MATH_3XTF32 = 2,   /* f32: hi*hi + hi*lo + lo*hi on tcgen05 */
+  NB_MATH_FP32 = 3      /* f32: FP32 FMA on CUDA cores (no tensor cores) */
+} nb_math_mode;
+
+typedef struct nb_tensor {
+  void* data;                  /* device pointer returned by nb_alloc (may be offset into it) */
+  int32_t dtype;               /* nb_dtype */
+  int32_t ndim;                /* 0..NB_MAX_DIMS */
+  int64_t shape[NB_MAX_DIMS];  /* column-major contiguous; entries >= ndim are ignored */
+} nb_tensor;
+
+/* Scalar-function catalogue: the derivative of each is the DiffRules / ChainRules @scalar_rule
+ * formula that ForwardDiff applies inside `fmad` (src/core.jl:285-292); the list is the one pinned
+ * by test/runtests.jl:28-52 (Base part).  Values are part of the ABI. */
+typedef enum nb_op {
+  /* unary */
+  NB_OP_IDENTITY = 0, NB_OP_NEG = 1, NB_OP_ABS = 2, NB_OP_ABS2 = 3, NB_OP_SQRT = 4, NB_OP_CBRT = 5,
+  NB_OP_INV = 6, NB_OP_EXP = 7, NB_OP_EXP2 = 8, NB_OP_EXP10 = 9, NB_OP_EXPM1 = 10, NB_OP_LOG = 11,
+  NB_OP_LOG2 = 12, NB_OP_LOG10 = 13, NB_OP_LOG1P = 14, NB_OP_SIN = 15, NB_OP_COS = 16,
+  NB_OP_TAN = 17, NB_OP_SEC = 18, NB_OP_CSC = 19, NB_OP_COT = 20, NB_OP_SINH = 21,
+  NB_OP_COSH = 22, NB_OP_TANH = 23, NB_OP_SECH = 24, NB_OP_CSCH = 25, NB_OP_COTH = 26,
+  NB_OP_ASIN = 27, NB_OP_ACOS = 28, NB_OP_ATAN = 29, NB_OP_ASEC = 30, NB_OP_ACSC = 31,
+  NB_OP_ACOT = 32, NB_OP_ASINH = 33, NB_OP_ACOSH = 34, NB_OP_ATANH = 35, NB_OP_ASECH = 36,
+  NB_OP_ACSCH = 37, NB_OP_ACOTH = 38, NB_OP_SIND = 39, NB_OP_COSD = 40, NB_OP_TAND = 41,
+  NB_OP_SECD = 42, NB_OP_CSCD = 43, NB_OP_COTD = 44, NB_OP_ASIND = 45, NB_OP_ACOSD = 46,
+  NB_OP_ATAND = 47, NB_OP_ASECD = 48, NB_OP_ACSCD = 49, NB_OP_ACOTD = 50, NB_OP_SINPI = 51,
+  NB_OP_COSPI = 52, NB_OP_DEG2RAD = 53, NB_OP_RAD2DEG = 54,
+  NB_OP_LOGISTIC = 55,  /* 1/(1+exp(-x)): examples/mlp.jl:42, examples/vae.jl:32, fused */
+  NB_OP_ERF = 56, NB_OP_ERFC = 57,
+  NB_OP_UNARY_END = 58,
+  /* binary */
+  NB_OP_ADD = 64, NB_OP_SUB = 65, NB_OP_MUL = 66, NB_OP_DIV = 67,
+  NB_OP_LDIV = 68,      /* x \ y == y / x */
+  NB_OP_POW = 69, NB_OP_HYPOT = 70, NB_OP_MAX = 71, NB_OP_MIN = 72,
+  NB_OP_ATAN2 = 73,     /* atan(y_, x_) with operand a = y_, b = x_ */
+  NB_OP_BINARY_END = 74
+} nb_op;
+
+typedef struct nb_stats {
+  uint64_t kernel_launches;   /* kernels of this library launched on the ctx stream */
+  uint64_t pool_bytes_in_use;
+  uint64_t pool_bytes_reserved;
+  uint64_t pool_high_water;
+  uint64_t cuda_mallocs;      /* pool misses that went to the driver */
+  uint64_t h2d_bytes, d2h_bytes;
+} nb_stats;
+
+/* ---- library / context --------------------------------------------------------------------- */
+int32_t nb_abi_version(void);
+/* Message of the last failing call on this ctx (ctx may be NULL for create failures). */
+const char* nb_last_error(nb_ctx* ctx);
+/* Replaces Julia's GC-owned `Array` storage + implicit single thread: owns one CUDA stream and a
+ * pooled, stream-ordered allocator (pool_bytes is pre-reserved; the pool grows on demand). */
+int32_t nb_ctx_create(int32_t device, uint64_t pool_bytes, nb_ctx** out);
+int32_t nb_ctx_destroy(nb_ctx* ctx);
+/* One reverse sweep == one stream epoch (src/core.jl:160-166, 200).  begin/end are cheap markers;
+ * end synchronises the stream so results may be read by the host. */
+int32_t nb_sweep_begin(nb_ctx* ctx);
+int32_t nb_sweep_end(nb_ctx* ctx);
+int32_t nb_sync(nb_ctx* ctx);
+int32_t nb_ctx_stream(nb_ctx* ctx, void** cuda_stream_out);
+int32_t nb_ctx_stats(nb_ctx* ctx, nb_stats* out);
+int32_t nb_device_count(int32_t* out);
+
+/* ---- buffers (replace Array allocation: functional.jl:62,77,85) ---------------------------- */
+int32_t nb_alloc(nb_ctx* ctx, uint64_t nbytes, void** out);
+int32_t nb_retain(nb_ctx* ctx, void* buf);
+int32_t nb_release(nb_ctx* ctx, void* buf);  /* safe from a GC finalizer thread */
+int32_t nb_refcount(nb_ctx* ctx, void* buf, int32_t* out);
+int32_t nb_h2d(nb_ctx* ctx, void* dst_dev, const void* src_host, uint64_t nbytes);
+int32_t nb_d2h(nb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t nbytes); /* syncs */
+int32_t nb_d2h_async(nb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t nbytes);
+int32_t nb_d2d(nb_ctx* ctx, void* dst_dev, const void* src_dev, uint64_t nbytes);
+int32_t nb_fill(nb_ctx* ctx, void* dst_dev, int32_t dtype, uint64_t count, double value);
+int32_t nb_host_alloc(uint64_t nbytes, void** out); /* pinned host memory */
+int32_t nb_host_free(void* p);
+
+/* ---- scalar programs (replace "any Julia scalar function under ForwardDiff duals",
+ *      src/core.jl:285-301).  Value slots: 0..nargs-1 are the operands, nargs+i is the result of
+ *      instruction i; a negative operand index -(c+1) names consts[c].  The program's value is the
+ *      last instruction's result (or operand 0 when n_instr == 0). */
+int32_t nb_prog_create(int32_t nargs, int32_t n_instr, const int32_t* ops, const int32_t* a,
+                       const int32_t* b, int32_t n_consts, const double* consts, nb_prog** out);
+int32_t nb_prog_destroy(nb_prog* prog);
+
+/* ---- family (1): broadcast forward / pullback fused with unbroadcast ----------------------- */
+/* out = f.(args...)   — primal of Branch(broadcast, (f, args...)): functional.jl:48-51, core.jl:89 */
+int32_t nb_bcast_fwd(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const nb_tensor* args,
+                     const nb_tensor* out);
+/* For every k in want_mask:  outs[k] (+)= unbroadcast_to(shape(outs[k]), ybar .* df/dx_k(args...))
+ * — replaces ∇(broadcast, Arg{N}, ...) -> broadcastsum/broadcastsum! (functional.jl:59-95), one
+ * fused pass for all wanted operands instead of one pass per operand (core.jl:149-156); bit k of
+ * accumulate_mask fuses the `add!!` of core.jl:203-205.  `ybar` may itself be broadcast (e.g. the
+ * scalar seed of `sum`).  `y_saved` (nullable) is the Branch's forward value (core.jl:76): used
+ * instead of re-evaluating f where df/dx is a function of y (tanh, exp, logistic, sqrt, ...). */
+int32_t nb_bcast_pullback(nb_ctx* ctx, const nb_prog* prog, const nb_tensor* ybar,
+                          const nb_tensor* y_saved, int32_t nargs, const nb_tensor* args,
+                          uint32_t want_mask, const nb_tensor* outs, uint32_t accumulate_mask);
+
+/* ---- family (2): reductions ----------------------------------------------------------------- */
+/* out (+)= scale * sum over the dims where `out` has extent 1 of f.(args...)
+ * — replaces sum / sum(f, .) / sum(abs2, .) / mean / mapreduce(f, +, .; dims) / dot forward
+ * (functional/reducedim.jl:4-72, functional/reduce.jl:4-12, ChainRules sum/mean/dot) and
+ * broadcastsum! itself (functional.jl:59-69).  prog == NULL means identity on args[0]. */
+int32_t nb_bcast_reduce(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const nb_tensor* args,
+                        double scale, const nb_tensor* out, int32_t accumulate);
+
+/* ---- family (3): dense linalg (BLAS column-major semantics) -------------------------------- */
+/* C = alpha*op(A)*op(B) + beta*C — replaces `*` and BLAS.gemm forward and the adjoints
+ * Abar = Ybar*B' ('N','T'), Bbar = A'*Ybar ('T','N') of ChainRules rrule(*) reached through
+ * src/sensitivities/chainrules.jl:179-191,286 and src/sensitivities/linalg/blas.jl:224-228;
+ * beta == 1 is the in-place accumulate (InplaceableThunk mul!(X, Y, B', true, true)). */
+int32_t nb_gemm(nb_ctx* ctx, char tA, char tB, int64_t m, int64_t n, int64_t k, double alpha,
+                const void* A, int64_t lda, const void* B, int64_t ldb, double beta, void* C,
+                int64_t ldc, int32_t dtype, int32_t math_mode);
+/* y = alpha*op(A)*x + beta*y   (A is m x n) — matrix*vector and BLAS.gemv (blas.jl tests :49-61) */
+int32_t nb_gemv(nb_ctx* ctx, char tA, int64_t m, int64_t n, double alpha, const void* A,
+                int64_t lda, const void* x, double beta, void* y, int32_t dtype);
+/* A = alpha*x*y' + beta*A  (A is m x n) — the outer-product adjoint of matrix*vector */
+int32_t nb_ger(nb_ctx* ctx, int64_t m, int64_t n, double alpha, const void* x, const void* y,
+               double beta, void* A, int64_t lda, int32_t dtype);
+/* out(n x m) = in(m x n)' — materialised adjoint/transpose (ChainRules rrule(adjoint)) */
+int32_t nb_transpose(nb_ctx* ctx, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
+                     int64_t ld_out, int32_t dtype);
+
+/* ---- batch-sharded gradients (new capability) ----------------------------- */
+int32_t nb_comm_unique_id(uint8_t id_out[128]);
+int32_t nb_comm_init(nb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id[128]);
+/* In-place sum of each buffer over all ranks (one grouped NCCL launch on the ctx stream). */
+int32_t nb_allreduce_sum(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const int64_t* counts,
+                         int32_t dtype);
+int32_t nb_comm_destroy(nb_ctx* ctx);
+
+/* ---- CUDA-graph capture of a whole forward + reverse sweep --------------------------------- */
+int32_t nb_graph_begin(nb_ctx* ctx);
+int32_t nb_graph_end(nb_ctx* ctx, nb_graph** out);
+int32_t nb_graph_launch(nb_ctx* ctx, nb_graph* g);
+int32_t nb_graph_destroy(nb_graph* g);
+
+/* ---- device timing on the ctx stream -------------------------------------------------------- */
+int32_t nb_event_create(void** out);
+int32_t nb_event_record(nb_ctx* ctx, void* ev);
+int32_t nb_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms_out); /* syncs ev_stop */
+int32_t nb_event_destroy(void* ev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NABLA_CUDA_H */

@@ -1,0 +1,86 @@
+// Shared internals of libnabla_cuda.so: context, pooled stream-ordered allocator, error plumbing.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nabla_cuda.h"
+
+#define NB_NUM_SMS_DEFAULT 148
+
+struct nb_block {
+  size_t size;  // size class actually allocated
+  int refs;
+};
+
+struct nb_ctx {
+  int device = 0;
+  int num_sms = NB_NUM_SMS_DEFAULT;
+  cudaStream_t stream = nullptr;
+  std::mutex mu;  // guards the pool maps (nb_release may come from a GC finalizer thread)
+  std::unordered_map<void*, nb_block> live;
+  std::map<size_t, std::vector<void*>> free_bins;
+  size_t free_bytes = 0;
+  size_t max_cached = 0;  // 0 = unlimited
+  nb_stats stats{};
+  std::string err;
+  bool capturing = false;
+  // communicator (comm.cu)
+  void* nccl_comm = nullptr;
+  int nranks = 1, rank = 0;
+  // tcgen05 GEMM staging (gemm_tf32.cu)
+  void* gemm_state = nullptr;
+};
+
+struct nb_graph {
+  cudaGraph_t graph = nullptr;
+  cudaGraphExec_t exec = nullptr;
+  uint64_t launches_per_replay = 0;
+};
+
+extern thread_local std::string nb_tls_error;
+
+static inline int32_t nb_fail(nb_ctx* ctx, int32_t code, const std::string& msg) {
+  if (ctx) ctx->err = msg;
+  nb_tls_error = msg;
+  return code;
+}
+
+#define NB_CUDA_OK(ctx, expr)                                                            \
+  do {                                                                                   \
+    cudaError_t _e = (expr);                                                             \
+    if (_e != cudaSuccess) {                                                             \
+      return nb_fail((ctx), NB_ERR_CUDA,                                                 \
+                     std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" __FILE__ \
+                         ":" + std::to_string(__LINE__) + ")");                          \
+    }                                                                                    \
+  } while (0)
+
+#define NB_REQUIRE(ctx, cond, code, msg)                 \
+  do {                                                   \
+    if (!(cond)) return nb_fail((ctx), (code), (msg));   \
+  } while (0)
+
+#define NB_LAUNCH_CHECK(ctx)                    \
+  do {                                          \
+    (ctx)->stats.kernel_launches++;             \
+    NB_CUDA_OK((ctx), cudaGetLastError());      \
+  } while (0)
+
+static inline size_t nb_dtype_size(int32_t dt) { return dt == NB_F64 ? 8 : 4; }
+
+// internal allocator entry points (ctx.cu)
+int32_t nb_pool_alloc(nb_ctx* ctx, size_t nbytes, void** out);
+int32_t nb_pool_release(nb_ctx* ctx, void* p);
+
+static inline int64_t nb_numel(const nb_tensor* t) {
+  int64_t n = 1;
+  for (int d = 0; d < t->ndim; ++d) n *= t->shape[d];
+  return n;
+}

@@ -1,0 +1,320 @@
+// Device-side scalar catalogue: values and DiffRules/ChainRules partial derivatives of every
+// nb_op, plus the program interpreter used for composite scalar functions.
+//
+// Replaces `fmad(f, x, Val{N})` (src/core.jl:285-292): the reference evaluates f on a
+// ForwardDiff.Dual per element; here single-primitive programs use the analytic partial directly
+// (same formula DiffRules would apply), and composite programs are differentiated by an exact
+// reverse accumulation over the program DAG (same derivative, one pass for all operands).
+#pragma once
+#include "common.cuh"
+
+struct nb_prog {
+  int32_t nargs;
+  int32_t n_instr;
+  int32_t n_consts;
+  int32_t op[NB_MAX_INSTR];
+  int32_t a[NB_MAX_INSTR];
+  int32_t b[NB_MAX_INSTR];
+  double consts[NB_MAX_CONSTS];
+};
+
+#define NB_PI 3.14159265358979323846
+#define NB_D2R (NB_PI / 180.0)
+#define NB_R2D (180.0 / NB_PI)
+#define NB_LN2 0.69314718055994530942
+#define NB_LN10 2.30258509299404568402
+#define NB_2_SQRTPI 1.12837916709551257390
+
+__host__ __device__ inline bool nb_op_is_unary(int op) { return op >= 0 && op < NB_OP_UNARY_END; }
+__host__ __device__ inline bool nb_op_is_binary(int op) {
+  return op >= NB_OP_ADD && op < NB_OP_BINARY_END;
+}
+
+// Which inputs does the partial derivative need?  bit0: operand a, bit1: operand b, bit2: y.
+// (for d/da of a unary op; binary ops report the union over both partials — refined on the host
+//  per wanted operand by nb_partial_needs)
+__host__ __device__ inline int nb_partial_needs(int op, int wrt /*0=a,1=b*/) {
+  const int A = 1, B = 2, Y = 4;
+  switch (op) {
+    case NB_OP_IDENTITY: case NB_OP_NEG: case NB_OP_DEG2RAD: case NB_OP_RAD2DEG: return 0;
+    case NB_OP_TANH: case NB_OP_EXP: case NB_OP_LOGISTIC: case NB_OP_SQRT: case NB_OP_INV:
+    case NB_OP_TAN: case NB_OP_EXP2: case NB_OP_EXP10: case NB_OP_CBRT: case NB_OP_COT:
+    case NB_OP_COTH: case NB_OP_TAND: case NB_OP_COTD: case NB_OP_EXPM1:
+      return Y;
+    case NB_OP_SEC: case NB_OP_CSC: case NB_OP_SECH: case NB_OP_CSCH: case NB_OP_SECD:
+    case NB_OP_CSCD:
+      return A | Y;
+    case NB_OP_ADD: case NB_OP_SUB: return 0;
+    case NB_OP_MUL: return wrt == 0 ? B : A;
+    case NB_OP_DIV: return wrt == 0 ? B : (B | Y);   // 1/b ; -y/b
+    case NB_OP_LDIV: return wrt == 0 ? (A | Y) : A;  // -y/a ; 1/a
+    case NB_OP_POW: return wrt == 0 ? (A | B) : (A | Y);
+    case NB_OP_HYPOT: return wrt == 0 ? (A | Y) : (B | Y);
+    case NB_OP_MAX: case NB_OP_MIN: case NB_OP_ATAN2: return A | B;
+    default: return A;  // unary ops whose partial is a function of x
+  }
+}
+
+template <typename T> __device__ __forceinline__ T nb_sinpi(T x);
+template <> __device__ __forceinline__ float nb_sinpi<float>(float x) { return sinpif(x); }
+template <> __device__ __forceinline__ double nb_sinpi<double>(double x) { return sinpi(x); }
+template <typename T> __device__ __forceinline__ T nb_cospi(T x);
+template <> __device__ __forceinline__ float nb_cospi<float>(float x) { return cospif(x); }
+template <> __device__ __forceinline__ double nb_cospi<double>(double x) { return cospi(x); }
+template <typename T> __device__ __forceinline__ T nb_exp10(T x);
+template <> __device__ __forceinline__ float nb_exp10<float>(float x) { return exp10f(x); }
+template <> __device__ __forceinline__ double nb_exp10<double>(double x) { return exp10(x); }
+template <typename T> __device__ __forceinline__ T nb_rsqrt(T x);
+template <> __device__ __forceinline__ float nb_rsqrt<float>(float x) { return 1.0f / sqrtf(x); }
+template <> __device__ __forceinline__ double nb_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
+
+// value of a catalogue op (full table; out-of-line so the hot kernels stay small)
+template <typename T>
+__device__ __noinline__ T nb_eval_cold(int op, T a, T b) {
+  const T one = T(1);
+  const T d2r = T(NB_D2R), r2d = T(NB_R2D);
+  switch (op) {
+    case NB_OP_IDENTITY: return a;
+    case NB_OP_NEG: return -a;
+    case NB_OP_ABS: return fabs(a);
+    case NB_OP_ABS2: return a * a;
+    case NB_OP_SQRT: return sqrt(a);
+    case NB_OP_CBRT: return cbrt(a);
+    case NB_OP_INV: return one / a;
+    case NB_OP_EXP: return exp(a);
+    case NB_OP_EXP2: return exp2(a);
+    case NB_OP_EXP10: return nb_exp10<T>(a);
+    case NB_OP_EXPM1: return expm1(a);
+    case NB_OP_LOG: return log(a);
+    case NB_OP_LOG2: return log2(a);
+    case NB_OP_LOG10: return log10(a);
+    case NB_OP_LOG1P: return log1p(a);
+    case NB_OP_SIN: return sin(a);
+    case NB_OP_COS: return cos(a);
+    case NB_OP_TAN: return tan(a);
+    case NB_OP_SEC: return one / cos(a);
+    case NB_OP_CSC: return one / sin(a);
+    case NB_OP_COT: return one / tan(a);
+    case NB_OP_SINH: return sinh(a);
+    case NB_OP_COSH: return cosh(a);
+    case NB_OP_TANH: return tanh(a);
+    case NB_OP_SECH: return one / cosh(a);
+    case NB_OP_CSCH: return one / sinh(a);
+    case NB_OP_COTH: return one / tanh(a);
+    case NB_OP_ASIN: return asin(a);
+    case NB_OP_ACOS: return acos(a);
+    case NB_OP_ATAN: return atan(a);
+    case NB_OP_ASEC: return acos(one / a);
+    case NB_OP_ACSC: return asin(one / a);
+    case NB_OP_ACOT: return atan(one / a);
+    case NB_OP_ASINH: return asinh(a);
+    case NB_OP_ACOSH: return acosh(a);
+    case NB_OP_ATANH: return atanh(a);
+    case NB_OP_ASECH: return acosh(one / a);
+    case NB_OP_ACSCH: return asinh(one / a);
+    case NB_OP_ACOTH: return atanh(one / a);
+    case NB_OP_SIND: return sin(d2r * a);
+    case NB_OP_COSD: return cos(d2r * a);
+    case NB_OP_TAND: return tan(d2r * a);
+    case NB_OP_SECD: return one / cos(d2r * a);
+    case NB_OP_CSCD: return one / sin(d2r * a);
+    case NB_OP_COTD: return one / tan(d2r * a);
+    case NB_OP_ASIND: return r2d * asin(a);
+    case NB_OP_ACOSD: return r2d * acos(a);
+    case NB_OP_ATAND: return r2d * atan(a);
+    case NB_OP_ASECD: return r2d * acos(one / a);
+    case NB_OP_ACSCD: return r2d * asin(one / a);
+    case NB_OP_ACOTD: return r2d * atan(one / a);
+    case NB_OP_SINPI: return nb_sinpi<T>(a);
+    case NB_OP_COSPI: return nb_cospi<T>(a);
+    case NB_OP_DEG2RAD: return d2r * a;
+    case NB_OP_RAD2DEG: return r2d * a;
+    case NB_OP_LOGISTIC: return one / (one + exp(-a));
+    case NB_OP_ERF: return erf(a);
+    case NB_OP_ERFC: return erfc(a);
+    case NB_OP_ADD: return a + b;
+    case NB_OP_SUB: return a - b;
+    case NB_OP_MUL: return a * b;
+    case NB_OP_DIV: return a / b;
+    case NB_OP_LDIV: return b / a;
+    case NB_OP_POW: return pow(a, b);
+    case NB_OP_HYPOT: return hypot(a, b);
+    case NB_OP_MAX: return fmax(a, b);
+    case NB_OP_MIN: return fmin(a, b);
+    case NB_OP_ATAN2: return atan2(a, b);
+    default: return a;
+  }
+}
+
+// d/da of a unary op; y is f(a) (valid only if nb_partial_needs says Y)
+template <typename T>
+__device__ __noinline__ T nb_dunary_cold(int op, T a, T y) {
+  const T one = T(1);
+  const T d2r = T(NB_D2R), r2d = T(NB_R2D);
+  switch (op) {
+    case NB_OP_IDENTITY: return one;
+    case NB_OP_NEG: return -one;
+    case NB_OP_ABS: return a > T(0) ? one : (a < T(0) ? -one : T(0));
+    case NB_OP_ABS2: return T(2) * a;
+    case NB_OP_SQRT: return T(0.5) / y;
+    case NB_OP_CBRT: return one / (T(3) * y * y);
+    case NB_OP_INV: return -(y * y);
+    case NB_OP_EXP: return y;
+    case NB_OP_EXP2: return T(NB_LN2) * y;
+    case NB_OP_EXP10: return T(NB_LN10) * y;
+    case NB_OP_EXPM1: return y + one;
+    case NB_OP_LOG: return one / a;
+    case NB_OP_LOG2: return one / (a * T(NB_LN2));
+    case NB_OP_LOG10: return one / (a * T(NB_LN10));
+    case NB_OP_LOG1P: return one / (one + a);
+    case NB_OP_SIN: return cos(a);
+    case NB_OP_COS: return -sin(a);
+    case NB_OP_TAN: return one + y * y;
+    case NB_OP_SEC: return y * tan(a);
+    case NB_OP_CSC: return -y / tan(a);
+    case NB_OP_COT: return -(one + y * y);
+    case NB_OP_SINH: return cosh(a);
+    case NB_OP_COSH: return sinh(a);
+    case NB_OP_TANH: return one - y * y;
+    case NB_OP_SECH: return -tanh(a) * y;
+    case NB_OP_CSCH: return -y / tanh(a);
+    case NB_OP_COTH: return one - y * y;
+    case NB_OP_ASIN: return nb_rsqrt<T>(one - a * a);
+    case NB_OP_ACOS: return -nb_rsqrt<T>(one - a * a);
+    case NB_OP_ATAN: return one / (one + a * a);
+    case NB_OP_ASEC: return one / (fabs(a) * sqrt(a * a - one));
+    case NB_OP_ACSC: return -one / (fabs(a) * sqrt(a * a - one));
+    case NB_OP_ACOT: return -one / (one + a * a);
+    case NB_OP_ASINH: return nb_rsqrt<T>(a * a + one);
+    case NB_OP_ACOSH: return nb_rsqrt<T>(a * a - one);
+    case NB_OP_ATANH: return one / (one - a * a);
+    case NB_OP_ASECH: return -one / (a * sqrt(one - a * a));
+    case NB_OP_ACSCH: return -one / (fabs(a) * sqrt(one + a * a));
+    case NB_OP_ACOTH: return one / (one - a * a);
+    case NB_OP_SIND: return d2r * cos(d2r * a);
+    case NB_OP_COSD: return -d2r * sin(d2r * a);
+    case NB_OP_TAND: return d2r * (one + y * y);
+    case NB_OP_SECD: return d2r * y * tan(d2r * a);
+    case NB_OP_CSCD: return -d2r * y / tan(d2r * a);
+    case NB_OP_COTD: return -d2r * (one + y * y);
+    case NB_OP_ASIND: return r2d * nb_rsqrt<T>(one - a * a);
+    case NB_OP_ACOSD: return -r2d * nb_rsqrt<T>(one - a * a);
+    case NB_OP_ATAND: return r2d / (one + a * a);
+    case NB_OP_ASECD: return r2d / (fabs(a) * sqrt(a * a - one));
+    case NB_OP_ACSCD: return -r2d / (fabs(a) * sqrt(a * a - one));
+    case NB_OP_ACOTD: return -r2d / (one + a * a);
+    case NB_OP_SINPI: return T(NB_PI) * nb_cospi<T>(a);
+    case NB_OP_COSPI: return -T(NB_PI) * nb_sinpi<T>(a);
+    case NB_OP_DEG2RAD: return d2r;
+    case NB_OP_RAD2DEG: return r2d;
+    case NB_OP_LOGISTIC: return y * (one - y);
+    case NB_OP_ERF: return T(NB_2_SQRTPI) * exp(-a * a);
+    case NB_OP_ERFC: return -T(NB_2_SQRTPI) * exp(-a * a);
+    default: return T(0);
+  }
+}
+
+
+// Hot ops are inlined into the kernels; the long tail of the catalogue goes through one call.
+template <typename T>
+__device__ __forceinline__ T nb_eval(int op, T a, T b) {
+  switch (op) {
+    case NB_OP_IDENTITY: return a;
+    case NB_OP_NEG: return -a;
+    case NB_OP_ABS2: return a * a;
+    case NB_OP_SQRT: return sqrt(a);
+    case NB_OP_INV: return T(1) / a;
+    case NB_OP_EXP: return exp(a);
+    case NB_OP_LOG: return log(a);
+    case NB_OP_TANH: return tanh(a);
+    case NB_OP_LOGISTIC: return T(1) / (T(1) + exp(-a));
+    case NB_OP_ADD: return a + b;
+    case NB_OP_SUB: return a - b;
+    case NB_OP_MUL: return a * b;
+    case NB_OP_DIV: return a / b;
+    default: return nb_eval_cold<T>(op, a, b);
+  }
+}
+
+template <typename T>
+__device__ __forceinline__ T nb_dunary(int op, T a, T y) {
+  switch (op) {
+    case NB_OP_IDENTITY: return T(1);
+    case NB_OP_NEG: return T(-1);
+    case NB_OP_ABS2: return T(2) * a;
+    case NB_OP_SQRT: return T(0.5) / y;
+    case NB_OP_INV: return -(y * y);
+    case NB_OP_EXP: return y;
+    case NB_OP_LOG: return T(1) / a;
+    case NB_OP_TANH: return T(1) - y * y;
+    case NB_OP_LOGISTIC: return y * (T(1) - y);
+    default: return nb_dunary_cold<T>(op, a, y);
+  }
+}
+
+// d/da (wrt == 0) or d/db (wrt == 1) of a binary op
+template <typename T>
+__device__ __forceinline__ T nb_dbinary(int op, int wrt, T a, T b, T y) {
+  const T one = T(1);
+  switch (op) {
+    case NB_OP_ADD: return one;
+    case NB_OP_SUB: return wrt == 0 ? one : -one;
+    case NB_OP_MUL: return wrt == 0 ? b : a;
+    case NB_OP_DIV: return wrt == 0 ? one / b : -y / b;
+    case NB_OP_LDIV: return wrt == 0 ? -y / a : one / a;
+    case NB_OP_POW: return wrt == 0 ? b * pow(a, b - one) : y * log(a);
+    case NB_OP_HYPOT: return wrt == 0 ? a / y : b / y;
+    case NB_OP_MAX: return wrt == 0 ? (a > b ? one : T(0)) : (a > b ? T(0) : one);
+    case NB_OP_MIN: return wrt == 0 ? (a < b ? one : T(0)) : (a < b ? T(0) : one);
+    case NB_OP_ATAN2: {
+      T den = a * a + b * b;
+      return wrt == 0 ? b / den : -a / den;
+    }
+    default: return T(0);
+  }
+}
+
+// ---- composite programs ---------------------------------------------------------------------
+#define NB_MAX_SLOTS (NB_MAX_ARGS + NB_MAX_INSTR)
+
+template <typename T>
+__device__ __forceinline__ T nb_slot(const nb_prog& P, const T* vals, int idx) {
+  return idx >= 0 ? vals[idx] : T(P.consts[-idx - 1]);
+}
+
+// forward evaluation: vals[0..nargs) must hold the operands; returns the program value
+template <typename T>
+__device__ __forceinline__ T nb_prog_eval(const nb_prog& P, T* vals) {
+  for (int i = 0; i < P.n_instr; ++i) {
+    T a = nb_slot<T>(P, vals, P.a[i]);
+    T b = nb_op_is_binary(P.op[i]) ? nb_slot<T>(P, vals, P.b[i]) : T(0);
+    vals[P.nargs + i] = nb_eval<T>(P.op[i], a, b);
+  }
+  return P.n_instr ? vals[P.nargs + P.n_instr - 1] : vals[0];
+}
+
+// reverse accumulation: adj[] receives d(program value)/d(slot); vals must be fully evaluated
+template <typename T>
+__device__ __forceinline__ void nb_prog_grad(const nb_prog& P, const T* vals, T* adj) {
+  const int nslots = P.nargs + P.n_instr;
+  for (int s = 0; s < nslots; ++s) adj[s] = T(0);
+  if (P.n_instr == 0) {
+    adj[0] = T(1);
+    return;
+  }
+  adj[nslots - 1] = T(1);
+  for (int i = P.n_instr - 1; i >= 0; --i) {
+    T g = adj[P.nargs + i];
+    if (g == T(0)) continue;
+    int op = P.op[i];
+    T y = vals[P.nargs + i];
+    T a = nb_slot<T>(P, vals, P.a[i]);
+    if (nb_op_is_binary(op)) {
+      T b = nb_slot<T>(P, vals, P.b[i]);
+      if (P.a[i] >= 0) adj[P.a[i]] += g * nb_dbinary<T>(op, 0, a, b, y);
+      if (P.b[i] >= 0) adj[P.b[i]] += g * nb_dbinary<T>(op, 1, a, b, y);
+    } else {
+      if (P.a[i] >= 0) adj[P.a[i]] += g * nb_dunary<T>(op, a, y);
+    }
+  }
+}

@@ -1,0 +1,254 @@
+"""Device context and column-major device arrays (the `DevArray <: AbstractArray` of the Julia glue).
+
+A ``Context`` wraps one ``nb_ctx``: one CUDA stream plus the pooled stream-ordered allocator that
+replaces Julia's GC-managed ``Array`` storage (reference: src/core.jl:76,89 keeps every Branch value
+alive on the tape; sensitivities are allocated at functional.jl:62,77,85)."""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _lib
+from ._lib import NB_F32, NB_F64, NB_MAX_DIMS, check, nb_tensor
+
+_DT = {np.dtype(np.float32): NB_F32, np.dtype(np.float64): NB_F64}
+_NP = {NB_F32: np.dtype(np.float32), NB_F64: np.dtype(np.float64)}
+
+
+class Context:
+    def __init__(self, device=None, pool_bytes=0):
+        L = _lib.lib()
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0"))
+        h = C.c_void_p()
+        check(L.nb_ctx_create(device, pool_bytes, C.byref(h)))
+        self.h = h
+        self.device = device
+        self.L = L
+        self.math_mode = _lib.MATH_DEFAULT
+        self._progs = {}
+        self.nranks, self.rank = 1, 0
+
+    def close(self):
+        if self.h:
+            for p in self._progs.values():
+                self.L.nb_prog_destroy(p)
+            self._progs.clear()
+            self.L.nb_ctx_destroy(self.h)
+            self.h = None
+
+    def sync(self):
+        check(self.L.nb_sync(self.h), self.h)
+
+    def stats(self):
+        s = _lib.nb_stats()
+        check(self.L.nb_ctx_stats(self.h, C.byref(s)), self.h)
+        return {k: int(getattr(s, k)) for k, _ in s._fields_}
+
+    def stream_ptr(self):
+        p = C.c_void_p()
+        check(self.L.nb_ctx_stream(self.h, C.byref(p)), self.h)
+        return p.value
+
+    # -- events (CUDA-event timing on the ctx stream) --
+    def event(self):
+        e = C.c_void_p()
+        check(self.L.nb_event_create(C.byref(e)))
+        return e
+
+    def record(self, ev):
+        check(self.L.nb_event_record(self.h, ev), self.h)
+
+    def elapsed_ms(self, a, b):
+        ms = C.c_float()
+        check(self.L.nb_event_elapsed_ms(a, b, C.byref(ms)))
+        return ms.value
+
+    # -- arrays --
+    def empty(self, shape, dtype):
+        return DevArray(self, tuple(int(s) for s in shape), np.dtype(dtype))
+
+    def full(self, shape, value, dtype):
+        a = self.empty(shape, dtype)
+        check(self.L.nb_fill(self.h, a.ptr, a.nb_dtype, a.size, float(value)), self.h)
+        return a
+
+    def zeros(self, shape, dtype):
+        return self.full(shape, 0.0, dtype)
+
+    def ones(self, shape, dtype):
+        return self.full(shape, 1.0, dtype)
+
+    def scalar(self, value, dtype):
+        return self.full((), value, dtype)
+
+    def asarray(self, x, dtype=None):
+        """Host -> device (column-major).  DevArrays pass through."""
+        if isinstance(x, DevArray):
+            return x
+        a = np.asarray(x)
+        if dtype is not None:
+            a = a.astype(dtype, copy=False)
+        elif a.dtype not in _DT:
+            a = a.astype(np.float64)
+        out = self.empty(a.shape, a.dtype)
+        out.copy_from_host(a)
+        return out
+
+
+_default = None
+
+
+def get_context():
+    """Process-wide default context (device = LOCAL_RANK or 0).  Raises if no GPU is present."""
+    global _default
+    if _default is None:
+        _default = Context()
+    return _default
+
+
+def set_context(ctx):
+    global _default
+    _default = ctx
+
+
+class DevArray:
+    """Dense column-major array in HBM, ``ndim <= 4`` (``ndim == 0`` is a device scalar).
+
+    ``shared`` marks a buffer that is (or may be) referenced from more than one reverse-tape slot,
+    e.g. when a rule returns ȳ itself; the accumulate path copies instead of mutating it
+    (SURVEY.md §7 hard part 5; reference pin: test/core.jl:211-224)."""
+
+    __slots__ = ("ctx", "ptr", "shape", "dtype", "shared", "adjvec", "_base", "__weakref__")
+    __array_priority__ = 3000.0
+
+    def __init__(self, ctx, shape, dtype, ptr=None, base=None):
+        if len(shape) > NB_MAX_DIMS:
+            raise ValueError(f"DevArray supports at most {NB_MAX_DIMS} dimensions, got {shape}")
+        if np.dtype(dtype) not in _DT:
+            raise TypeError(f"DevArray eltype must be Float32 or Float64, got {dtype}")
+        self.ctx = ctx
+        self.shape = tuple(shape)
+        self.dtype = np.dtype(dtype)
+        self.shared = False
+        self.adjvec = False
+        self._base = base
+        if ptr is None:
+            p = C.c_void_p()
+            check(ctx.L.nb_alloc(ctx.h, max(self.nbytes, 1), C.byref(p)), ctx.h)
+            self.ptr = p.value
+        else:
+            self.ptr = ptr
+
+    def __del__(self):
+        try:
+            if self._base is None and self.ptr and self.ctx.h:
+                self.ctx.L.nb_release(self.ctx.h, self.ptr)
+        except Exception:
+            pass
+
+    # -- metadata --
+    @property
+    def ndim(self):
+        return len(self.shape)
+
+    @property
+    def size(self):
+        n = 1
+        for s in self.shape:
+            n *= s
+        return n
+
+    @property
+    def nbytes(self):
+        return self.size * self.dtype.itemsize
+
+    @property
+    def nb_dtype(self):
+        return _DT[self.dtype]
+
+    def tensor(self, shape=None):
+        t = nb_tensor()
+        shp = self.shape if shape is None else shape
+        t.data = self.ptr
+        t.dtype = self.nb_dtype
+        t.ndim = len(shp)
+        for i in range(NB_MAX_DIMS):
+            t.shape[i] = shp[i] if i < len(shp) else 1
+        return t
+
+    def reshape(self, shape):
+        """Column-major reshape: a view on the same buffer (keeps it alive through ``_base``)."""
+        shape = tuple(int(s) for s in shape)
+        n = 1
+        for s in shape:
+            n *= s
+        if n != self.size:
+            raise ValueError(f"DimensionMismatch: cannot reshape {self.shape} to {shape}")
+        v = DevArray(self.ctx, shape, self.dtype, ptr=self.ptr, base=self._base or self)
+        v.shared = True
+        return v
+
+    # -- transfers --
+    def copy_from_host(self, a):
+        a = np.asfortranarray(a, dtype=self.dtype)
+        if a.shape != self.shape:
+            raise ValueError(f"DimensionMismatch: {a.shape} vs {self.shape}")
+        if self.nbytes:
+            # pageable source: the copy is complete (staged) when the call returns
+            check(self.ctx.L.nb_h2d(self.ctx.h, self.ptr, a.ctypes.data, self.nbytes), self.ctx.h)
+            self.ctx.sync()  # `a` may be a temporary: do not return before the DMA has read it
+        return self
+
+    def numpy(self):
+        out = np.empty(self.shape, dtype=self.dtype, order="F")
+        if self.nbytes:
+            check(self.ctx.L.nb_d2h(self.ctx.h, out.ctypes.data, self.ptr, self.nbytes), self.ctx.h)
+        if self.adjvec:
+            return out
+        return out if self.ndim else out[()]
+
+    def item(self):
+        return float(self.numpy())
+
+    def __float__(self):
+        return self.item()
+
+    def copy(self):
+        out = DevArray(self.ctx, self.shape, self.dtype)
+        check(self.ctx.L.nb_d2d(self.ctx.h, out.ptr, self.ptr, self.nbytes), self.ctx.h)
+        out.adjvec = self.adjvec
+        return out
+
+    def __repr__(self):
+        return f"DevArray{{{self.dtype.name}}}{self.shape}"
+
+
+class BroadcastView:
+    """A lazily broadcast sensitivity: ``base`` (a DevArray whose extents are 1 or full) viewed at
+    ``shape``.  This is the device analogue of the ``InplaceableThunk`` ChainRules returns from the
+    ``sum``/``mean`` rules (x̄ = broadcast(last∘tuple, x, ȳ)): it is only materialised if a consumer
+    cannot take a broadcast operand; the broadcast-pullback kernel reads it in place."""
+
+    __slots__ = ("base", "shape")
+
+    def __init__(self, base, shape):
+        self.base = base
+        self.shape = tuple(shape)
+
+    @property
+    def dtype(self):
+        return self.base.dtype
+
+    @property
+    def ctx(self):
+        return self.base.ctx
+
+    def materialize(self):
+        from .kernels import bcast_reduce
+        out = self.base.ctx.empty(self.shape, self.base.dtype)
+        bcast_reduce(None, [self.base], out)
+        return out
+
+    def numpy(self):
+        return self.materialize().numpy()
