@@ -10,12 +10,14 @@ test-only CPU restatement)."""
 from . import _lib
 from ._lib import (DimensionMismatch, NablaCudaError, UnsupportedOp, MATH_DEFAULT, MATH_TF32,
                    MATH_3XTF32, MATH_FP32)
-from .device import BroadcastView, Context, DevArray, get_context, set_context
+from .device import BroadcastView, Context, DevArray, PinnedArray, get_context, set_context
 from .core import (Arg, Branch, Leaf, Node, Primitive, Tape, explicit_intercepts, grad, nabla,
                    oneslike, pos, propagate, reverse_tape, tape, unbox, unthunk, zeroslike, as_device)
 from .scalar import CATALOGUE, Program, ScalarFn, Sym, compile_scalar
 from .rules import (Ref, adjoint, broadcast, dot, gemm, gemv, ldivide, map_, mapfoldl, mapfoldr,
                     mapreduce, matmul, mean, sum, transpose)
+
+from .sweep import CapturedGradient, Communicator, ShardedGradient, shard_bounds
 
 for _n, _f in CATALOGUE.items():
     globals()[{"abs": "abs_", "max": "max_", "min": "min_", "pow": "pow_"}.get(_n, _n)] = _f

@@ -148,6 +148,8 @@ def as_device(x, ctx=None, dtype=None):
         return x
     ctx = ctx or get_context()
     if isinstance(x, numbers.Real):
+        if dtype is None and isinstance(x, np.floating) and x.dtype in (np.float32, np.float64):
+            dtype = x.dtype  # a Float32 scalar stays Float32 (Julia does not widen it either)
         return ctx.asarray(np.asarray(float(x), dtype=dtype or np.float64))
     return ctx.asarray(x, dtype)
 

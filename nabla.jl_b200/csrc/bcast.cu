@@ -730,7 +730,18 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
       NB_REQUIRE(ctx, ext_of(C.ysaved, d) == F[d], NB_ERR_SHAPE, "y_saved must have the full shape");
   int64_t total = 1;
   for (int d = 0; d < NB_MAX_DIMS; ++d) total *= F[d];
-  if (total == 0) return NB_OK;  // empty arrays: nothing to do
+  if (total == 0) {
+    // empty index space: element-wise outputs are empty too; a reduction over nothing is zero
+    // (Julia: sum(Float64[]) == 0.0), so non-accumulating reduced outputs are zero-filled
+    for (int k = 0; k < C.nout; ++k) {
+      const int64_t cnt = nb_numel(C.outs[k]);
+      if (cnt > 0 && !C.out_acc[k]) {
+        int32_t rc = nb_fill(ctx, C.outs[k]->data, dt, (uint64_t)cnt, 0.0);
+        if (rc != NB_OK) return rc;
+      }
+    }
+    return NB_OK;
+  }
 
   // collapse dims: merge neighbours whose presence pattern is identical for every participant
   const int np = (int)parts.size();

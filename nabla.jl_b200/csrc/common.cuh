@@ -17,6 +17,7 @@
 struct nb_block {
   size_t size;  // size class actually allocated
   int refs;
+  uint32_t tag;  // 0 = general pool; otherwise the id of the captured graph that owns the block
 };
 
 struct nb_ctx {
@@ -31,6 +32,13 @@ struct nb_ctx {
   nb_stats stats{};
   std::string err;
   bool capturing = false;
+  // Blocks handed out while a sweep is being captured into a CUDA graph are baked into the graph
+  // by address, so they must never serve anyone else while the graph lives: they are tagged with
+  // the graph id, recycled only inside that capture (cap_bins) and parked until nb_graph_destroy.
+  uint32_t cap_tag = 0, next_tag = 1;
+  uint64_t cap_launch_base = 0;
+  std::map<size_t, std::vector<void*>> cap_bins;
+  std::unordered_map<uint32_t, std::vector<std::pair<void*, size_t>>> parked;
   // communicator (comm.cu)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
@@ -42,6 +50,8 @@ struct nb_graph {
   cudaGraph_t graph = nullptr;
   cudaGraphExec_t exec = nullptr;
   uint64_t launches_per_replay = 0;
+  nb_ctx* ctx = nullptr;
+  uint32_t tag = 0;
 };
 
 extern thread_local std::string nb_tls_error;

@@ -32,27 +32,36 @@ int32_t nb_pool_alloc(nb_ctx* ctx, size_t nbytes, void** out) {
   size_t cls = size_class(nbytes ? nbytes : 1);
   std::lock_guard<std::mutex> lk(ctx->mu);
   void* p = nullptr;
-  auto it = ctx->free_bins.find(cls);
-  if (it != ctx->free_bins.end() && !it->second.empty()) {
-    p = it->second.back();
-    it->second.pop_back();
-    ctx->free_bytes -= cls;
-  } else {
-    cudaError_t e = cudaMalloc(&p, cls);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      trim_locked(ctx);
-      e = cudaMalloc(&p, cls);
+  if (ctx->cap_tag) {  // capture-private recycling first
+    auto ct = ctx->cap_bins.find(cls);
+    if (ct != ctx->cap_bins.end() && !ct->second.empty()) {
+      p = ct->second.back();
+      ct->second.pop_back();
     }
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return nb_fail(ctx, NB_ERR_OOM, "nb_alloc: out of device memory requesting " +
-                                          std::to_string(cls) + " bytes");
-    }
-    ctx->stats.cuda_mallocs++;
-    ctx->stats.pool_bytes_reserved += cls;
   }
-  ctx->live[p] = nb_block{cls, 1};
+  if (!p) {
+    auto it = ctx->free_bins.find(cls);
+    if (it != ctx->free_bins.end() && !it->second.empty()) {
+      p = it->second.back();
+      it->second.pop_back();
+      ctx->free_bytes -= cls;
+    } else {
+      cudaError_t e = cudaMalloc(&p, cls);
+      if (e != cudaSuccess && !ctx->cap_tag) {
+        cudaGetLastError();
+        trim_locked(ctx);
+        e = cudaMalloc(&p, cls);
+      }
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return nb_fail(ctx, NB_ERR_OOM, "nb_alloc: out of device memory requesting " +
+                                            std::to_string(cls) + " bytes");
+      }
+      ctx->stats.cuda_mallocs++;
+      ctx->stats.pool_bytes_reserved += cls;
+    }
+  }
+  ctx->live[p] = nb_block{cls, 1, ctx->cap_tag};
   ctx->stats.pool_bytes_in_use += cls;
   if (ctx->stats.pool_bytes_in_use > ctx->stats.pool_high_water)
     ctx->stats.pool_high_water = ctx->stats.pool_bytes_in_use;
@@ -65,9 +74,16 @@ int32_t nb_pool_release(nb_ctx* ctx, void* p) {
   auto it = ctx->live.find(p);
   if (it == ctx->live.end()) return nb_fail(ctx, NB_ERR_INVALID, "nb_release: unknown buffer");
   if (--it->second.refs > 0) return NB_OK;
-  size_t cls = it->second.size;
+  const size_t cls = it->second.size;
+  const uint32_t tag = it->second.tag;
   ctx->live.erase(it);
   ctx->stats.pool_bytes_in_use -= cls;
+  if (tag) {
+    if (tag == ctx->cap_tag) ctx->cap_bins[cls].push_back(p);   // reusable inside this capture
+    else if (ctx->parked.count(tag)) ctx->parked[tag].push_back({p, cls});  // graph still alive
+    else { ctx->free_bins[cls].push_back(p); ctx->free_bytes += cls; }
+    return NB_OK;
+  }
   ctx->free_bins[cls].push_back(p);
   ctx->free_bytes += cls;
   if (ctx->max_cached && ctx->free_bytes > ctx->max_cached && !ctx->capturing) {
@@ -139,6 +155,12 @@ int32_t nb_ctx_destroy(nb_ctx* ctx) {
     trim_locked(ctx);
     for (auto& kv : ctx->live) cudaFree(kv.first);
     ctx->live.clear();
+    for (auto& kv : ctx->parked)
+      for (auto& pr : kv.second) cudaFree(pr.first);
+    ctx->parked.clear();
+    for (auto& kv : ctx->cap_bins)
+      for (void* p : kv.second) cudaFree(p);
+    ctx->cap_bins.clear();
   }
   cudaStreamDestroy(ctx->stream);
   delete ctx;
@@ -245,25 +267,40 @@ int32_t nb_host_free(void* p) {
 int32_t nb_graph_begin(nb_ctx* ctx) {
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, !ctx->capturing, NB_ERR_INVALID, "nb_graph_begin: already capturing");
+  NB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
   NB_CUDA_OK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
+  std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->capturing = true;
-  ctx->stats.kernel_launches = 0;
+  ctx->cap_tag = ctx->next_tag++;
+  ctx->parked[ctx->cap_tag];
+  ctx->cap_launch_base = ctx->stats.kernel_launches;
   return NB_OK;
 }
 
 int32_t nb_graph_end(nb_ctx* ctx, nb_graph** out) {
   NB_REQUIRE(ctx, ctx && out, NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, ctx->capturing, NB_ERR_INVALID, "nb_graph_end: not capturing");
-  ctx->capturing = false;
+  uint32_t tag;
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    tag = ctx->cap_tag;
+    ctx->capturing = false;
+    ctx->cap_tag = 0;
+    auto& park = ctx->parked[tag];  // blocks recycled inside the capture stay with the graph
+    for (auto& kv : ctx->cap_bins)
+      for (void* p : kv.second) park.push_back({p, kv.first});
+    ctx->cap_bins.clear();
+  }
   cudaGraph_t g = nullptr;
   NB_CUDA_OK(ctx, cudaStreamEndCapture(ctx->stream, &g));
   nb_graph* ng = new nb_graph();
   ng->graph = g;
-  ng->launches_per_replay = ctx->stats.kernel_launches;
+  ng->ctx = ctx;
+  ng->tag = tag;
+  ng->launches_per_replay = ctx->stats.kernel_launches - ctx->cap_launch_base;
   cudaError_t e = cudaGraphInstantiate(&ng->exec, g, 0);
   if (e != cudaSuccess) {
-    cudaGraphDestroy(g);
-    delete ng;
+    nb_graph_destroy(ng);
     return nb_fail(ctx, NB_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
   }
   *out = ng;
@@ -279,6 +316,21 @@ int32_t nb_graph_launch(nb_ctx* ctx, nb_graph* g) {
 
 int32_t nb_graph_destroy(nb_graph* g) {
   if (!g) return NB_OK;
+  if (g->ctx) {  // hand the graph's blocks back to the general pool (after the stream drains)
+    nb_ctx* ctx = g->ctx;
+    cudaStreamSynchronize(ctx->stream);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->parked.find(g->tag);
+    if (it != ctx->parked.end()) {
+      for (auto& pr : it->second) {
+        ctx->free_bins[pr.second].push_back(pr.first);
+        ctx->free_bytes += pr.second;
+      }
+      ctx->parked.erase(it);
+    }
+    for (auto& kv : ctx->live)
+      if (kv.second.tag == g->tag) kv.second.tag = 0;  // still referenced: becomes a normal block
+  }
   if (g->exec) cudaGraphExecDestroy(g->exec);
   if (g->graph) cudaGraphDestroy(g->graph);
   delete g;

@@ -64,6 +64,29 @@ class Context:
         check(self.L.nb_event_elapsed_ms(a, b, C.byref(ms)))
         return ms.value
 
+    # -- per-launch device timing (bench.py roofline): when ``profiler`` is a list, the kernel
+    #    wrappers bracket their launch with CUDA events on the ctx stream and append
+    #    (tag, work, unit, ev_start, ev_stop) to it --
+    profiler = None
+
+    def profile_begin(self):
+        self.profiler = []
+
+    def profile_end(self):
+        """-> list of (tag, work, unit, milliseconds); synchronises."""
+        recs, self.profiler = self.profiler or [], None
+        self.sync()
+        out = []
+        for tag, work, unit, a, b in recs:
+            out.append((tag, work, unit, self.elapsed_ms(a, b)))
+            self.L.nb_event_destroy(a)
+            self.L.nb_event_destroy(b)
+        return out
+
+    # -- pinned host staging --
+    def pinned_empty(self, shape, dtype):
+        return PinnedArray(self, shape, dtype)
+
     # -- arrays --
     def empty(self, shape, dtype):
         return DevArray(self, tuple(int(s) for s in shape), np.dtype(dtype))
@@ -200,6 +223,20 @@ class DevArray:
             self.ctx.sync()  # `a` may be a temporary: do not return before the DMA has read it
         return self
 
+    def copy_from_pinned(self, pinned):
+        """Asynchronous H2D from pinned host memory on the ctx stream (no host synchronisation)."""
+        if pinned.nbytes != self.nbytes:
+            raise ValueError(f"DimensionMismatch: {pinned.shape} vs {self.shape}")
+        check(self.ctx.L.nb_h2d(self.ctx.h, self.ptr, pinned.ptr, self.nbytes), self.ctx.h)
+        return self
+
+    def copy_to_pinned(self, pinned):
+        """Asynchronous D2H into pinned host memory; valid after ``ctx.sync()``."""
+        if pinned.nbytes != self.nbytes:
+            raise ValueError(f"DimensionMismatch: {pinned.shape} vs {self.shape}")
+        check(self.ctx.L.nb_d2h_async(self.ctx.h, pinned.ptr, self.ptr, self.nbytes), self.ctx.h)
+        return pinned
+
     def numpy(self):
         out = np.empty(self.shape, dtype=self.dtype, order="F")
         if self.nbytes:
@@ -222,6 +259,32 @@ class DevArray:
 
     def __repr__(self):
         return f"DevArray{{{self.dtype.name}}}{self.shape}"
+
+
+class PinnedArray:
+    """Page-locked host buffer (``nb_host_alloc``) viewed as a column-major NumPy array ``.a``."""
+
+    def __init__(self, ctx, shape, dtype):
+        self.ctx = ctx
+        self.shape = tuple(int(x) for x in shape)
+        self.dtype = np.dtype(dtype)
+        n = 1
+        for x in self.shape:
+            n *= x
+        self.nbytes = n * self.dtype.itemsize
+        p = C.c_void_p()
+        check(ctx.L.nb_host_alloc(max(self.nbytes, 1), C.byref(p)))
+        self.ptr = p.value
+        buf = (C.c_char * max(self.nbytes, 1)).from_address(self.ptr)
+        self.a = np.frombuffer(buf, dtype=self.dtype, count=n).reshape(self.shape, order="F")
+
+    def __del__(self):
+        try:
+            if self.ptr:
+                self.ctx.L.nb_host_free(self.ptr)
+                self.ptr = None
+        except Exception:
+            pass
 
 
 class BroadcastView:

@@ -36,6 +36,28 @@ def _prog_handle(prog, ctx):
     return None if prog is None else prog.handle(ctx)
 
 
+class _timed:
+    """Bracket a launch with CUDA events when the context is profiling (see Context.profile_begin)."""
+
+    __slots__ = ("ctx", "tag", "work", "unit", "ev")
+
+    def __init__(self, ctx, tag, work, unit):
+        self.ctx, self.tag, self.work, self.unit = ctx, tag, work, unit
+
+    def __enter__(self):
+        if self.ctx.profiler is not None:
+            self.ev = self.ctx.event()
+            self.ctx.record(self.ev)
+        return self
+
+    def __exit__(self, *exc):
+        if self.ctx.profiler is not None and exc[0] is None:
+            e1 = self.ctx.event()
+            self.ctx.record(e1)
+            self.ctx.profiler.append((self.tag, self.work, self.unit, self.ev, e1))
+        return False
+
+
 def bcast_fwd(prog, args, out):
     ctx = out.ctx
     check(ctx.L.nb_bcast_fwd(ctx.h, _prog_handle(prog, ctx), len(args), _pack([a.tensor() for a in args]),
@@ -67,8 +89,9 @@ def bcast_pullback(prog, ybar, y_saved, args, outs, accumulate):
     yb = ybar.base if isinstance(ybar, BroadcastView) else ybar
     ybt = C.byref(yb.tensor()) if yb is not None else None
     yst = C.byref(y_saved.tensor()) if y_saved is not None else None
-    check(ctx.L.nb_bcast_pullback(ctx.h, _prog_handle(prog, ctx), ybt, yst, len(args),
-                                  _pack([a.tensor() for a in args]), want, _pack(ts), acc), ctx.h)
+    with _timed(ctx, "bcast_pullback", 0, "B"):
+        check(ctx.L.nb_bcast_pullback(ctx.h, _prog_handle(prog, ctx), ybt, yst, len(args),
+                                      _pack([a.tensor() for a in args]), want, _pack(ts), acc), ctx.h)
     return outs
 
 
@@ -77,8 +100,9 @@ def gemm(tA, tB, alpha, A, B, beta, Cm, m, n, k, lda=None, ldb=None, ldc=None):
     lda = lda or (k if tA == "T" else m)
     ldb = ldb or (n if tB == "T" else k)
     ldc = ldc or m
-    check(ctx.L.nb_gemm(ctx.h, tA.encode(), tB.encode(), m, n, k, float(alpha), A.ptr, lda, B.ptr, ldb,
-                        float(beta), Cm.ptr, ldc, Cm.nb_dtype, ctx.math_mode), ctx.h)
+    with _timed(ctx, f"gemm_{tA}{tB}_{m}x{n}x{k}", 2.0 * m * n * k, "FLOP"):
+        check(ctx.L.nb_gemm(ctx.h, tA.encode(), tB.encode(), m, n, k, float(alpha), A.ptr, lda, B.ptr, ldb,
+                            float(beta), Cm.ptr, ldc, Cm.nb_dtype, ctx.math_mode), ctx.h)
     return Cm
 
 

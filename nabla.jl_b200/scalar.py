@@ -185,11 +185,11 @@ def compile_scalar(f, nargs, const_args=None):
             return s.index
         if s.kind == "const":
             return const_index(s.value)
-        key = id(s)
-        if key in memo:
-            return memo[key]
         a = emit(s.a)
         b = emit(s.b) if s.b is not None else 0
+        key = (s.op, a, b)  # structural CSE: identical sub-expressions are emitted once
+        if key in memo:
+            return memo[key]
         if s.op not in OPCODES:
             raise UnsupportedOp(4, f"scalar primitive `{s.op}` is not in the device catalogue")
         if len(ops) >= NB_MAX_INSTR:

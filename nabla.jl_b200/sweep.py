@@ -1,0 +1,149 @@
+"""Whole-sweep execution: CUDA-graph capture of one gradient evaluation and batch-sharded gradients.
+
+``CapturedGradient``  — forward pass + reverse sweep of ``∇(f)`` recorded ONCE as a CUDA graph
+    (SURVEY.md §8(f) rank 1).  The tape is built by the same host code as the eager path
+    (core.py / rules.py, mirroring src/core.jl:214-229); only the launches are replayed, so the
+    ~100 launches of the small MLP/VAE configurations cost one ``cudaGraphLaunch``.
+``ShardedGradient``   — batch (column) sharding over G ranks: every rank evaluates
+    the objective on its shard with the batch-independent prior scaled by 1/G, then ONE grouped
+    NCCL allreduce(sum) of the objective and every parameter sensitivity runs on the sweep stream.
+    The reference has no distributed layer; single-rank results are the parity target."""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+from ._lib import check
+from .core import Leaf, Node, Tape, nabla, unbox, unthunk, zeroslike
+from .device import DevArray, get_context
+
+
+class CapturedGradient:
+    """``∇(f; get_output=true)(params...)`` captured as a CUDA graph.
+
+    ``params`` are DevArrays; ``f`` may close over further DevArrays (the data batch).  Replays read
+    whatever those buffers hold at launch time, so a new batch is fed by copying into the same
+    buffers (``DevArray.copy_from_host`` / ``Context.h2d_async``).  ``f`` must not read device values
+    on the host while tracing (that would synchronise inside the capture)."""
+
+    def __init__(self, f, params, ctx=None, warmup=True):
+        self.ctx = ctx or (params[0].ctx if params else get_context())
+        self.params = list(params)
+        self._graph = None
+        L, h = self.ctx.L, self.ctx.h
+        if warmup:
+            # one eager evaluation first: compiles the scalar programs and sizes the pool, so the
+            # capture itself makes no cudaMalloc
+            self._evaluate(f)
+            self.ctx.sync()
+        check(L.nb_graph_begin(h), h)
+        try:
+            self.y, self.grads, self._tape = self._evaluate(f)
+        except BaseException:
+            g = C.c_void_p()
+            L.nb_graph_end(h, C.byref(g))
+            if g:
+                L.nb_graph_destroy(g)
+            raise
+        g = C.c_void_p()
+        check(L.nb_graph_end(h, C.byref(g)), h)
+        self._graph = g
+        before = self.ctx.stats()["kernel_launches"]
+        self()                      # first replay materialises the outputs
+        self.launches_per_replay = self.ctx.stats()["kernel_launches"] - before
+
+    def _evaluate(self, f):
+        t = Tape()
+        leaves = [Leaf(t, p) for p in self.params]
+        y = f(*leaves)
+        if not isinstance(y, Node):
+            raise TypeError("CapturedGradient: the objective does not depend on the parameters")
+        df = nabla(y)
+        grads = [unthunk(df.raw(l)) if df.isassigned(l) else zeroslike(l) for l in leaves]
+        # a sensitivity that aliases another slot (a rule returned ȳ itself) gets its own buffer so
+        # the in-place allreduce of ShardedGradient never sums one buffer twice
+        grads = [g.copy() if g.shared else g for g in grads]
+        # keep the forward tape and the reverse tape alive: the graph refers to their buffers
+        return unbox(y), grads, (t, df)
+
+    def __call__(self):
+        check(self.ctx.L.nb_graph_launch(self.ctx.h, self._graph), self.ctx.h)
+        return self.y, self.grads
+
+    def close(self):
+        if self._graph is not None and self.ctx.h:
+            self.ctx.L.nb_graph_destroy(self._graph)
+        self._graph = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Communicator:
+    """NCCL communicator bound to a context (include/nabla_cuda.h ``nb_comm_*``).  The 128-byte
+    unique id is created on rank 0 and handed to ``exchange(id_bytes_or_None) -> id_bytes`` — any
+    out-of-band broadcast (bench.py uses ``torch.distributed``)."""
+
+    def __init__(self, ctx, rank, nranks, exchange):
+        self.ctx, self.rank, self.nranks = ctx, rank, nranks
+        if nranks > 1:
+            uid = (C.c_uint8 * 128)()
+            if rank == 0:
+                check(ctx.L.nb_comm_unique_id(uid))
+            raw = exchange(bytes(uid) if rank == 0 else None)
+            uid = (C.c_uint8 * 128)(*raw)
+            check(ctx.L.nb_comm_init(ctx.h, nranks, rank, uid), ctx.h)
+            ctx.nranks, ctx.rank = nranks, rank
+
+    def allreduce_sum(self, arrays):
+        """In-place sum over ranks of every array (one grouped launch per dtype on the ctx stream)."""
+        if self.nranks == 1 or not arrays:
+            return
+        ctx = self.ctx
+        for dt in (np.dtype(np.float32), np.dtype(np.float64)):
+            group = [a for a in arrays if a.dtype == dt]
+            if not group:
+                continue
+            n = len(group)
+            ptrs = (C.c_void_p * n)(*[a.ptr for a in group])
+            counts = (C.c_int64 * n)(*[a.size for a in group])
+            check(ctx.L.nb_allreduce_sum(ctx.h, n, ptrs, counts, group[0].nb_dtype), ctx.h)
+
+    def close(self):
+        if self.nranks > 1 and self.ctx.h:
+            self.ctx.L.nb_comm_destroy(self.ctx.h)
+
+
+def shard_bounds(B, rank, nranks):
+    """Contiguous, near-equal column range of rank ``rank`` (matches workloads.shard_columns)."""
+    return (B * rank) // nranks, (B * (rank + 1)) // nranks
+
+
+class ShardedGradient:
+    """Batch-sharded gradient evaluation.
+
+    ``make_objective(prior_scale)`` returns the objective closed over THIS rank's data shard, with
+    batch-independent terms multiplied by ``prior_scale`` = 1/G.  ``step()`` runs the (optionally
+    graph-captured) sweep and the allreduce; results stay on the device."""
+
+    def __init__(self, make_objective, params, comm, capture=True):
+        self.comm = comm
+        self.ctx = comm.ctx
+        self.params = list(params)
+        self.f = make_objective(1.0 / comm.nranks)
+        self.captured = CapturedGradient(self.f, self.params, self.ctx) if capture else None
+
+    def step(self):
+        if self.captured is not None:
+            y, grads = self.captured()
+        else:
+            y, grads = nabla(self.f, get_output=True)(*self.params)
+            y, grads = unbox(y), [unthunk(g) for g in grads]
+            for i, g in enumerate(grads):   # a sensitivity that aliases another slot gets its own buffer
+                if g.shared:
+                    grads[i] = g.copy()
+        self.comm.allreduce_sum([y] + list(grads))
+        return y, grads

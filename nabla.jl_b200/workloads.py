@@ -24,33 +24,35 @@ def apply_transforms(nb, X, W, b, f):
     return h
 
 
-def mlp_log_joint(nb, X, Y, one_minus_Y, W, b, lam, eps=1e-15):
-    """examples/mlp.jl:56-77.  ``one_minus_Y`` is the constant ``1 .- Y`` (line 73)."""
+def mlp_log_joint(nb, X, Y, W, b, lam, eps=1e-15):
+    """examples/mlp.jl:56-77.  ``1 - Y`` (line 73) is read as ``1 .- Y``; ``Y`` is data, not a Node, so
+    that broadcast is a plain forward computation re-done every evaluation, as in the reference."""
     log_prior = 0.0
     for Wn, bn in zip(W, b):
         log_prior = log_prior + (nb.sum(nb.abs2, Wn) + nb.sum(nb.abs2, bn))
     log_prior = log_prior * (-0.5 * lam)
     f = nb.broadcast(logistic_of(nb), apply_transforms(nb, X, W, b, nb.tanh))
     f = nb.broadcast(nb.div, f, nb.sum(f, dims=1))
+    one_minus_Y = nb.broadcast(nb.sub, 1.0, Y)
     t1 = nb.broadcast(nb.mul, Y, nb.broadcast(nb.log, nb.broadcast(nb.add, f, eps)))
     t2 = nb.broadcast(nb.mul, one_minus_Y, nb.broadcast(nb.log, nb.broadcast(nb.sub, 1.0 + eps, f)))
     log_lik = nb.sum(nb.broadcast(nb.add, t1, t2))
     return log_lik + log_prior, f
 
 
-def mlp_objective(nb, X, Y, one_minus_Y, lam, nlayers, prior_scale=1.0, eps=1e-15):
+def mlp_objective(nb, X, Y, lam, nlayers, prior_scale=1.0, eps=1e-15):
     """Scalar objective of the parameters (W1..Wn, b1..bn) for ``nabla``.  ``prior_scale`` = 1/G
     when the batch is sharded over G ranks so the allreduce-sum counts the prior once
     (SURVEY.md §7 hard part 7)."""
     def obj(*params):
         W, b = params[:nlayers], params[nlayers:]
-        return mlp_log_joint(nb, X, Y, one_minus_Y, W, b, lam * prior_scale, eps)[0]
+        return mlp_log_joint(nb, X, Y, W, b, lam * prior_scale, eps)[0]
     return obj
 
 
-def vae_log_joint(nb, X, one_minus_X, noise, Wh, Wmu, Wsig, Vh, Vf, lam, scal, dz, eps=1e-12,
-                  prior_scale=1.0):
-    """examples/vae.jl:67-90 with L = 1."""
+def vae_log_joint(nb, X, noise, Wh, Wmu, Wsig, Vh, Vf, lam, scal, dz, eps=1e-12, prior_scale=1.0):
+    """examples/vae.jl:67-90 with L = 1.  ``scal`` uses the GLOBAL batch size; ``prior_scale`` = 1/G
+    under batch sharding (the allreduce-sum then counts the prior once)."""
     logistic = logistic_of(nb)
     logprior = (-0.5 * lam * prior_scale) * (nb.sum(nb.abs2, Wh) + nb.sum(nb.abs2, Wmu)
                                                + nb.sum(nb.abs2, Wsig) + nb.sum(nb.abs2, Vh)
@@ -60,6 +62,7 @@ def vae_log_joint(nb, X, one_minus_X, noise, Wh, Wmu, Wsig, Vh, Vf, lam, scal, d
     sig = nb.broadcast(nb.exp, nb.matmul(Wsig, h_enc))
     z = nb.broadcast(nb.add, mu, nb.broadcast(nb.mul, sig, noise))       # vae.jl:77
     f = nb.broadcast(logistic, nb.matmul(Vf, nb.broadcast(nb.tanh, nb.matmul(Vh, z))))  # decode :38
+    one_minus_X = nb.broadcast(nb.sub, 1.0, X)
     t1 = nb.broadcast(nb.mul, X, nb.broadcast(nb.log, nb.broadcast(nb.add, f, eps)))
     t2 = nb.broadcast(nb.mul, one_minus_X, nb.broadcast(nb.log, nb.broadcast(nb.sub, 1.0 + eps, f)))
     loglik = 0.0 + nb.sum(nb.broadcast(nb.add, t1, t2))
@@ -69,6 +72,20 @@ def vae_log_joint(nb, X, one_minus_X, noise, Wh, Wmu, Wsig, Vh, Vf, lam, scal, d
                   - nb.sum(nb.broadcast(nb.log, sig2)))                   # klvae, vae.jl:39
     elbo = loglik - klqp
     return scal * elbo + logprior
+
+
+def vae_objective(nb, X, noise, lam, scal, dz, prior_scale=1.0):
+    def obj(*params):
+        return vae_log_joint(nb, X, noise, *params, lam=lam, scal=scal, dz=dz, prior_scale=prior_scale)
+    return obj
+
+
+def shard_columns(a, rank, nranks):
+    """Batch (column) shard of a (d x B) array for rank ``rank`` of ``nranks``:
+    contiguous, near-equal column ranges in rank order."""
+    B = a.shape[-1]
+    lo, hi = (B * rank) // nranks, (B * (rank + 1)) // nranks
+    return a[..., lo:hi]
 
 
 def quad_symmetric(nb, A):

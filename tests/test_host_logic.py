@@ -1,0 +1,96 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every symbol the header
+declares, the opcode table matches, the scalar tracer lowers functions correctly, and the product
+path fails loudly (no CPU fallback) when no GPU is present."""
+import ctypes
+import os
+import subprocess
+
+import pytest
+
+import nabla_jl_b200 as nb
+from nabla_jl_b200 import _lib, scalar
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = _lib.lib()
+    declared = _lib.declared_symbols()
+    assert len(declared) >= 40
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in include/nabla_cuda.h but not exported"
+    assert set(_lib._SIGS) == set(declared)
+    assert L.nb_abi_version() == 1
+
+
+def test_library_is_sm100a_and_has_no_oracle_dependency():
+    out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "sm_100a" in out
+    for dirpath, _, files in os.walk(os.path.join(ROOT, "nabla.jl_b200")):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "nabla_oracle" not in src.replace("nb = nabla_oracle", ""), f"{f} must not import the oracle"
+
+
+def test_opcodes_match_header():
+    ops = _lib.OPCODES
+    assert ops["identity"] == 0 and ops["tanh"] == 23 and ops["logistic"] == 55
+    assert ops["add"] == 64 and ops["atan2"] == 73
+    assert len(scalar.UNARY) == 58 and len(scalar.BINARY) == 10
+
+
+def test_tracer_single_primitive_and_constants():
+    p = nb.compile_scalar(nb.tanh, 1)
+    assert p.key == (1, (23,), (0,), (0,), ())
+    p = nb.compile_scalar(nb.sub, 2, {0: 1.5})          # (1+ϵ) .- f : constant baked in
+    assert p.nargs == 1 and p.ops == (65,) and p.a == (-1,) and p.b == (0,) and p.consts == (1.5,)
+    p = nb.compile_scalar(lambda x: x, 1)
+    assert p.ops == () and p.single_op == 0
+
+
+def test_tracer_recognises_logistic_and_literal_pow():
+    for f in (lambda x: 1.0 / (1.0 + nb.exp(-x)), lambda x: 1 / (nb.exp(-x) + 1), lambda x: nb.inv(1 + nb.exp(-x))):
+        assert nb.compile_scalar(f, 1).ops == (_lib.OPCODES["logistic"],)
+    assert nb.compile_scalar(lambda x: x ** 2, 1).ops == (_lib.OPCODES["abs2"],)
+
+
+def test_tracer_composite_program_with_cse():
+    f = lambda x, y, z: x * y + y * z + x * z
+    p = nb.compile_scalar(f, 3)
+    assert p.nargs == 3 and p.ops == (66, 66, 64, 66, 64)
+    g = lambda x: nb.sin(x) * nb.sin(x)   # structural CSE: sin(x) emitted once
+    assert len(nb.compile_scalar(g, 1).ops) == 2
+    def h(x):
+        s = nb.sin(x)
+        return s * s
+    assert len(nb.compile_scalar(h, 1).ops) == 2    # shared sub-expression emitted once
+
+
+def test_tracer_rejects_unsupported():
+    with pytest.raises(nb.UnsupportedOp):
+        nb.compile_scalar(lambda x: 1.0 if x > 0 else 2.0, 1)       # data-dependent branch
+    def too_long(x):
+        for _ in range(40):
+            x = nb.sin(x)
+        return x
+    with pytest.raises(nb.UnsupportedOp):
+        nb.compile_scalar(too_long, 1)
+
+
+def test_no_cpu_fallback_without_gpu():
+    n = ctypes.c_int32()
+    _lib.lib().nb_device_count(ctypes.byref(n))
+    if n.value > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(nb.NablaCudaError, match="no CUDA device"):
+        nb.Context()
+
+
+def test_julia_broadcast_shape_rule():
+    from nabla_jl_b200.kernels import jl_broadcast_shape
+    assert jl_broadcast_shape((5,), (5, 7)) == (5, 7)          # vector is a column
+    assert jl_broadcast_shape((1, 7), (5,)) == (5, 7)
+    assert jl_broadcast_shape((), (3, 1, 2)) == (3, 1, 2)
+    with pytest.raises(nb.DimensionMismatch):
+        jl_broadcast_shape((5,), (7,))

@@ -259,12 +259,12 @@ def test_whole_models_check_errs():
     import nabla_jl_b200.workloads as wl
     rng = np.random.default_rng(11)
     W, b, X, Y = wl.mlp_inputs((6, 5, 4, 3), 7, np.float64, seed=0)
-    obj = wl.mlp_objective(o, X, Y, 1.0 - Y, 1e-3, 3)
+    obj = wl.mlp_objective(o, X, Y, 1e-3, 3)
     xs = tuple(W) + tuple(b)
     vs = tuple(rng.standard_normal(p.shape) for p in xs)
     assert o.check_errs(obj, 1.0, xs, vs, eps_abs=1e-8, eps_rel=1e-6)
     params, X, noise = wl.vae_inputs(dx=8, dz=3, dh=6, B=5, seed=3)
-    obj = lambda *p: wl.vae_log_joint(o, X, 1.0 - X, noise, *p, lam=1e-3, scal=60000 / 5, dz=3)
+    obj = lambda *p: wl.vae_log_joint(o, X, noise, *p, lam=1e-3, scal=60000 / 5, dz=3)
     vs = tuple(rng.standard_normal(p.shape) for p in params)
     assert o.check_errs(obj, 1.0, params, vs, eps_abs=1e-6, eps_rel=1e-6)
     # C3 analytic: Ā = 1 - tanh²(A .+ b), b̄ = Σ_j Ā[:, j]
