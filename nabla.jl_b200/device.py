@@ -214,7 +214,9 @@ class DevArray:
 
     # -- transfers --
     def copy_from_host(self, a):
-        a = np.asfortranarray(a, dtype=self.dtype)
+        a = np.asarray(a, dtype=self.dtype)
+        if a.ndim:   # (asfortranarray would promote a 0-dim scalar to shape (1,))
+            a = np.asfortranarray(a)
         if a.shape != self.shape:
             raise ValueError(f"DimensionMismatch: {a.shape} vs {self.shape}")
         if self.nbytes:

@@ -133,7 +133,7 @@ def _mr_fused(y, ybar, rvs):
     seen = {}
     post = []
     for k, j in enumerate(dev_pos):
-        a = y.args[j]
+        a = y.args[j + 1]   # y.args = (f, operands...): operand j is argument j + 1
         if not isinstance(a, Node):
             continue
         xid = a.pos
@@ -374,8 +374,16 @@ _adjoint = Primitive("adjoint", _adjoint_forward)
 
 @_adjoint.grad(1)
 def _adjoint_grad(p, y, ybar, x):
-    """ChainRules rrule(adjoint): x̄ = ȳ'."""
-    return _adjoint_forward(ybar)
+    """ChainRules rrule(adjoint): x̄ = ȳ', projected back to the operand's shape (a Vector operand
+    gets a Vector sensitivity, not an n x 1 matrix)."""
+    ybar = K.materialize(ybar)
+    if x.ndim == 1:
+        return ybar.reshape((x.shape[0],))
+    if x.ndim == 2 and x.adjvec:
+        v = ybar.reshape((1, x.shape[1]))
+        v.adjvec = True
+        return v
+    return K.transpose(ybar)
 
 
 def adjoint(x):
