@@ -625,3 +625,33 @@ def test_graph_capture_replays_sweep(nb, ctx):
     for a, e in zip(g1, ref):
         np.testing.assert_array_equal(a.numpy(), e)
     assert cap.launches_per_replay > 0
+
+
+@pytest.mark.parametrize("mode,tol", [("3xtf32", 2e-5), ("tf32", 3e-3), ("fp32", 2e-5)])
+def test_gemm_tensor_core_modes(nb, ctx, mode, tol):
+    """Float32 GEMM on tcgen05 (kind::tf32) for all four transposes, ragged M/N/K tails, alpha/beta.
+    3xTF32 (default) must sit well inside rtol 1e-4; single-pass TF32 is reported at its own 1e-3
+    class; the CUDA-core FP32 path is the cross-check.  Reference: NumPy Float64."""
+    from nabla_jl_b200 import kernels as K
+    rng = np.random.default_rng(42)
+    old = ctx.math_mode
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32}[mode]
+    try:
+        for (m, n, k) in ((256, 256, 256), (384, 512, 1000), (132, 260, 72), (128, 2048, 4096), (1024, 136, 520), (256, 128, 16384 + 40)):
+            for tA in "NT":
+                for tB in "NT":
+                    A = rng.standard_normal((k, m) if tA == "T" else (m, k)).astype(np.float32)
+                    B = rng.standard_normal((n, k) if tB == "T" else (k, n)).astype(np.float32)
+                    C0 = rng.standard_normal((m, n)).astype(np.float32)
+                    opA = A.T if tA == "T" else A
+                    opB = B.T if tB == "T" else B
+                    Ad, Bd = ctx.asarray(A), ctx.asarray(B)
+                    for alpha, beta in ((1.0, 0.0), (-0.7, 1.0), (1.3, 0.5)):
+                        Cd = ctx.asarray(C0)
+                        K.gemm(tA, tB, alpha, Ad, Bd, beta, Cd, m, n, k)
+                        ref = alpha * (opA.astype(np.float64) @ opB.astype(np.float64)) + beta * C0.astype(np.float64)
+                        got = Cd.numpy().astype(np.float64)
+                        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+                        assert err < tol, f"{mode} {tA}{tB} {m}x{n}x{k} alpha={alpha} beta={beta}: rel err {err:.3e}"
+    finally:
+        ctx.math_mode = old

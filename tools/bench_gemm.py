@@ -1,0 +1,40 @@
+"""GEMM throughput probe: the wide-MLP shapes (forward NN, Abar NT, Bbar TN) in each math mode.
+Usage: python tools/bench_gemm.py [B] [modes]   (env NB_GEMM_BN=128|256 overrides the tile width)"""
+import os
+import sys
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import nabla_jl_b200 as nb  # noqa: E402
+from nabla_jl_b200 import kernels as K  # noqa: E402
+
+ctx = nb.get_context()
+Bc = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
+modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["tf32", "3xtf32"]
+D = 8192
+rng = np.random.default_rng(0)
+W = ctx.asarray(rng.standard_normal((D, D)).astype(np.float32))
+X = ctx.asarray(rng.standard_normal((D, Bc)).astype(np.float32))
+Y = ctx.empty((D, Bc), np.float32)
+Wb = ctx.empty((D, D), np.float32)
+Xb = ctx.empty((D, Bc), np.float32)
+shapes = {
+    "fwd  NN W*X        ": lambda: K.gemm("N", "N", 1.0, W, X, 0.0, Y, D, Bc, D),
+    "Abar NT Ybar*X'    ": lambda: K.gemm("N", "T", 1.0, Y, X, 0.0, Wb, D, D, Bc),
+    "Bbar TN W'*Ybar    ": lambda: K.gemm("T", "N", 1.0, W, Y, 0.0, Xb, D, Bc, D),
+}
+flops = 2.0 * D * D * Bc
+for mode in modes:
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32}[mode]
+    for name, fn in shapes.items():
+        for _ in range(2):
+            fn()
+        e0, e1 = ctx.event(), ctx.event()
+        reps = 5
+        ctx.record(e0)
+        for _ in range(reps):
+            fn()
+        ctx.record(e1)
+        ctx.sync()
+        ms = ctx.elapsed_ms(e0, e1) / reps
+        print(f"{mode:7s} {name} B={Bc}: {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
