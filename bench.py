@@ -346,7 +346,8 @@ def run_gpu(args):
         step()
     barrier()
     sampler = ClockSampler(local) if rank == 0 else None
-    launches0 = ctx.stats()["kernel_launches"]
+    stats0 = ctx.stats()
+    launches0 = stats0["kernel_launches"]
     ctx.profile_begin()
     barrier()
     ms = timed_region(ctx, step, args.steps)
@@ -368,9 +369,10 @@ def run_gpu(args):
     by_tag = {}
     for tag, work, unit, t in recs:
         if unit == "FLOP":
-            d = by_tag.setdefault(tag, [0.0, 0, work])
+            d = by_tag.setdefault(tag, [0.0, 0, work, []])
             d[0] += t
             d[1] += 1
+            d[3].append(t)
     roof = None
     gemm_ms_total = sum(v[0] for v in by_tag.values())
     if by_tag:
@@ -389,7 +391,7 @@ def run_gpu(args):
                 "launches": sum(v[1] for v in by_tag.values()),
                 "share_of_step": gemm_ms_total / ms,
                 "avg_launch_ms": gemm_ms_total / max(1, sum(v[1] for v in by_tag.values())),
-                "per_shape": {k: {"launches": v[1], "avg_ms": v[0] / v[1],
+                "per_shape": {k: {"launches": v[1], "avg_ms": v[0] / v[1], "min_ms": min(v[3]), "max_ms": max(v[3]),
                                   "TFLOP/s": v[2] / (v[0] / v[1] * 1e-3) / 1e12} for k, v in by_tag.items()}}
     line = {
         "metric": "gradient evals/sec", "value": value, "unit": "evals/s", "n_gpus": n,
@@ -398,6 +400,8 @@ def run_gpu(args):
         "config": workload_config(args, n),
         "TFLOP/s_algorithmic": mlp_flops(dims, B) / (ms_step * 1e-3) / 1e12,
         "clocks": clocks, "gpu_launches": int(launches),
+        "pool": {"cuda_mallocs_in_timed_regions": ctx.stats()["cuda_mallocs"] - stats0["cuda_mallocs"],
+                 "high_water_GB": ctx.stats()["pool_high_water"] / 1e9},
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "evals/s",
                 "h2d_bytes_per_step": int(Xp.nbytes + Yp.nbytes), "d2h_bytes_per_step": int(yp.nbytes),
                 "ms_per_step": ms_e2e / args.steps},

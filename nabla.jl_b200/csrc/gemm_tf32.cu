@@ -36,7 +36,10 @@ constexpr int BM = 128;
 constexpr int BK = 32;       // floats per K step (128 bytes)
 constexpr int UMMA_K = 8;    // K of one tcgen05.mma.kind::tf32
 constexpr int NTHREADS = 192;
-constexpr int KCHUNK = 2048; // K range accumulated in TMEM before the epilogue folds it into C
+// K range accumulated in TMEM before the epilogue folds it into C.  Also bounds the L2 working set of
+// the tiles in flight: a 16 x ~9 block of tiles touches (16 x 128 + 10 x 256) x KCHUNK x 4 B per chunk
+// (x2 with hi/lo operands) = 35 MB for both settings, so two chunks in flight still fit the 126 MB L2.
+template <int NPASS> struct KChunk { static constexpr int value = NPASS == 3 ? 1024 : 2048; };
 constexpr uint32_t CHUNK_BYTES = BK * 128;  // one MN-major chunk: 32 MN elements x BK k-rows
 
 struct GemmArgs {
@@ -245,8 +248,8 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUt
       int s = 0, a = 0;
       uint32_t ph = 0, aph = 0;
       for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-       for (int kb0 = 0; kb0 < nkb; kb0 += KCHUNK / BK) {
-        const int kb1 = min(nkb, kb0 + KCHUNK / BK);
+       for (int kb0 = 0; kb0 < nkb; kb0 += KChunk<NPASS>::value / BK) {
+        const int kb1 = min(nkb, kb0 + KChunk<NPASS>::value / BK);
         mbar_wait(&tempty[a], aph ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
@@ -285,7 +288,7 @@ k_gemm_tf32(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUt
      int tm, tn;
      tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
      const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
-     for (int kb0 = 0; kb0 < nkb; kb0 += KCHUNK / BK) {
+     for (int kb0 = 0; kb0 < nkb; kb0 += KChunk<NPASS>::value / BK) {
       const float beta = kb0 == 0 ? g.beta : 1.f;  // later chunks accumulate onto the first
       mbar_wait(&tfull[a], aph);
       tc_fence_after();

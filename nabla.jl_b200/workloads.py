@@ -68,8 +68,9 @@ def vae_log_joint(nb, X, noise, Wh, Wmu, Wsig, Vh, Vf, lam, scal, dz, eps=1e-12,
     loglik = 0.0 + nb.sum(nb.broadcast(nb.add, t1, t2))
     loglik = loglik / 1.0
     sig2 = nb.broadcast(nb.mul, sig, sig)                                  # σz .* σz, vae.jl:85
-    klqp = 0.5 * (nb.sum(sig2) + nb.sum(nb.abs2, mu) - float(dz)
-                  - nb.sum(nb.broadcast(nb.log, sig2)))                   # klvae, vae.jl:39
+    # klvae, vae.jl:39; the constant D is batch-independent, so a shard carries 1/G of it
+    klqp = 0.5 * (nb.sum(sig2) + nb.sum(nb.abs2, mu) - float(dz) * prior_scale
+                  - nb.sum(nb.broadcast(nb.log, sig2)))
     elbo = loglik - klqp
     return scal * elbo + logprior
 

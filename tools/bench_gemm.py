@@ -29,12 +29,14 @@ for mode in modes:
     for name, fn in shapes.items():
         for _ in range(2):
             fn()
-        e0, e1 = ctx.event(), ctx.event()
-        reps = 5
-        ctx.record(e0)
-        for _ in range(reps):
+        reps = int(os.environ.get("REPS", "5"))
+        evs = [ctx.event() for _ in range(reps + 1)]
+        ctx.record(evs[0])
+        for i in range(reps):
             fn()
-        ctx.record(e1)
+            ctx.record(evs[i + 1])
         ctx.sync()
-        ms = ctx.elapsed_ms(e0, e1) / reps
-        print(f"{mode:7s} {name} B={Bc}: {ms:8.3f} ms  {flops / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
+        ts = sorted(ctx.elapsed_ms(evs[i], evs[i + 1]) for i in range(reps))
+        ms = sum(ts) / reps
+        print(f"{mode:7s} {name} B={Bc}: avg {ms:8.3f} ms  min {ts[0]:8.3f}  med {ts[reps // 2]:8.3f}  max {ts[-1]:8.3f}  "
+              f"{flops / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
