@@ -301,6 +301,11 @@ def nabla(f_or_node, ybar=None, *, get_output=False):
             out = tuple(df[a_] if df.isassigned(a_) else zeroslike(a_) for a_ in args_)
         else:
             out = tuple(zeroslike(a_) for a_ in args_)
+        # Tape -> Node -> Tape is a reference cycle: dropping the node list here lets reference
+        # counting return every forward value and intermediate sensitivity to the device pool as
+        # soon as this call returns, instead of whenever Python's cyclic collector runs (which made
+        # successive evaluations overlap in memory and hit cudaMalloc).  `y` stays a valid Node.
+        t.tape.clear()
         return (y, out) if get_output else out
 
     return gradient_fn
