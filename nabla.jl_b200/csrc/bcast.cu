@@ -479,11 +479,21 @@ __global__ void __launch_bounds__(256) k_finish(const T* __restrict__ partial, i
     if (threadIdx.x == 0) out[0] = acc ? out[0] + s * scale : s * scale;
     return;
   }
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= count) return;
+  // 32 outputs per block (coalesced along i), the 8 warps split the partials, fixed combination order
+  __shared__ T sm[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + tx;
   T s = T(0);
-  for (int64_t p = 0; p < nparts; ++p) s += partial[p * count + i];
-  out[i] = acc ? out[i] + s * scale : s * scale;
+  if (i < count)
+    for (int64_t p = ty; p < nparts; p += 8) s += partial[p * count + i];
+  sm[ty][tx] = s;
+  __syncthreads();
+  if (ty == 0 && i < count) {
+    T t = T(0);
+#pragma unroll
+    for (int y = 0; y < 8; ++y) t += sm[y][tx];
+    out[i] = acc ? out[i] + t * scale : t * scale;
+  }
 }
 
 // ---- k_nd: generic fallback for > 2 collapsed groups (one output per launch) -----------------
@@ -542,6 +552,8 @@ __global__ void __launch_bounds__(256) k_nd(MRP P, const nb_prog G, const NDP D)
   *dst = P.out[D.k].acc ? *dst + s : s;
 }
 
+#include "bcast_lean.cuh"
+
 // =================================================================================================
 // host-side dispatch
 // =================================================================================================
@@ -566,8 +578,20 @@ struct Call {
 
 static inline int64_t ext_of(const nb_tensor* t, int d) { return d < t->ndim ? t->shape[d] : 1; }
 
+template <typename T>
+struct LeanFlatF {
+  const MRP& P; int64_t nvec; unsigned blocks; cudaStream_t st;
+  template <int OP, int MODE> void operator()() { lean_launch_flat<T, OP, MODE>(P, nvec, blocks, st); }
+};
+template <typename T>
+struct LeanTallF {
+  const MRP& P; dim3 grid, block; size_t smem; int64_t cps; cudaStream_t st;
+  template <int OP, int MODE> void operator()() { lean_launch_tall<T, OP, MODE>(P, grid, block, smem, cps, st); }
+};
+
+// lean_mode: LM_* when the call qualifies for the compile-time-specialised kernels, -1 otherwise
 template <typename T, template <typename, int> class Ev>
-int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups) {
+int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_mode) {
   constexpr int V = VecOf<T>::V;
   cudaStream_t st = ctx->stream;
   const int sms = ctx->num_sms;
@@ -575,7 +599,7 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups) {
   std::vector<Pending> pend;
   auto finish = [&]() -> int32_t {
     for (auto& q : pend) {
-      int64_t blocks = q.count == 1 ? 1 : (q.count + 255) / 256;
+      int64_t blocks = q.count == 1 ? 1 : (q.count + 31) / 32;
       k_finish<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)q.partial, q.nparts, q.count,
                                                     (T*)P.out[q.k].p, T(P.scale), P.out[q.k].acc);
       NB_LAUNCH_CHECK(ctx);
@@ -605,6 +629,11 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups) {
         int32_t rc = alloc_partial(k, blocks, 1);
         if (rc != NB_OK) return rc;
       }
+    }
+    if (lean_mode >= 0 && P.rows % V == 0 &&
+        lean_dispatch<T>(P.op, lean_mode, LeanFlatF<T>{P, P.rows / V, (unsigned)blocks, st})) {
+      NB_LAUNCH_CHECK(ctx);
+      return finish();
     }
     k_flat<T, Ev><<<(unsigned)blocks, 256, 0, st>>>(P, G);
     NB_LAUNCH_CHECK(ctx);
@@ -661,7 +690,7 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups) {
     const int64_t min_cols = (int64_t)TY * 4;
     if (slabs > (P.cols + min_cols - 1) / min_cols) slabs = (P.cols + min_cols - 1) / min_cols;
     if (slabs < 1) slabs = 1;
-    if (slabs > 65535) slabs = 65535;
+    if (slabs > 256) slabs = 256;  // bounds the second-phase work (k_finish sums `slabs` partials)
     const int64_t cps = (P.cols + slabs - 1) / slabs;
     slabs = (P.cols + cps - 1) / cps;
     for (int k = 0; k < P.nout; ++k) {
@@ -673,7 +702,9 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups) {
     }
     dim3 grid((unsigned)rblocks, (unsigned)slabs), block(TX, TY);
     const size_t smem = (size_t)256 * V * sizeof(T);
-    k_tall<T, Ev><<<grid, block, smem, st>>>(P, G, cps);
+    if (!(lean_mode >= 0 && !any_wcol && P.rows % V == 0 &&
+          lean_dispatch<T>(P.op, lean_mode, LeanTallF<T>{P, grid, block, smem, cps, st})))
+      k_tall<T, Ev><<<grid, block, smem, st>>>(P, G, cps);
     NB_LAUNCH_CHECK(ctx);
     int32_t rc = finish();
     if (rc != NB_OK) return rc;
@@ -868,10 +899,28 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
   }
 
   if (ng <= 2) {
-    if (dt == NB_F32) return fast ? launch_all<float, FastEv>(ctx, P, G, ng)
-                                  : launch_all<float, GenEv>(ctx, P, G, ng);
-    return fast ? launch_all<double, FastEv>(ctx, P, G, ng)
-                : launch_all<double, GenEv>(ctx, P, G, ng);
+    // Lean eligibility: hot single primitive, vectorisable, saved y present when the partial needs it,
+    // and the wanted sensitivities are plain d/da, d/db (or both, in operand order).
+    int lean_mode = -1;
+    if (fast && P.vec_ok && lean_hot_op(P.op)) {
+      if (!C.pullback) lean_mode = LM_FWD;
+      else if (P.nout == 1 && (P.out[0].wrt == 1 || P.out[0].wrt == 2)) lean_mode = P.out[0].wrt;
+      else if (P.nout == 2 && P.out[0].wrt == 1 && P.out[1].wrt == 2) lean_mode = LM_PULL_AB;
+      if (lean_mode > 0) {
+        int needs = 0;
+        if (lean_mode & 1) needs |= nb_partial_needs(P.op, 0);
+        if (lean_mode & 2) needs |= nb_partial_needs(P.op, 1);
+        if ((needs & 4) && !C.ysaved) lean_mode = -1;  // would have to recompute y: general kernel
+      }
+      if (lean_mode >= 0) {
+        P.load_mask = (P.is_const[0] ? 0 : 1) | (P.is_const[1] ? 0 : 2);
+        P.has_y = C.ysaved != nullptr;
+      }
+    }
+    if (dt == NB_F32) return fast ? launch_all<float, FastEv>(ctx, P, G, ng, lean_mode)
+                                  : launch_all<float, GenEv>(ctx, P, G, ng, -1);
+    return fast ? launch_all<double, FastEv>(ctx, P, G, ng, lean_mode)
+                : launch_all<double, GenEv>(ctx, P, G, ng, -1);
   }
 
   // ---- generic N-D fallback: one launch per output ------------------------------------------

@@ -25,15 +25,15 @@ struct nb_prog {
 #define NB_LN10 2.30258509299404568402
 #define NB_2_SQRTPI 1.12837916709551257390
 
-__host__ __device__ inline bool nb_op_is_unary(int op) { return op >= 0 && op < NB_OP_UNARY_END; }
-__host__ __device__ inline bool nb_op_is_binary(int op) {
+__host__ __device__ constexpr bool nb_op_is_unary(int op) { return op >= 0 && op < NB_OP_UNARY_END; }
+__host__ __device__ constexpr bool nb_op_is_binary(int op) {
   return op >= NB_OP_ADD && op < NB_OP_BINARY_END;
 }
 
 // Which inputs does the partial derivative need?  bit0: operand a, bit1: operand b, bit2: y.
 // (for d/da of a unary op; binary ops report the union over both partials — refined on the host
 //  per wanted operand by nb_partial_needs)
-__host__ __device__ inline int nb_partial_needs(int op, int wrt /*0=a,1=b*/) {
+__host__ __device__ constexpr int nb_partial_needs(int op, int wrt /*0=a,1=b*/) {
   const int A = 1, B = 2, Y = 4;
   switch (op) {
     case NB_OP_IDENTITY: case NB_OP_NEG: case NB_OP_DEG2RAD: case NB_OP_RAD2DEG: return 0;

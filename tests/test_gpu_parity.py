@@ -372,7 +372,7 @@ def test_gemm_all_transposes(nb, orc, dtype, tA, tB):
     # test/sensitivities/linalg/blas.jl:36-47 (N = 100) plus ragged and tile-sized shapes
     rng = np.random.default_rng(123456)
     sc = 1.0
-    for (m, k, n) in ((100, 100, 100), (37, 53, 29), (128, 256, 64), (10, 300, 260), (513, 40, 7)):
+    for (m, k, n) in ((100, 100, 100), (37, 53, 29), (128, 256, 64), (10, 300, 260), (513, 40, 7), (60, 3001, 150)):
         A = rng.standard_normal((k, m) if tA == "T" else (m, k))
         B = rng.standard_normal((n, k) if tB == "T" else (k, n))
         yb = rng.standard_normal((m, n))

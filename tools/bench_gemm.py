@@ -11,13 +11,16 @@ from nabla_jl_b200 import kernels as K  # noqa: E402
 ctx = nb.get_context()
 Bc = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["tf32", "3xtf32"]
-D = 8192
+D = int(os.environ.get("D", "8192"))
+DT = np.float64 if os.environ.get("DTYPE", "f32") == "f64" else np.float32
+if DT == np.float64:
+    modes = ["f64"]
 rng = np.random.default_rng(0)
-W = ctx.asarray(rng.standard_normal((D, D)).astype(np.float32))
-X = ctx.asarray(rng.standard_normal((D, Bc)).astype(np.float32))
-Y = ctx.empty((D, Bc), np.float32)
-Wb = ctx.empty((D, D), np.float32)
-Xb = ctx.empty((D, Bc), np.float32)
+W = ctx.asarray(rng.standard_normal((D, D)).astype(DT))
+X = ctx.asarray(rng.standard_normal((D, Bc)).astype(DT))
+Y = ctx.empty((D, Bc), DT)
+Wb = ctx.empty((D, D), DT)
+Xb = ctx.empty((D, Bc), DT)
 shapes = {
     "fwd  NN W*X        ": lambda: K.gemm("N", "N", 1.0, W, X, 0.0, Y, D, Bc, D),
     "Abar NT Ybar*X'    ": lambda: K.gemm("N", "T", 1.0, Y, X, 0.0, Wb, D, D, Bc),
@@ -25,7 +28,7 @@ shapes = {
 }
 flops = 2.0 * D * D * Bc
 for mode in modes:
-    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32}[mode]
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "f64": nb.MATH_DEFAULT}[mode]
     for name, fn in shapes.items():
         for _ in range(2):
             fn()
