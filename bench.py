@@ -291,7 +291,7 @@ def run_gpu(args):
 
     ctx = nb.Context(device=local)
     nb.set_context(ctx)
-    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32}[args.math] \
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "bf16x3": nb.MATH_BF16X3}[args.math] \
         if args.dtype == "f32" else nb.MATH_DEFAULT
     dtype = np.float32 if args.dtype == "f32" else np.float64
     dims, B = WIDE_DIMS, args.batch
@@ -379,15 +379,17 @@ def run_gpu(args):
         # aggregate all big GEMM launches (they are the same kernel): achieved = sum FLOP / sum time
         flop = sum(v[2] * v[1] for v in by_tag.values())
         achieved = flop / (gemm_ms_total * 1e-3) / 1e12
-        ratio = {"3xtf32": 0.5, "tf32": 0.5, "fp32": 0.5}[args.math] if args.dtype == "f32" else 0.5
+        ratio = {"bf16x3": 1.0, "3xtf32": 0.5, "tf32": 0.5, "fp32": 0.5}[args.math] if args.dtype == "f32" else 0.5
         peak = peaks["bf16_sustained"] * ratio
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": None,
                 "kernel": "nb_gemm (dense GEMM sensitivities: forward A*B, Abar=Ybar*B', Bbar=A'*Ybar)",
-                "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s x 0.5 "
-                             "(kind::tf32 runs at half the bf16 rate); achieved counts ALGORITHMIC flops "
-                             "2mnk, so 3xTF32 (three tensor passes per product, needed for rtol 1e-4) "
-                             "tops out at 1/3 of this peak",
+                "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s x {ratio} "
+                             "(kind::f16 for bf16x3, kind::tf32 at half that rate otherwise); achieved counts "
+                             "ALGORITHMIC flops 2mnk: the split modes needed for rtol 1e-4 (bf16x3, 3xtf32) "
+                             "issue three tensor passes per product, so they top out at 1/3 of this peak "
+                             "(tensor_work_frac = 3 x frac)",
+                "tensor_work_frac": (3.0 if args.math in ("bf16x3", "3xtf32") else 1.0) * achieved / peak,
                 "launches": sum(v[1] for v in by_tag.values()),
                 "share_of_step": gemm_ms_total / ms,
                 "avg_launch_ms": gemm_ms_total / max(1, sum(v[1] for v in by_tag.values())),
@@ -436,7 +438,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=32768, help="GLOBAL batch (columns)")
     ap.add_argument("--dtype", default="f32", choices=["f32", "f64"])
-    ap.add_argument("--math", default="3xtf32", choices=["3xtf32", "tf32", "fp32"])
+    ap.add_argument("--math", default="bf16x3", choices=["bf16x3", "3xtf32", "tf32", "fp32"])
     ap.add_argument("--cpu-cols", type=int, default=128)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

@@ -1,0 +1,591 @@
+// Family (3), tensor-core part: Float32 GEMM on the 5th-generation tensor cores.
+//
+//   C(m x n) = alpha * op(A) * op(B) + beta * C       (BLAS column-major, all four transposes)
+//
+// replaces OpenBLAS sgemm behind ChainRules' rrule(*) / BLAS.gemm adjoints (reached through
+// src/sensitivities/chainrules.jl:179-191,286 and src/sensitivities/linalg/blas.jl:224-228):
+// forward W*X, Abar = Ybar*B' ('N','T'), Bbar = A'*Ybar ('T','N'); beta = 1 is the in-place accumulate.
+//
+// Design (sm_100a):
+//   * persistent kernel, one CTA per SM, tile 128 x BN (BN = 256 or 128), K step = one 128-byte
+//     swizzle row; 6 warps: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread)
+//     + TMEM owner, warps 2..5 = epilogue (TMEM -> registers -> coalesced column-major stores).
+//   * operands are staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzles) straight from the
+//     column-major arrays: a non-transposed A is "MN-major", a transposed A is "K-major" (the UMMA
+//     descriptors carry the major-ness, so no transposed copy of any operand is ever made).
+//   * accumulators live in TMEM (2 x BN columns, double-buffered so the epilogue of chunk i overlaps
+//     the main loop of chunk i+1); smem ring of STAGES stages guarded by full/empty mbarriers;
+//     tcgen05.commit releases smem stages and publishes finished accumulators.
+//   * precision modes (nb_math_mode).  kind::tf32 keeps 10 mantissa bits of each operand: 7.7e-4
+//     relative error, outside the 1e-4 bar.  The split modes write x = hi + lo and issue
+//     lo*hi + hi*lo + hi*hi into one accumulator (three tensor passes per product):
+//       NB_MATH_3XTF32  hi = tf32(x), lo = x - hi (both exact): 21 bits, 4e-7 error, 3 tf32 passes.
+//       NB_MATH_BF16X3  (DEFAULT) hi = bf16(x), lo = bf16(x - hi): 16 bits (residual <= 2^-18 |x|),
+//                       ~1e-5 error, 3 kind::f16 passes at twice the tf32 rate.  The tensor pipe is
+//                       power-limited on this part (1 kW cap), so tensor work per useful FLOP is the
+//                       cost that matters: half of 3xTF32's time and energy.  The split copies are this
+//                       kernel's own temporaries, so their leading dimension is padded to a multiple of
+//                       8 elements: ANY lda/ldb/alignment works (e.g. the 10-row output layer).
+//   * the tensor core adds each product group into the FP32 accumulator with truncation, so the error
+//     of one long accumulation grows linearly in K (measured 2.9e-5 at K = 4096 for tf32).  K is
+//     therefore processed in chunks of KCHUNK: every chunk gets a fresh TMEM accumulator and the
+//     epilogue folds it into C with a correctly rounded FP32 add (C tile re-read from L2), which keeps
+//     the error at the single-chunk level for any K (the Abar GEMMs have K = batch = 32768).
+#include <cuda.h>
+#include <cuda_bf16.h>
+
+#include <cstring>
+
+#include "common.cuh"
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int NTHREADS = 192;
+
+// Operand kinds.  Every staged row is 128 bytes (one swizzle row), so tile byte sizes are kind-independent.
+enum { KIND_TF32 = 0, KIND_3XTF32 = 1, KIND_BF16X3 = 2 };
+template <int KIND>
+struct KindT {
+  static constexpr int ESIZE = KIND == KIND_BF16X3 ? 2 : 4;      // bytes per staged element
+  static constexpr int BK = 128 / ESIZE;                          // elements of K per stage (32 / 64)
+  static constexpr int UMMA_K = 32 / ESIZE;                       // K of one tcgen05.mma (8 / 16)
+  static constexpr int MN_CHUNK = 128 / ESIZE;                    // MN-elements per 128-byte row (32 / 64)
+  static constexpr uint32_t CHUNK_BYTES = BK * 128;               // one MN-major chunk: MN_CHUNK x BK rows
+  static constexpr int NSPLIT = KIND == KIND_TF32 ? 1 : 2;        // staged copies per operand (hi, lo)
+  static constexpr int NPASS = KIND == KIND_TF32 ? 1 : 3;
+  static constexpr uint32_t FMT = KIND == KIND_BF16X3 ? 1u : 2u;  // instruction-descriptor a/b format
+  // MN-major smem layout (see make_desc)
+  static constexpr uint64_t MN_TYPE = KIND == KIND_BF16X3 ? 2 : 1;
+  static constexpr uint64_t MN_SBO = KIND == KIND_BF16X3 ? 1024 : 512;
+  static constexpr uint32_t MN_KSTEP = UMMA_K * 128;              // bytes to the next UMMA_K k-rows
+  // K range accumulated in TMEM before the epilogue folds it into C.  Also bounds the L2 working set
+  // of the tiles in flight (a 16 x ~9 block of tiles): ~35 MB per chunk for every kind.
+  static constexpr int KCHUNK = KIND == KIND_3XTF32 ? 1024 : 2048;
+};
+
+struct GemmArgs {
+  int64_t M, N, K;
+  int32_t a_mn, b_mn;  // operand is MN-major in memory (A: not transposed, B: transposed)
+  float alpha, beta;
+  float* C;
+  int64_t ldc;
+  int32_t tiles_m, tiles_n;
+};
+
+// Tile rasterisation: groups of GROUP_M tile-rows are swept along n with m fastest inside the group,
+// so the ~148 tiles in flight form a compact GROUP_M x ~9 block whose operand panels (per K chunk) stay
+// resident in the 126 MB L2 even when the CTAs drift apart.
+constexpr int GROUP_M = 16;
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
+  const int per_group = GROUP_M * tiles_n;
+  const int group = t / per_group;
+  const int first_m = group * GROUP_M;
+  const int gsize = min(tiles_m - first_m, GROUP_M);
+  const int r = t - group * per_group;
+  tm = first_m + r % gsize;
+  tn = r / gsize;
+}
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 20000000000LL) __trap();  // ~10 s
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+// D[tmem] (+)= A[smem] * B[smem], M = 128, N and major-ness from idesc
+template <int KIND>
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+  if (KIND == KIND_BF16X3) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  }
+}
+
+// UMMA shared-memory descriptors (cute/arch/mma_sm100_desc.hpp SmemDescriptor):
+//   K-major  (SWIZZLE_128B, layout type 2): rows of 128 B along K; 8-row swizzle atoms 1024 B apart
+//            (SBO); LBO unused (1).
+//   MN-major tf32 (SWIZZLE_128B_BASE32B, layout type 1 — the only MN-major layout kind::tf32 accepts,
+//            cutlass sm100_common.inl "for mn-major tf32 operands, SW128_32B is the only available smem
+//            layout"): rows of 128 B hold 32 MN-elements of one k; 4-row swizzle atoms (32-byte chunks
+//            XOR row%4) 512 B apart (SBO); the next 32 MN-elements at LBO = CHUNK_BYTES.  TMA writes
+//            exactly this with CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B.
+//   MN-major bf16: ordinary SWIZZLE_128B (type 2): rows hold 64 MN-elements, 8-row atoms, SBO = 1024,
+//            the next 64 MN-elements at LBO = CHUNK_BYTES.
+template <int KIND>
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, bool mn_major) {
+  using KT = KindT<KIND>;
+  const uint64_t lbo = mn_major ? (KT::CHUNK_BYTES >> 4) : 1;
+  const uint64_t sbo = mn_major ? (KT::MN_SBO >> 4) : (1024 >> 4);
+  const uint64_t type = mn_major ? KT::MN_TYPE : 2;
+  return (uint64_t)((saddr & 0x3FFFF) >> 4) | (lbo << 16) | (sbo << 32) | (1ull << 46) | (type << 61);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15,"
+      " %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+        "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+        "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+template <int BN, int KIND>
+struct Cfg {
+  static constexpr uint32_t A_BYTES = BM * 128;
+  static constexpr uint32_t B_BYTES = BN * 128;
+  static constexpr uint32_t NSPLIT = KindT<KIND>::NSPLIT;
+  static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * NSPLIT;
+  static constexpr int STAGES = (int)(196608u / STAGE_BYTES);  // 192 KB of operand ring
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
+};
+
+template <int BN, int KIND>
+__global__ void __launch_bounds__(NTHREADS, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
+          const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1, const GemmArgs g) {
+  using C_ = Cfg<BN, KIND>;
+  using KT = KindT<KIND>;
+  constexpr int STAGES = C_::STAGES;
+  constexpr int BK = KT::BK, NPASS = KT::NPASS, MNC = KT::MN_CHUNK;
+  constexpr uint32_t CHUNK_BYTES = KT::CHUNK_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * C_::STAGE_BYTES);
+  uint64_t* full = bars;                     // [STAGES]
+  uint64_t* empty = bars + STAGES;           // [STAGES]
+  uint64_t* tfull = bars + 2 * STAGES;       // [2]
+  uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ntiles = g.tiles_m * g.tiles_n;
+  const int nkb = (int)((g.K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM allocation is warp-collective; this warp also frees it
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(C_::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int tm, tn;
+        tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+        const int m0 = tm * BM, n0 = tn * BN;
+        for (int kb = 0; kb < nkb; ++kb) {  // chunk boundaries do not concern the producer
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+          uint8_t* st = smem + s * C_::STAGE_BYTES;
+          const int k0 = kb * BK;
+#pragma unroll
+          for (int h = 0; h < (int)C_::NSPLIT; ++h) {
+            uint8_t* a_dst = st + h * C_::A_BYTES;
+            uint8_t* b_dst = st + C_::NSPLIT * C_::A_BYTES + h * C_::B_BYTES;
+            const CUtensorMap* ma = h ? &mA1 : &mA0;
+            const CUtensorMap* mb = h ? &mB1 : &mB0;
+            if (g.a_mn) {
+#pragma unroll
+              for (int c = 0; c < BM / MNC; ++c) tma_load_2d(a_dst + c * CHUNK_BYTES, ma, &full[s], m0 + MNC * c, k0);
+            } else {
+              tma_load_2d(a_dst, ma, &full[s], k0, m0);
+            }
+            if (g.b_mn) {
+#pragma unroll
+              for (int c = 0; c < BN / MNC; ++c) tma_load_2d(b_dst + c * CHUNK_BYTES, mb, &full[s], n0 + MNC * c, k0);
+            } else {
+              tma_load_2d(b_dst, mb, &full[s], k0, n0);
+            }
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (KT::FMT << 7) | (KT::FMT << 10) | ((uint32_t)g.a_mn << 15) |
+                             ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t a_kstep = g.a_mn ? KT::MN_KSTEP : 32u;  // K-major: UMMA_K elements = 32 bytes
+      const uint32_t b_kstep = g.b_mn ? KT::MN_KSTEP : 32u;
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        for (int kb0 = 0; kb0 < nkb; kb0 += KT::KCHUNK / BK) {
+          const int kb1 = min(nkb, kb0 + KT::KCHUNK / BK);
+          mbar_wait(&tempty[a], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * C_::STAGE_BYTES);
+            const uint32_t a_hi = st, a_lo = st + C_::A_BYTES;
+            const uint32_t b_hi = st + C_::NSPLIT * C_::A_BYTES, b_lo = b_hi + C_::B_BYTES;
+#pragma unroll
+            for (int p = 0; p < NPASS; ++p) {
+              // small terms first: lo*hi, hi*lo, then hi*hi
+              const uint32_t ab = NPASS == 1 ? a_hi : (p == 0 ? a_lo : a_hi);
+              const uint32_t bb = NPASS == 1 ? b_hi : (p == 1 ? b_lo : b_hi);
+#pragma unroll
+              for (int kk = 0; kk < BK / KT::UMMA_K; ++kk) {
+                tc_mma<KIND>(d_tmem, make_desc<KIND>(ab + kk * a_kstep, g.a_mn),
+                             make_desc<KIND>(bb + kk * b_kstep, g.b_mn), idesc,
+                             (uint32_t)(((kb - kb0) | p | kk) != 0));
+              }
+            }
+            tc_commit(&empty[s]);  // smem stage reusable once these MMAs have read it
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          tc_commit(&tfull[a]);  // accumulator (one K chunk) complete
+          if (++a == 2) { a = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5) =====================
+    const int q = warp & 3;  // TMEM lane quadrant this warp may access
+    int a = 0;
+    uint32_t aph = 0;
+    const float alpha = g.alpha;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int tm, tn;
+      tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+      const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
+      for (int kb0 = 0; kb0 < nkb; kb0 += KT::KCHUNK / BK) {
+        const float beta = kb0 == 0 ? g.beta : 1.f;  // later chunks accumulate onto the first
+        mbar_wait(&tfull[a], aph);
+        tc_fence_after();
+        const int64_t gm = m0 + q * 32 + lane;
+        const bool row_ok = gm < g.M;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t)(a * BN + c * 32) + ((uint32_t)(q * 32) << 16), v);
+          const int64_t nb = n0 + c * 32;
+          if (nb < g.N && row_ok) {
+            float* cp = g.C + gm + nb * g.ldc;
+            const int jmax = (int)min((int64_t)32, g.N - nb);
+            if (beta == 0.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < jmax) cp[(int64_t)j * g.ldc] = alpha * __uint_as_float(v[j]);
+            } else {
+              // all 32 loads first (independent, in flight together), then the stores: interleaving
+              // them serialises on L2 latency because the compiler must assume the columns alias
+              float old[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) old[j] = j < jmax ? __ldcg(cp + (int64_t)j * g.ldc) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < jmax) cp[(int64_t)j * g.ldc] = alpha * __uint_as_float(v[j]) + beta * old[j];
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(&tempty[a]);
+        if (++a == 2) { a = 0; aph ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_::TMEM_COLS));
+  }
+}
+
+// ---- operand splits: column-major (rows x cols, ld_in) -> hi, lo with leading dimension ld_out --------
+// tf32: hi = round-to-nearest tf32(x) (low 13 mantissa bits zero), lo = x - hi (exact), stored as f32
+__device__ __forceinline__ void split1(float x, float& hi, float& lo) {
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(x));
+  hi = __uint_as_float(t);
+  lo = x - hi;
+}
+// bf16: hi = bf16(x), lo = bf16(x - hi); x - hi - lo <= 2^-18 |x|
+__device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+template <typename O>
+__global__ void __launch_bounds__(256) k_split(const float* __restrict__ x, int64_t rows, int64_t cols,
+                                               int64_t ld_in, O* __restrict__ hi, O* __restrict__ lo,
+                                               int64_t ld_out, int vec) {
+  // grid.y strides over columns, grid.x * 256 threads over groups of 4 rows
+  const int64_t r4 = (rows + 3) >> 2;
+  for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) {
+    const float* xc = x + c * ld_in;
+    O* hc = hi + c * ld_out;
+    O* lc = lo + c * ld_out;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r4; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i << 2;
+      float v[4];
+      if (vec && r + 3 < rows) {
+        const float4 q = *reinterpret_cast<const float4*>(xc + r);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = r + e < rows ? xc[r + e] : 0.f;
+      }
+      __align__(16) O h[4];
+      __align__(16) O l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split1(v[e], h[e], l[e]);
+      if (r + 3 < rows) {  // ld_out is a multiple of 8 and r of 4: 8/16-byte aligned vector stores
+        if (sizeof(O) == 2) {
+          *reinterpret_cast<uint2*>(hc + r) = *reinterpret_cast<const uint2*>(h);
+          *reinterpret_cast<uint2*>(lc + r) = *reinterpret_cast<const uint2*>(l);
+        } else {
+          *reinterpret_cast<uint4*>(hc + r) = *reinterpret_cast<const uint4*>(h);
+          *reinterpret_cast<uint4*>(lc + r) = *reinterpret_cast<const uint4*>(l);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (r + e < rows) { hc[r + e] = h[e]; lc[r + e] = l[e]; }
+      }
+    }
+  }
+}
+
+// ---- host ---------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+struct GemmState {
+  EncodeTiledFn encode = nullptr;
+};
+
+GemmState* state_of(nb_ctx* ctx) {
+  if (!ctx->gemm_state) {
+    GemmState* st = new GemmState();
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      st->encode = (EncodeTiledFn)fn;
+    else
+      cudaGetLastError();
+    ctx->gemm_state = st;
+  }
+  return (GemmState*)ctx->gemm_state;
+}
+
+// 2-D map over a column-major (d0 x d1, ld) array; box = {box0, box1}, zero OOB fill
+bool make_map(GemmState* st, CUtensorMap* map, const void* base, CUtensorMapDataType dt, int esize, int64_t d0,
+              int64_t d1, int64_t ld, uint32_t box0, uint32_t box1, CUtensorMapSwizzle swz) {
+  cuuint64_t dims[2] = {(cuuint64_t)d0, (cuuint64_t)d1};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
+  cuuint32_t box[2] = {box0, box1};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = st->encode(map, dt, 2, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
+                          CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int BN, int KIND>
+int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
+  using C_ = Cfg<BN, KIND>;
+  auto kern = k_gemm_tc<BN, KIND>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    NB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM));
+    attr_done = true;
+  }
+  const int ntiles = g.tiles_m * g.tiles_n;
+  const int grid = ntiles < ctx->num_sms ? ntiles : ctx->num_sms;
+  kern<<<grid, NTHREADS, C_::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+template <typename O>
+int32_t run_split(nb_ctx* ctx, const float* x, int64_t rows, int64_t cols, int64_t ld_in, O* hi, O* lo,
+                  int64_t ld_out) {
+  const int vec = ((uintptr_t)x % 16 == 0) && (ld_in % 4 == 0);
+  int64_t gx = ((rows + 3) / 4 + 255) / 256;
+  if (gx > 64) gx = 64;
+  int64_t gy = cols;
+  const int64_t want = (int64_t)ctx->num_sms * 16;
+  if (gx * gy > want) gy = (want + gx - 1) / gx;
+  if (gy > 65535) gy = 65535;
+  if (gy < 1) gy = 1;
+  k_split<O><<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ctx->stream>>>(x, rows, cols, ld_in, hi, lo, ld_out, vec);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
+}  // namespace
+
+void nb_gemm_state_free(nb_ctx* ctx) {
+  delete (GemmState*)ctx->gemm_state;
+  ctx->gemm_state = nullptr;
+}
+
+// Returns NB_ERR_UNSUPPORTED when the problem is too small to be worth a 128-row tensor tile or (single
+// pass tf32 only, which reads the caller's arrays directly) when TMA cannot describe the operands.
+int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, float alpha,
+                        const float* A, int64_t lda, const float* B, int64_t ldb, float beta, float* C,
+                        int64_t ldc, int32_t math_mode) {
+  GemmState* st = state_of(ctx);
+  if (!st->encode) return NB_ERR_UNSUPPORTED;
+  if (m * n * k < (int64_t)1 << 18) return NB_ERR_UNSUPPORTED;  // tiny: one tile would idle 147 SMs
+  if (m >= (1ll << 31) || n >= (1ll << 31) || k >= (1ll << 31)) return NB_ERR_UNSUPPORTED;
+  const int kind = math_mode == NB_MATH_TF32 ? KIND_TF32 : math_mode == NB_MATH_3XTF32 ? KIND_3XTF32 : KIND_BF16X3;
+  if (kind == KIND_TF32) {
+    if (((uintptr_t)A | (uintptr_t)B) & 15) return NB_ERR_UNSUPPORTED;
+    if ((lda & 3) || (ldb & 3)) return NB_ERR_UNSUPPORTED;
+  }
+  const bool a_mn = !tA, b_mn = tB;
+  // stored extents: A is (a_r x a_c, lda), B is (b_r x b_c, ldb)
+  const int64_t a_r = tA ? k : m, a_c = tA ? m : k;
+  const int64_t b_r = tB ? n : k, b_c = tB ? k : n;
+  int BN = 256;
+  {
+    const int64_t tm = (m + BM - 1) / BM;
+    if (tm * ((n + 255) / 256) < ctx->num_sms && n > 128) BN = 128;  // more, smaller tiles to fill the SMs
+    if (n <= 128) BN = 128;
+    if (const char* e = getenv("NB_GEMM_BN")) BN = atoi(e) == 128 ? 128 : 256;
+  }
+  const int esize = kind == KIND_BF16X3 ? 2 : 4;
+  const void* src[4] = {A, A, B, B};  // A hi, A lo, B hi, B lo
+  int64_t ld_a = lda, ld_b = ldb;
+  void* tmp[4] = {nullptr, nullptr, nullptr, nullptr};
+  if (kind != KIND_TF32) {
+    const int64_t pad = 16 / esize * 1;  // leading dimensions of the split copies: 16-byte multiples
+    ld_a = (a_r + pad - 1) / pad * pad;
+    ld_b = (b_r + pad - 1) / pad * pad;
+    for (int i = 0; i < 4; ++i) {
+      const size_t bytes = (size_t)(i < 2 ? ld_a * a_c : ld_b * b_c) * esize;
+      int32_t rc = nb_pool_alloc(ctx, bytes, &tmp[i]);
+      if (rc != NB_OK) {
+        for (int j = 0; j < i; ++j) nb_pool_release(ctx, tmp[j]);
+        return rc;
+      }
+      src[i] = tmp[i];
+    }
+    int32_t rc;
+    if (kind == KIND_BF16X3) {
+      rc = run_split<__nv_bfloat16>(ctx, A, a_r, a_c, lda, (__nv_bfloat16*)tmp[0], (__nv_bfloat16*)tmp[1], ld_a);
+      if (rc == NB_OK)
+        rc = run_split<__nv_bfloat16>(ctx, B, b_r, b_c, ldb, (__nv_bfloat16*)tmp[2], (__nv_bfloat16*)tmp[3], ld_b);
+    } else {
+      rc = run_split<float>(ctx, A, a_r, a_c, lda, (float*)tmp[0], (float*)tmp[1], ld_a);
+      if (rc == NB_OK) rc = run_split<float>(ctx, B, b_r, b_c, ldb, (float*)tmp[2], (float*)tmp[3], ld_b);
+    }
+    if (rc != NB_OK) {
+      for (int i = 0; i < 4; ++i) nb_pool_release(ctx, tmp[i]);
+      return rc;
+    }
+  }
+  const CUtensorMapDataType dt = kind == KIND_BF16X3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  const uint32_t bk = 128 / esize, mnc = 128 / esize;
+  // MN-major -> inner dim is the MN extent, box {mnc, bk}; K-major -> inner dim k, box {bk, tile rows}
+  const CUtensorMapSwizzle swz_mn = kind == KIND_BF16X3 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
+  const uint32_t abox0 = a_mn ? mnc : bk, abox1 = a_mn ? bk : BM;
+  const uint32_t bbox0 = b_mn ? mnc : bk, bbox1 = b_mn ? bk : (uint32_t)BN;
+  CUtensorMap maps[4];
+  bool ok = true;
+  for (int i = 0; i < 4 && ok; ++i) {
+    const bool isA = i < 2;
+    ok = make_map(st, &maps[i], src[i], dt, esize, isA ? a_r : b_r, isA ? a_c : b_c, isA ? ld_a : ld_b,
+                  isA ? abox0 : bbox0, isA ? abox1 : bbox1,
+                  (isA ? a_mn : b_mn) ? swz_mn : CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  int32_t rc = NB_OK;
+  if (!ok) {
+    rc = NB_ERR_UNSUPPORTED;
+  } else {
+    GemmArgs g;
+    g.M = m; g.N = n; g.K = k;
+    g.a_mn = a_mn; g.b_mn = b_mn;
+    g.alpha = alpha; g.beta = beta;
+    g.C = C; g.ldc = ldc;
+    g.tiles_m = (int32_t)((m + BM - 1) / BM);
+    g.tiles_n = (int32_t)((n + BN - 1) / BN);
+    if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
+    else if (kind == KIND_3XTF32) rc = BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
+    else rc = BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);
+  }
+  for (int i = 0; i < 4; ++i)
+    if (tmp[i]) nb_pool_release(ctx, tmp[i]);
+  return rc;
+}

@@ -549,6 +549,15 @@ def test_mlp_gradient_f32(nb, orc):
         close(a, b, np.float32)
 
 
+def test_wide_mlp_gradient_f32_default_math(nb, orc):
+    """A scaled-down C5 (wide MLP, Float32, default BF16x3 tensor-core GEMMs, K up to 2048) against the
+    Float64 oracle: the whole-gradient error must stay inside 1e-4."""
+    y, g, yr, gr = _mlp_both(nb, orc, (784, 2048, 2048, 10), 1024, np.float32, seed=4)
+    np.testing.assert_allclose(y, yr, rtol=1e-4)
+    for a, b in zip(g, gr):
+        close(a, b, np.float32)
+
+
 def test_vae_gradient_f64(nb, orc):
     # C4: examples/vae.jl:67-90
     import nabla_jl_b200.workloads as wl
@@ -627,7 +636,7 @@ def test_graph_capture_replays_sweep(nb, ctx):
     assert cap.launches_per_replay > 0
 
 
-@pytest.mark.parametrize("mode,tol", [("3xtf32", 2e-5), ("tf32", 3e-3), ("fp32", 2e-5)])
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("3xtf32", 2e-5), ("tf32", 3e-3), ("fp32", 2e-5)])
 def test_gemm_tensor_core_modes(nb, ctx, mode, tol):
     """Float32 GEMM on tcgen05 (kind::tf32) for all four transposes, ragged M/N/K tails, alpha/beta.
     3xTF32 (default) must sit well inside rtol 1e-4; single-pass TF32 is reported at its own 1e-3
@@ -635,9 +644,9 @@ def test_gemm_tensor_core_modes(nb, ctx, mode, tol):
     from nabla_jl_b200 import kernels as K
     rng = np.random.default_rng(42)
     old = ctx.math_mode
-    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32}[mode]
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "bf16x3": nb.MATH_BF16X3}[mode]
     try:
-        for (m, n, k) in ((256, 256, 256), (384, 512, 1000), (132, 260, 72), (128, 2048, 4096), (1024, 136, 520), (256, 128, 16384 + 40)):
+        for (m, n, k) in ((256, 256, 256), (384, 512, 1000), (132, 260, 72), (128, 2048, 4096), (1024, 136, 520), (256, 128, 16384 + 40), (10, 2048, 1030), (250, 77, 333)):
             for tA in "NT":
                 for tB in "NT":
                     A = rng.standard_normal((k, m) if tA == "T" else (m, k)).astype(np.float32)

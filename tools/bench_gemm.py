@@ -10,7 +10,7 @@ from nabla_jl_b200 import kernels as K  # noqa: E402
 
 ctx = nb.get_context()
 Bc = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
-modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["tf32", "3xtf32"]
+modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["tf32", "3xtf32", "bf16x3"]
 D = int(os.environ.get("D", "8192"))
 DT = np.float64 if os.environ.get("DTYPE", "f32") == "f64" else np.float32
 if DT == np.float64:
@@ -28,7 +28,7 @@ shapes = {
 }
 flops = 2.0 * D * D * Bc
 for mode in modes:
-    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "f64": nb.MATH_DEFAULT}[mode]
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "bf16x3": nb.MATH_BF16X3, "f64": nb.MATH_DEFAULT}[mode]
     for name, fn in shapes.items():
         for _ in range(2):
             fn()

@@ -32,7 +32,7 @@ cases = {
     "random": (rng.standard_normal((m, k)), rng.standard_normal((k, n))),
 }
 for mode in modes:
-    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32}[mode]
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "bf16x3": nb.MATH_BF16X3}[mode]
     for tA in "NT":
         for tB in "NT":
             for name, (opA, opB) in cases.items():
