@@ -190,6 +190,18 @@ def timed_region(ctx, fn, steps):
     return ms
 
 
+def _time_oracle(fn, reps=3):
+    """Best-of-reps wall time of one oracle gradient evaluation on the host cores."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import nabla_oracle as orc
+    best = float("inf")
+    for _ in range(reps):
+        t0 = time.perf_counter()
+        fn(orc)
+        best = min(best, time.perf_counter() - t0)
+    return {"ms_per_eval": best * 1e3, "evals_per_s": 1.0 / best, "cores": host_threads()}
+
+
 def extra_measurements(nb, ctx, peaks, quick):
     """HBM-bound kernels (C3) and the small configs (C1, C4), N=1 only.  Short."""
     from nabla_jl_b200 import kernels as K, workloads as wl
@@ -214,7 +226,12 @@ def extra_measurements(nb, ctx, peaks, quick):
         add = nb.compile_scalar(nb.add, 2)
         tanh = nb.compile_scalar(nb.tanh, 1)
         fused = nb.compile_scalar(lambda p, q: nb.tanh(p + q), 2)
+        brow = ctx.asarray(rng.standard_normal((1, n)).astype(dt))
+        browbar = ctx.empty((1, n), dt)
         cases = {
+            # transposed-reduction variant (b :: 1 x n): unbroadcast over ROWS, one value per column
+            "pullback_add_unbroadcast_brow": (lambda: K.bcast_pullback(add, tb1, None, [A, brow], [None, browbar],
+                                                                       [False, False]), N * s + n * s),
             "fwd_add": (lambda: K.bcast_fwd(add, [A, b], t1), 2 * N * s + m * s),
             "fwd_tanh": (lambda: K.bcast_fwd(tanh, [t1], y), 2 * N * s),
             "fwd_sum": (lambda: K.bcast_reduce(None, [y], sout), N * s),
@@ -255,6 +272,39 @@ def extra_measurements(nb, ctx, peaks, quick):
         ms = timed_region(ctx, fn, reps) / reps
         out[f"c1_mlp_f64_B4096_{label}"] = {"ms_per_eval": ms, "evals_per_s": 1e3 / ms,
                                             "TFLOP/s": mlp_flops((784, 500, 300, 10), 4096) / (ms * 1e-3) / 1e12}
+    out["c1_mlp_f64_B4096_cpu_oracle"] = _time_oracle(lambda orc: orc.nabla(wl.mlp_objective(orc, X, Y, LAM, 3))(*W, *b))
+    # C2: quadratic forms at N = 4096, Float64
+    Aq, xq, yq = wl.quad_inputs(4096)
+    Aqd = ctx.asarray(Aq)
+    for name, fn, args_ in (("c2_quad_symmetric_x'Ax", wl.quad_symmetric(nb, Aqd), (xq,)),
+                            ("c2_quad_asymmetric_x'Ay", wl.quad_asymmetric(nb, Aqd), (xq, yq))):
+        pa = [ctx.asarray(a) for a in args_]
+        f = nb.CapturedGradient(fn, pa, ctx)      # CUDA-graph replay of the whole sweep
+        for _ in range(3):
+            f()
+        reps = 10 if quick else 30
+        ms = timed_region(ctx, f, reps) / reps
+        nbytes = 2 * 4096 * 4096 * 8   # A streamed once forward and once in the reverse sweep
+        out[name + "_f64_N4096"] = {"ms_per_eval": ms, "evals_per_s": 1e3 / ms, "GB/s": nbytes / (ms * 1e-3) / 1e9,
+                                    "frac_of_hbm_peak": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                    "note": "two GEMV passes over A (134 MB, about the size of the L2); CUDA-graph replay"}
+    # matrix form quad(A, B) = B'AB with Ybar = I (test/core.jl:206-218): 8 DMMA GEMMs of 4096^3
+    Bq = ctx.asarray(np.random.default_rng(5).standard_normal((4096, 4096)))
+    eye = ctx.asarray(np.eye(4096))
+    def quad_matrix():
+        t = nb.Tape()
+        A_, B_ = nb.Leaf(t, Aqd), nb.Leaf(t, Bq)
+        Q = nb.matmul(nb.adjoint(B_), nb.matmul(A_, B_))
+        rt = nb.nabla(Q, eye)
+        t.tape.clear()
+        return rt
+    for _ in range(2):
+        quad_matrix()
+    reps = 3 if quick else 5
+    ms = timed_region(ctx, quad_matrix, reps) / reps
+    out["c2_quad_matrix_B'AB_f64_N4096"] = {"ms_per_eval": ms, "TFLOP/s": 6 * 2.0 * 4096 ** 3 / (ms * 1e-3) / 1e12,
+                                            "note": "2 forward + 4 reverse DMMA GEMMs and 3 transposes per evaluation"}
+    del Aqd, Bq, eye
     vp, VX, noise = wl.vae_inputs(B=4096, seed=3)
     VXd, Nd = ctx.asarray(VX), ctx.asarray(noise)
     vparams = [ctx.asarray(p) for p in vp]
@@ -264,6 +314,8 @@ def extra_measurements(nb, ctx, peaks, quick):
         cap()
     reps = 10 if quick else 50
     ms = timed_region(ctx, cap, reps) / reps
+    out["c4_vae_f64_B4096_cpu_oracle"] = _time_oracle(
+        lambda orc: orc.nabla(wl.vae_objective(orc, VX, noise, LAM, 60000 / 4096, 10))(*vp))
     out["c4_vae_f64_B4096_graph"] = {"ms_per_eval": ms, "evals_per_s": 1e3 / ms,
                                      "TFLOP/s": 2.0 * 4096 * (2 * 799000 + 407000) / (ms * 1e-3) / 1e12,
                                      "launches_per_eval": cap.launches_per_replay}

@@ -171,21 +171,29 @@ struct GenEv {
     for (int i = 0; i < V; ++i) yb[i] = T(1);
     if (P.pullback && P.has_ybar)
       load_vals<T, V>(P.ybar.p, r * P.ybar.rs + c * P.ybar.cs, P.ybar.rs != 0, nvalid, vok, yb);
-    T vals[NB_MAX_SLOTS], adj[NB_MAX_SLOTS];
+    // V-wide interpretation: one opcode decode per V elements (ops.cuh)
+    T vals[NB_MAX_SLOTS][V];
 #pragma unroll
-    for (int i = 0; i < V; ++i) {
+    for (int k = 0; k < NB_MAX_ARGS; ++k)
+      if (k < P.nargs) {
 #pragma unroll
-      for (int k = 0; k < NB_MAX_ARGS; ++k)
-        if (k < P.nargs) vals[k] = x[k][i];
-      T y = nb_prog_eval<T>(G, vals);
-      if (!P.pullback) {
-        o[0][i] = y;
-      } else {
-        nb_prog_grad<T>(G, vals, adj);
-#pragma unroll
-        for (int k = 0; k < MAXOUT; ++k)
-          if (k < P.nout) o[k][i] = yb[i] * adj[P.out[k].wrt];
+        for (int i = 0; i < V; ++i) vals[k][i] = x[k][i];
       }
+    nb_prog_eval_vec<T, V>(G, vals);
+    if (!P.pullback) {
+      const int last = G.n_instr ? G.nargs + G.n_instr - 1 : 0;
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[0][i] = vals[last][i];
+    } else {
+      T adj[NB_MAX_SLOTS][V];
+      nb_prog_grad_vec<T, V>(G, vals, adj);
+#pragma unroll
+      for (int k = 0; k < MAXOUT; ++k)
+        if (k < P.nout) {
+          const int w = P.out[k].wrt;
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[k][i] = yb[i] * adj[w][i];
+        }
     }
   }
 };
@@ -589,6 +597,12 @@ struct LeanTallF {
   template <int OP, int MODE> void operator()() { lean_launch_tall<T, OP, MODE>(P, grid, block, smem, cps, st); }
 };
 
+template <typename T>
+struct LeanWcolF {
+  const MRP& P; unsigned blocks; cudaStream_t st;
+  template <int OP, int MODE> void operator()() { lean_launch_wcol<T, OP, MODE>(P, blocks, st); }
+};
+
 // lean_mode: LM_* when the call qualifies for the compile-time-specialised kernels, -1 otherwise
 template <typename T, template <typename, int> class Ev>
 int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_mode) {
@@ -678,6 +692,21 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
   // rows > 32: KEEP_COLS outputs go to the warp-per-column kernel, everything else to k_tall
   bool any_tall = false, any_wcol = false;
   for (int k = 0; k < P.nout; ++k) (P.out[k].mode == OM_KEEP_COLS ? any_wcol : any_tall) = true;
+  if (any_wcol && lean_mode >= 0 && P.rows % V == 0) {
+    // lean warp-per-column kernel: handles KEEP_COLS and ELEM outputs in ONE pass
+    bool ok = true;
+    for (int k = 0; k < P.nout; ++k) ok = ok && (P.out[k].mode == OM_KEEP_COLS || P.out[k].mode == OM_ELEM);
+    if (ok) {
+      for (int k = 0; k < P.nout; ++k) P.out[k].active = 1;
+      int64_t blocks = (P.cols + 7) / 8;
+      const int64_t cap = (int64_t)sms * 8;
+      if (blocks > cap) blocks = cap;
+      if (lean_dispatch<T>(P.op, lean_mode, LeanWcolF<T>{P, (unsigned)blocks, st})) {
+        NB_LAUNCH_CHECK(ctx);
+        return NB_OK;
+      }
+    }
+  }
   if (any_tall) {
     for (int k = 0; k < P.nout; ++k) P.out[k].active = P.out[k].mode != OM_KEEP_COLS;
     const int64_t rvec = (P.rows + V - 1) / V;

@@ -265,6 +265,73 @@ __global__ void __launch_bounds__(256) k_tall_lean(const MRP P, int64_t cols_per
   }
 }
 
+// ---- wcol: one warp per column, rows % V == 0; outputs ELEM / KEEP_COLS (reduce over the rows) ------
+template <typename T, int OP, int MODE>
+__global__ void __launch_bounds__(256) k_wcol_lean(const MRP P) {
+  constexpr int V = VecOf<T>::V;
+  constexpr int U = 4;
+  constexpr int NOUT = MODE == LM_PULL_AB ? 2 : 1;
+  using Pk = LeanPack<T, V, OP, MODE>;
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const T scale = T(P.scale);
+  constexpr int64_t STEP = 32 * V;
+  for (int64_t c = warp; c < P.cols; c += nwarps) {
+    T acc[NOUT];
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) acc[k] = T(0);
+    int64_t r = (int64_t)lane * V;
+    for (; r + (U - 1) * STEP < P.rows; r += U * STEP) {
+      Pk x[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) x[u].load(P, r + u * STEP, c);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        T o[2][V];
+        x[u].compute(o);
+#pragma unroll
+        for (int k = 0; k < NOUT; ++k) {
+          if (P.out[k].mode == OM_ELEM)
+            lean_store<T, V>(P.out[k], (r + u * STEP) * P.out[k].rs + c * P.out[k].cs, o[k], scale);
+          else {
+#pragma unroll
+            for (int v = 0; v < V; ++v) acc[k] += o[k][v];
+          }
+        }
+      }
+    }
+    for (; r < P.rows; r += STEP) {
+      Pk x;
+      x.load(P, r, c);
+      T o[2][V];
+      x.compute(o);
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        if (P.out[k].mode == OM_ELEM) lean_store<T, V>(P.out[k], r * P.out[k].rs + c * P.out[k].cs, o[k], scale);
+        else {
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[k] += o[k][v];
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < NOUT; ++k) {
+      if (P.out[k].mode != OM_KEEP_COLS) continue;
+      const T s = warp_sum(acc[k]);
+      if (lane == 0) {
+        T* dst = (T*)P.out[k].p + c * P.out[k].cs;
+        *dst = P.out[k].acc ? *dst + s * scale : s * scale;
+      }
+    }
+  }
+}
+
+template <typename T, int OP, int MODE>
+void lean_launch_wcol(const MRP& P, unsigned blocks, cudaStream_t st) {
+  k_wcol_lean<T, OP, MODE><<<blocks, 256, 0, st>>>(P);
+}
+
 // ---- dispatch ------------------------------------------------------------------------------------
 template <typename T, int OP, int MODE>
 void lean_launch_flat(const MRP& P, int64_t nvec, unsigned blocks, cudaStream_t st) {

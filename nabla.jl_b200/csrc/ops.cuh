@@ -318,3 +318,119 @@ __device__ __forceinline__ void nb_prog_grad(const nb_prog& P, const T* vals, T*
     }
   }
 }
+
+// ---- V-wide program interpreter: one opcode decode per V elements --------------------------------
+// (the scalar interpreter above decodes every instruction once per ELEMENT; profiles/r1: 5-9 % of HBM
+//  peak for a two-instruction lambda.  Here slot values live as V-vectors in thread-local memory and
+//  the opcode switch is hoisted out of the element loop for the hot primitives.)
+template <typename T, int V>
+__device__ __forceinline__ void nb_eval_vec(int op, const T (&a)[V], const T (&b)[V], T (&r)[V]) {
+#define NB_VEC_CASE(OPC, EXPR) \
+  case OPC:                    \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) { const T x = a[v], y = b[v]; (void)y; r[v] = (EXPR); } \
+    break;
+  switch (op) {
+    NB_VEC_CASE(NB_OP_IDENTITY, x) NB_VEC_CASE(NB_OP_NEG, -x) NB_VEC_CASE(NB_OP_ABS2, x * x)
+    NB_VEC_CASE(NB_OP_SQRT, sqrt(x)) NB_VEC_CASE(NB_OP_INV, T(1) / x) NB_VEC_CASE(NB_OP_EXP, exp(x))
+    NB_VEC_CASE(NB_OP_LOG, log(x)) NB_VEC_CASE(NB_OP_TANH, tanh(x))
+    NB_VEC_CASE(NB_OP_LOGISTIC, T(1) / (T(1) + exp(-x))) NB_VEC_CASE(NB_OP_ADD, x + y)
+    NB_VEC_CASE(NB_OP_SUB, x - y) NB_VEC_CASE(NB_OP_MUL, x * y) NB_VEC_CASE(NB_OP_DIV, x / y)
+    default:
+#pragma unroll
+      for (int v = 0; v < V; ++v) r[v] = nb_eval_cold<T>(op, a[v], b[v]);
+  }
+#undef NB_VEC_CASE
+}
+
+// partials of instruction `op` at (a, b) with value y: da (and db for binary ops), V-wide
+template <typename T, int V>
+__device__ __forceinline__ void nb_partials_vec(int op, const T (&a)[V], const T (&b)[V], const T (&y)[V],
+                                                T (&da)[V], T (&db)[V]) {
+#define NB_VEC_D(OPC, EA, EB)  \
+  case OPC:                    \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) { const T x = a[v], z = b[v], w = y[v]; (void)x; (void)z; (void)w; \
+      da[v] = (EA); db[v] = (EB); } \
+    break;
+  switch (op) {
+    NB_VEC_D(NB_OP_IDENTITY, T(1), T(0)) NB_VEC_D(NB_OP_NEG, T(-1), T(0)) NB_VEC_D(NB_OP_ABS2, T(2) * x, T(0))
+    NB_VEC_D(NB_OP_SQRT, T(0.5) / w, T(0)) NB_VEC_D(NB_OP_INV, -(w * w), T(0)) NB_VEC_D(NB_OP_EXP, w, T(0))
+    NB_VEC_D(NB_OP_LOG, T(1) / x, T(0)) NB_VEC_D(NB_OP_TANH, T(1) - w * w, T(0))
+    NB_VEC_D(NB_OP_LOGISTIC, w * (T(1) - w), T(0)) NB_VEC_D(NB_OP_ADD, T(1), T(1)) NB_VEC_D(NB_OP_SUB, T(1), T(-1))
+    NB_VEC_D(NB_OP_MUL, z, x) NB_VEC_D(NB_OP_DIV, T(1) / z, -w / z)
+    default:
+      if (nb_op_is_binary(op)) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+          da[v] = nb_dbinary<T>(op, 0, a[v], b[v], y[v]);
+          db[v] = nb_dbinary<T>(op, 1, a[v], b[v], y[v]);
+        }
+      } else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) { da[v] = nb_dunary_cold<T>(op, a[v], y[v]); db[v] = T(0); }
+      }
+  }
+#undef NB_VEC_D
+}
+
+template <typename T, int V>
+__device__ __forceinline__ void nb_slot_vec(const nb_prog& P, T (*vals)[V], int idx, T (&out)[V]) {
+  if (idx >= 0) {
+#pragma unroll
+    for (int v = 0; v < V; ++v) out[v] = vals[idx][v];
+  } else {
+    const T c = T(P.consts[-idx - 1]);
+#pragma unroll
+    for (int v = 0; v < V; ++v) out[v] = c;
+  }
+}
+
+// forward: vals[0..nargs) hold the operands on entry; on exit every slot is evaluated
+template <typename T, int V>
+__device__ __forceinline__ void nb_prog_eval_vec(const nb_prog& P, T (*vals)[V]) {
+  for (int i = 0; i < P.n_instr; ++i) {
+    T a[V], b[V], r[V];
+    nb_slot_vec<T, V>(P, vals, P.a[i], a);
+    if (nb_op_is_binary(P.op[i])) nb_slot_vec<T, V>(P, vals, P.b[i], b);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) b[v] = T(0);
+    }
+    nb_eval_vec<T, V>(P.op[i], a, b, r);
+#pragma unroll
+    for (int v = 0; v < V; ++v) vals[P.nargs + i][v] = r[v];
+  }
+}
+
+// reverse accumulation over the program DAG: adj[s] = d(program value)/d(slot s), V-wide
+template <typename T, int V>
+__device__ __forceinline__ void nb_prog_grad_vec(const nb_prog& P, T (*vals)[V], T (*adj)[V]) {
+  const int nslots = P.nargs + P.n_instr;
+  for (int s = 0; s < nslots; ++s)
+#pragma unroll
+    for (int v = 0; v < V; ++v) adj[s][v] = T(0);
+  const int last = P.n_instr ? nslots - 1 : 0;
+#pragma unroll
+  for (int v = 0; v < V; ++v) adj[last][v] = T(1);
+  for (int i = P.n_instr - 1; i >= 0; --i) {
+    const int op = P.op[i], ia = P.a[i], ib = P.b[i];
+    const bool bin = nb_op_is_binary(op);
+    T g[V], a[V], b[V], y[V], da[V], db[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { g[v] = adj[P.nargs + i][v]; y[v] = vals[P.nargs + i][v]; }
+    nb_slot_vec<T, V>(P, vals, ia, a);
+    if (bin) nb_slot_vec<T, V>(P, vals, ib, b);
+    else {
+#pragma unroll
+      for (int v = 0; v < V; ++v) b[v] = T(0);
+    }
+    nb_partials_vec<T, V>(op, a, b, y, da, db);
+    if (ia >= 0) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) adj[ia][v] += g[v] * da[v];
+    }
+    if (bin && ib >= 0) {
+#pragma unroll
+      for (int v = 0; v < V; ++v) adj[ib][v] += g[v] * db[v];
+    }
+  }
+}
