@@ -366,8 +366,10 @@ def run_gpu(args):
     Xp.a[...] = Xs
     Yp.a[...] = Ys
     yp = ctx.pinned_empty((), dtype)
-    sg = nb.ShardedGradient(lambda ps: wl.mlp_objective(nb, Xd, Yd, LAM, nl, prior_scale=ps), params, comm,
-                            capture=False)
+    # data term (log-likelihood of this rank's columns) + shared term (log-prior): gradients of the data
+    # term are allreduced per parameter as soon as they are final, overlapped with the rest of the sweep
+    sg = nb.OverlappedShardedGradient(wl.mlp_data_objective(nb, Xd, Yd, nl), wl.mlp_prior_objective(nb, LAM, nl),
+                                      params, comm)
 
     def step():
         return sg.step()

@@ -185,6 +185,13 @@ int32_t nb_comm_init(nb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id
 /* In-place sum of each buffer over all ranks (one grouped NCCL launch on the ctx stream). */
 int32_t nb_allreduce_sum(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const int64_t* counts,
                          int32_t dtype);
+/* Overlapped exchange: the reduction runs on the communicator's own stream, ordered after everything
+ * enqueued so far on the ctx stream, so the sweep keeps launching backward kernels while parameter
+ * sensitivities that are already final travel over NVLink.  nb_comm_join makes the ctx stream wait
+ * for every reduction started this way.  The buffers must stay allocated until the join. */
+int32_t nb_allreduce_sum_async(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const int64_t* counts,
+                               int32_t dtype);
+int32_t nb_comm_join(nb_ctx* ctx);
 int32_t nb_comm_destroy(nb_ctx* ctx);
 
 /* ---- CUDA-graph capture of a whole forward + reverse sweep --------------------------------- */

@@ -17,7 +17,8 @@ from .scalar import CATALOGUE, Program, ScalarFn, Sym, compile_scalar
 from .rules import (Ref, adjoint, broadcast, dot, gemm, gemv, ldivide, map_, mapfoldl, mapfoldr,
                     mapreduce, matmul, mean, sum, transpose)
 
-from .sweep import CapturedGradient, Communicator, ShardedGradient, shard_bounds
+from .sweep import (CapturedGradient, Communicator, OverlappedShardedGradient, ShardedGradient,
+                    shard_bounds)
 
 for _n, _f in CATALOGUE.items():
     globals()[{"abs": "abs_", "max": "max_", "min": "min_", "pow": "pow_"}.get(_n, _n)] = _f

@@ -101,6 +101,8 @@ _SIGS = {
     "nb_comm_unique_id": ([C.POINTER(C.c_uint8)], _i32),
     "nb_comm_init": ([_p, _i32, _i32, C.POINTER(C.c_uint8)], _i32),
     "nb_allreduce_sum": ([_p, _i32, _pp, C.POINTER(_i64), _i32], _i32),
+    "nb_allreduce_sum_async": ([_p, _i32, _pp, C.POINTER(_i64), _i32], _i32),
+    "nb_comm_join": ([_p], _i32),
     "nb_comm_destroy": ([_p], _i32),
     "nb_graph_begin": ([_p], _i32),
     "nb_graph_end": ([_p, _pp], _i32),

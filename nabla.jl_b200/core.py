@@ -256,13 +256,37 @@ def propagate_branch(y, rvs_tape):
                 d_tape[xid - 1] = fresh
 
 
-def propagate(fwd_tape, rvs_tape):
-    """``propagate(fwd_tape, rvs_tape)`` (core.jl:160-166): strictly descending tape index."""
+def last_contribution_positions(fwd_tape, upto):
+    """For every Leaf: the SMALLEST tape position among the Branches (<= upto) that take it as an
+    argument.  The sweep runs in descending order (core.jl:160-166) and a Leaf slot only receives
+    contributions from its direct consumers (core.jl:149-156), so once the sweep has processed that
+    position the Leaf's sensitivity is final."""
+    first_use = {}
+    for node in fwd_tape.tape[:upto]:
+        if isinstance(node, Branch):
+            for a in node.args:
+                if isinstance(a, Leaf) and a.pos not in first_use:
+                    first_use[a.pos] = node.pos
+    return first_use
+
+
+def propagate(fwd_tape, rvs_tape, on_final=None):
+    """``propagate(fwd_tape, rvs_tape)`` (core.jl:160-166): strictly descending tape index.
+
+    ``on_final(leaf_pos, slot)`` (optional, not in the reference) is called as soon as a Leaf's
+    sensitivity can no longer change — used to start its allreduce while the sweep continues."""
+    finals = {}
+    if on_final is not None:
+        for leaf_pos, p in last_contribution_positions(fwd_tape, len(rvs_tape)).items():
+            finals.setdefault(p, []).append(leaf_pos)
     for delta in range(len(rvs_tape), 0, -1):
         if rvs_tape.tape[delta - 1] is not UNDEF:
             node = fwd_tape.tape[delta - 1]
             if isinstance(node, Branch):
                 propagate_branch(node, rvs_tape)
+        for leaf_pos in finals.get(delta, ()):
+            if rvs_tape.tape[leaf_pos - 1] is not UNDEF:
+                on_final(leaf_pos, rvs_tape)
     return rvs_tape
 
 

@@ -105,7 +105,62 @@ int32_t nb_allreduce_sum(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const i
   return NB_OK;
 }
 
+static int32_t reduce_on(nb_ctx* ctx, cudaStream_t st, int32_t n_bufs, void* const* bufs, const int64_t* counts,
+                         int32_t dtype) {
+  ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  ncclResult_t r = api().GroupStart();
+  if (r != 0) return nccl_fail(ctx, "ncclGroupStart", r);
+  for (int i = 0; i < n_bufs; ++i) {
+    r = api().AllReduce(bufs[i], bufs[i], (size_t)counts[i], dtype == NB_F64 ? ncclFloat64 : ncclFloat32,
+                        ncclSum, comm, st);
+    if (r != 0) {
+      api().GroupEnd();
+      return nccl_fail(ctx, "ncclAllReduce", r);
+    }
+  }
+  r = api().GroupEnd();
+  if (r != 0) return nccl_fail(ctx, "ncclGroupEnd", r);
+  ctx->stats.kernel_launches++;
+  return NB_OK;
+}
+
+int32_t nb_allreduce_sum_async(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const int64_t* counts,
+                               int32_t dtype) {
+  NB_REQUIRE(ctx, ctx && (n_bufs == 0 || (bufs && counts)), NB_ERR_INVALID, "NULL argument");
+  NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
+  if (ctx->nranks == 1 && !ctx->nccl_comm) return NB_OK;
+  NB_REQUIRE(ctx, ctx->nccl_comm, NB_ERR_COMM, "nb_allreduce_sum_async: nb_comm_init was not called");
+  NB_REQUIRE(ctx, !ctx->capturing, NB_ERR_UNSUPPORTED, "overlapped reductions cannot be captured into a graph");
+  if (!ctx->comm_stream) {
+    NB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    NB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+    NB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
+  }
+  NB_CUDA_OK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  NB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
+  ctx->comm_pending = true;
+  return reduce_on(ctx, ctx->comm_stream, n_bufs, bufs, counts, dtype);
+}
+
+int32_t nb_comm_join(nb_ctx* ctx) {
+  NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
+  if (!ctx->comm_pending) return NB_OK;
+  NB_CUDA_OK(ctx, cudaEventRecord(ctx->ev_join, ctx->comm_stream));
+  NB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0));
+  ctx->comm_pending = false;
+  return NB_OK;
+}
+
 int32_t nb_comm_destroy(nb_ctx* ctx) {
+  if (ctx && ctx->comm_stream) {
+    cudaStreamSynchronize(ctx->comm_stream);
+    cudaStreamDestroy(ctx->comm_stream);
+    cudaEventDestroy(ctx->ev_fork);
+    cudaEventDestroy(ctx->ev_join);
+    ctx->comm_stream = nullptr;
+    ctx->ev_fork = ctx->ev_join = nullptr;
+    ctx->comm_pending = false;
+  }
   if (ctx && ctx->nccl_comm) {
     api().CommDestroy((ncclComm_t)ctx->nccl_comm);
     ctx->nccl_comm = nullptr;

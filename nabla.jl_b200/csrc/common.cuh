@@ -42,6 +42,9 @@ struct nb_ctx {
   // communicator (comm.cu)
   void* nccl_comm = nullptr;
   int nranks = 1, rank = 0;
+  cudaStream_t comm_stream = nullptr;      // overlapped reductions (nb_allreduce_sum_async)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool comm_pending = false;
   // tcgen05 GEMM staging (gemm_tf32.cu)
   void* gemm_state = nullptr;
 };

@@ -16,6 +16,9 @@ from . import _lib
 from ._lib import check
 from .core import Leaf, Node, Tape, nabla, unbox, unthunk, zeroslike
 from .device import DevArray, get_context
+from .scalar import CATALOGUE, compile_scalar
+
+_ADD_PROG = compile_scalar(CATALOGUE["add"], 2)
 
 
 class CapturedGradient:
@@ -112,6 +115,25 @@ class Communicator:
             counts = (C.c_int64 * n)(*[a.size for a in group])
             check(ctx.L.nb_allreduce_sum(ctx.h, n, ptrs, counts, group[0].nb_dtype), ctx.h)
 
+    def allreduce_sum_async(self, arrays):
+        """Start the in-place sum on the communicator's own stream, ordered after the work enqueued so
+        far on the sweep stream; ``join()`` makes the sweep stream wait for all of them."""
+        if self.nranks == 1 or not arrays:
+            return
+        ctx = self.ctx
+        for dt in (np.dtype(np.float32), np.dtype(np.float64)):
+            group = [a for a in arrays if a.dtype == dt]
+            if not group:
+                continue
+            n = len(group)
+            ptrs = (C.c_void_p * n)(*[a.ptr for a in group])
+            counts = (C.c_int64 * n)(*[a.size for a in group])
+            check(ctx.L.nb_allreduce_sum_async(ctx.h, n, ptrs, counts, group[0].nb_dtype), ctx.h)
+
+    def join(self):
+        if self.nranks > 1:
+            check(self.ctx.L.nb_comm_join(self.ctx.h), self.ctx.h)
+
     def close(self):
         if self.nranks > 1 and self.ctx.h:
             self.ctx.L.nb_comm_destroy(self.ctx.h)
@@ -120,6 +142,65 @@ class Communicator:
 def shard_bounds(B, rank, nranks):
     """Contiguous, near-equal column range of rank ``rank`` (matches workloads.shard_columns)."""
     return (B * rank) // nranks, (B * (rank + 1)) // nranks
+
+
+class OverlappedShardedGradient:
+    """Batch-sharded gradient of ``data_objective + shared_objective`` with the exchange OVERLAPPED
+    with the reverse sweep.
+
+    ``data_objective`` is this rank's shard of the batch-dependent term (its gradients are summed over
+    ranks); ``shared_objective`` is the batch-independent term (the prior), evaluated identically on
+    every rank and never reduced.  Sweep 1 (data) starts the allreduce of each parameter sensitivity
+    on the communicator stream the moment the sensitivity is final (``propagate(..., on_final)``): the
+    last layer's weights travel over NVLink while the GEMMs of the layers below still run.  Sweep 2
+    (shared) then accumulates in place into the reduced buffers (the reverse tape is pre-filled with
+    them, so the reference's accumulate path ``add!!`` does the sum).  On one rank this launches exactly
+    the kernels of the single ``∇(data + shared)`` sweep in the same accumulation order."""
+
+    def __init__(self, data_objective, shared_objective, params, comm):
+        self.comm, self.ctx = comm, comm.ctx
+        self.params = list(params)
+        self.f_data, self.f_shared = data_objective, shared_objective
+
+    def step(self):
+        from .core import oneslike, propagate, reverse_tape
+        from .kernels import bcast_fwd
+        comm = self.comm
+        # ---- sweep 1: data term, allreduce of every final leaf slot overlapped with the sweep
+        t = Tape()
+        leaves = [Leaf(t, p) for p in self.params]
+        y = self.f_data(*leaves)
+        rt = reverse_tape(y, oneslike(y))
+        grads = {}
+
+        def on_final(leaf_pos, rvs):
+            g = unthunk(rvs.raw(leaf_pos))
+            if g.shared:
+                g = g.copy()
+            rvs.tape[leaf_pos - 1] = g
+            grads[leaf_pos] = g
+            comm.allreduce_sum_async([g])
+
+        propagate(t, rt, on_final=on_final)
+        yd = unbox(y)
+        comm.allreduce_sum_async([yd])
+        g1 = [grads.get(l.pos) for l in leaves]
+        t.tape.clear()
+        # ---- sweep 2: shared term accumulates in place into the reduced buffers
+        t2 = Tape()
+        leaves2 = [Leaf(t2, p) for p in self.params]
+        y2 = self.f_shared(*leaves2)
+        comm.join()                      # the reduced sensitivities are about to be updated
+        rt2 = reverse_tape(y2, oneslike(y2))
+        for l, g in zip(leaves2, g1):
+            if g is not None:
+                rt2.tape[l.pos - 1] = g
+        propagate(t2, rt2)
+        out = [unthunk(rt2.raw(l)) if rt2.isassigned(l) else zeroslike(l) for l in leaves2]
+        ytot = self.ctx.empty((), yd.dtype)
+        bcast_fwd(_ADD_PROG, [yd, unbox(y2)], ytot)
+        t2.tape.clear()
+        return ytot, out
 
 
 class ShardedGradient:

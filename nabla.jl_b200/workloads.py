@@ -40,6 +40,30 @@ def mlp_log_joint(nb, X, Y, W, b, lam, eps=1e-15):
     return log_lik + log_prior, f
 
 
+def mlp_data_objective(nb, X, Y, nlayers, eps=1e-15):
+    """The batch-dependent part of ``mlp_log_joint``: the log-likelihood (examples/mlp.jl:67-73)."""
+    def obj(*params):
+        W, b = params[:nlayers], params[nlayers:]
+        f = nb.broadcast(logistic_of(nb), apply_transforms(nb, X, W, b, nb.tanh))
+        f = nb.broadcast(nb.div, f, nb.sum(f, dims=1))
+        one_minus_Y = nb.broadcast(nb.sub, 1.0, Y)
+        t1 = nb.broadcast(nb.mul, Y, nb.broadcast(nb.log, nb.broadcast(nb.add, f, eps)))
+        t2 = nb.broadcast(nb.mul, one_minus_Y, nb.broadcast(nb.log, nb.broadcast(nb.sub, 1.0 + eps, f)))
+        return nb.sum(nb.broadcast(nb.add, t1, t2))
+    return obj
+
+
+def mlp_prior_objective(nb, lam, nlayers):
+    """The batch-independent part of ``mlp_log_joint``: the log-prior (examples/mlp.jl:61-65)."""
+    def obj(*params):
+        W, b = params[:nlayers], params[nlayers:]
+        log_prior = 0.0
+        for Wn, bn in zip(W, b):
+            log_prior = log_prior + (nb.sum(nb.abs2, Wn) + nb.sum(nb.abs2, bn))
+        return log_prior * (-0.5 * lam)
+    return obj
+
+
 def mlp_objective(nb, X, Y, lam, nlayers, prior_scale=1.0, eps=1e-15):
     """Scalar objective of the parameters (W1..Wn, b1..bn) for ``nabla``.  ``prior_scale`` = 1/G
     when the batch is sharded over G ranks so the allreduce-sum counts the prior once

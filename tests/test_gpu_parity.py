@@ -664,3 +664,28 @@ def test_gemm_tensor_core_modes(nb, ctx, mode, tol):
                         assert err < tol, f"{mode} {tA}{tB} {m}x{n}x{k} alpha={alpha} beta={beta}: rel err {err:.3e}"
     finally:
         ctx.math_mode = old
+
+
+def test_overlapped_sharded_gradient_single_rank_is_bitwise_the_plain_sweep(nb, ctx):
+    """data objective + shared objective evaluated as two sweeps (the multi-GPU path, nranks = 1 here)
+    launches the same kernels in the same accumulation order as ∇(mlp_log_joint): bitwise equal."""
+    import nabla_jl_b200.workloads as wl
+    dims, B = (20, 16, 12, 10), 64
+    W, b, X, Y = wl.mlp_inputs(dims, B, np.float64, seed=0)
+    Xd, Yd = ctx.asarray(X), ctx.asarray(Y)
+    params = [ctx.asarray(p) for p in (*W, *b)]
+    yr, gr = nb.nabla(wl.mlp_objective(nb, Xd, Yd, 1e-3, 3), get_output=True)(*params)
+    comm = nb.Communicator(ctx, 0, 1, None)
+    og = nb.OverlappedShardedGradient(wl.mlp_data_objective(nb, Xd, Yd, 3), wl.mlp_prior_objective(nb, 1e-3, 3),
+                                      params, comm)
+    y, g = og.step()
+    np.testing.assert_allclose(float(_np(y)), float(_np(yr)), rtol=1e-15)
+    for a, r in zip(g, gr):
+        np.testing.assert_array_equal(_np(a), _np(r))
+    # the hook fires once per parameter, in descending order of each Leaf's first consumer
+    t = nb.Tape()
+    leaves = [nb.Leaf(t, p) for p in params]
+    yn = wl.mlp_data_objective(nb, Xd, Yd, 3)(*leaves)
+    order = []
+    nb.propagate(t, nb.reverse_tape(yn, nb.oneslike(yn)), on_final=lambda pos, rvs: order.append(pos))
+    assert sorted(order) == [l.pos for l in leaves] and order[0] in (leaves[2].pos, leaves[5].pos)

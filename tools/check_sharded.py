@@ -43,6 +43,19 @@ for capture in (False, True):
         print(f"world={world} capture={capture}: max rel grad err {err:.3e}, objective rel err {yerr:.3e}", flush=True)
         assert err < 1e-10 and yerr < 1e-10
     dist.barrier()
+# overlapped variant: per-parameter allreduce on the communicator stream while the sweep continues
+og = nb.OverlappedShardedGradient(wl.mlp_data_objective(nb, Xd, Yd, 3), wl.mlp_prior_objective(nb, 1e-3, 3), params, comm)
+for it in range(2):
+    y, grads = og.step()
+ctx.sync()
+if rank == 0:
+    Xf, Yf = ctx.asarray(X), ctx.asarray(Y)
+    yr, gr = nb.nabla(wl.mlp_objective(nb, Xf, Yf, 1e-3, 3), get_output=True)(*params)
+    err = max(np.linalg.norm(g.numpy() - r.numpy()) / np.linalg.norm(r.numpy()) for g, r in zip(grads, gr))
+    yerr = abs(float(y.numpy()) - float(nb.unbox(yr).numpy())) / abs(float(nb.unbox(yr).numpy()))
+    print(f"world={world} overlapped: max rel grad err {err:.3e}, objective rel err {yerr:.3e}", flush=True)
+    assert err < 1e-10 and yerr < 1e-10
+dist.barrier()
 comm.close()
 dist.destroy_process_group()
 if rank == 0:
