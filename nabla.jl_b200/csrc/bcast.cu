@@ -788,6 +788,7 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
   if (C.ysaved)
     for (int d = 0; d < NB_MAX_DIMS; ++d)
       NB_REQUIRE(ctx, ext_of(C.ysaved, d) == F[d], NB_ERR_SHAPE, "y_saved must have the full shape");
+  for (int k = 0; k < C.nout; ++k) nb_note_write(ctx, C.outs[k]->data);
   int64_t total = 1;
   for (int d = 0; d < NB_MAX_DIMS; ++d) total *= F[d];
   if (total == 0) {
@@ -1095,6 +1096,7 @@ int32_t nb_bcast_pullback(nb_ctx* ctx, const nb_prog* prog, const nb_tensor* yba
 int32_t nb_fill(nb_ctx* ctx, void* dst, int32_t dtype, uint64_t count, double value) {
   NB_REQUIRE(ctx, ctx && (dst || !count), NB_ERR_INVALID, "NULL argument");
   if (!count) return NB_OK;
+  nb_note_write(ctx, dst);
   int64_t blocks = (count + 1023) / 1024;
   if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
   if (dtype == NB_F32) k_fill<float><<<(unsigned)blocks, 256, 0, ctx->stream>>>((float*)dst, count, (float)value);

@@ -89,6 +89,7 @@ int32_t nb_allreduce_sum(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const i
   if (ctx->nranks == 1 && !ctx->nccl_comm) return NB_OK;  // single rank: the sum is the identity
   NB_REQUIRE(ctx, ctx->nccl_comm, NB_ERR_COMM, "nb_allreduce_sum: nb_comm_init was not called");
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  for (int i = 0; i < n_bufs; ++i) nb_note_write(ctx, bufs[i]);
   ncclResult_t r = api().GroupStart();
   if (r != 0) return nccl_fail(ctx, "ncclGroupStart", r);
   for (int i = 0; i < n_bufs; ++i) {
@@ -108,6 +109,7 @@ int32_t nb_allreduce_sum(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const i
 static int32_t reduce_on(nb_ctx* ctx, cudaStream_t st, int32_t n_bufs, void* const* bufs, const int64_t* counts,
                          int32_t dtype) {
   ncclComm_t comm = (ncclComm_t)ctx->nccl_comm;
+  for (int i = 0; i < n_bufs; ++i) nb_note_write(ctx, bufs[i]);
   ncclResult_t r = api().GroupStart();
   if (r != 0) return nccl_fail(ctx, "ncclGroupStart", r);
   for (int i = 0; i < n_bufs; ++i) {

@@ -88,6 +88,13 @@ static inline int32_t nb_fail(nb_ctx* ctx, int32_t code, const std::string& msg)
 
 static inline size_t nb_dtype_size(int32_t dt) { return dt == NB_F64 ? 8 : 4; }
 
+// Operand-split cache of the tensor-core GEMM (gemm_tc.cu): every array of a sweep is multiplied twice
+// (W in the forward product and in W'*Ybar, an activation in the forward product and in Ybar*h', Ybar in
+// both adjoints), so the hi/lo copies are kept until the source buffer is written or released.  Every
+// entry point that writes device memory reports the destination here.
+void nb_note_write(nb_ctx* ctx, const void* dst);
+void nb_split_cache_clear(nb_ctx* ctx);
+
 // internal allocator entry points (ctx.cu)
 int32_t nb_pool_alloc(nb_ctx* ctx, size_t nbytes, void** out);
 int32_t nb_pool_release(nb_ctx* ctx, void* p);

@@ -70,6 +70,16 @@ int32_t nb_pool_alloc(nb_ctx* ctx, size_t nbytes, void** out) {
 }
 
 int32_t nb_pool_release(nb_ctx* ctx, void* p) {
+  {
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->live.find(p);
+    if (it == ctx->live.end()) return nb_fail(ctx, NB_ERR_INVALID, "nb_release: unknown buffer");
+    if (it->second.refs > 1) {
+      --it->second.refs;
+      return NB_OK;
+    }
+  }
+  nb_note_write(ctx, p);  // the block is about to be recycled: cached splits of it are stale
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->live.find(p);
   if (it == ctx->live.end()) return nb_fail(ctx, NB_ERR_INVALID, "nb_release: unknown buffer");
@@ -224,6 +234,7 @@ int32_t nb_refcount(nb_ctx* ctx, void* buf, int32_t* out) {
 int32_t nb_h2d(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   if (!nbytes) return NB_OK;
+  nb_note_write(ctx, dst);
   NB_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += nbytes;
   return NB_OK;
@@ -247,6 +258,7 @@ int32_t nb_d2h(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
 int32_t nb_d2d(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   if (!nbytes) return NB_OK;
+  nb_note_write(ctx, dst);
   NB_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
   return NB_OK;
 }
@@ -268,6 +280,7 @@ int32_t nb_graph_begin(nb_ctx* ctx) {
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, !ctx->capturing, NB_ERR_INVALID, "nb_graph_begin: already capturing");
   NB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
+  nb_split_cache_clear(ctx);  // a replayed graph rewrites buffers without passing through the host
   NB_CUDA_OK(ctx, cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
   std::lock_guard<std::mutex> lk(ctx->mu);
   ctx->capturing = true;
@@ -280,6 +293,7 @@ int32_t nb_graph_begin(nb_ctx* ctx) {
 int32_t nb_graph_end(nb_ctx* ctx, nb_graph** out) {
   NB_REQUIRE(ctx, ctx && out, NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, ctx->capturing, NB_ERR_INVALID, "nb_graph_end: not capturing");
+  nb_split_cache_clear(ctx);
   uint32_t tag;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
@@ -309,6 +323,7 @@ int32_t nb_graph_end(nb_ctx* ctx, nb_graph** out) {
 
 int32_t nb_graph_launch(nb_ctx* ctx, nb_graph* g) {
   NB_REQUIRE(ctx, ctx && g && g->exec, NB_ERR_INVALID, "NULL argument");
+  nb_split_cache_clear(ctx);
   NB_CUDA_OK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
   ctx->stats.kernel_launches += g->launches_per_replay;
   return NB_OK;

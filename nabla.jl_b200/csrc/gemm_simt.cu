@@ -142,6 +142,7 @@ int32_t nb_gemm(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k
              "nb_gemm: leading dimension too small (DimensionMismatch)");
   if (m == 0 || n == 0) return NB_OK;
   NB_REQUIRE(ctx, A && B && C, NB_ERR_INVALID, "nb_gemm: NULL matrix");
+  nb_note_write(ctx, C);
   if (k == 0 || alpha == 0.0) {  // C = beta*C
     const int64_t tot = m * n;
     if (dtype == NB_F32) k_scale_mat<float><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(m, n, (float)beta, (float*)C, ldc);
@@ -168,6 +169,7 @@ int32_t nb_transpose(nb_ctx* ctx, int64_t m, int64_t n, const void* in, int64_t 
   NB_REQUIRE(ctx, ctx && (in || !(m * n)) && (out || !(m * n)), NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, ld_in >= m && ld_out >= n, NB_ERR_SHAPE, "nb_transpose: leading dimension too small");
   if (m == 0 || n == 0) return NB_OK;
+  nb_note_write(ctx, out);
   dim3 grid((unsigned)((m + 31) / 32), (unsigned)((n + 31) / 32));
   if (dtype == NB_F32) k_transpose<float><<<grid, 256, 0, ctx->stream>>>(m, n, (const float*)in, ld_in, (float*)out, ld_out);
   else if (dtype == NB_F64) k_transpose<double><<<grid, 256, 0, ctx->stream>>>(m, n, (const double*)in, ld_in, (double*)out, ld_out);

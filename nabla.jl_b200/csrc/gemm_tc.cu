@@ -13,6 +13,10 @@
 //   * operands are staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzles) straight from the
 //     column-major arrays: a non-transposed A is "MN-major", a transposed A is "K-major" (the UMMA
 //     descriptors carry the major-ness, so no transposed copy of any operand is ever made).
+//   * tiles are handed out DYNAMICALLY: the producer thread takes the next tile index from a global
+//     atomic counter and publishes it to the MMA and epilogue roles through a 4-slot shared-memory ring
+//     (mbarrier full/empty), so a CTA that starts late or shares its SM with an NCCL kernel (the
+//     overlapped allreduce) simply processes fewer tiles instead of delaying the whole GEMM.
 //   * accumulators live in TMEM (2 x BN columns, double-buffered so the epilogue of chunk i overlaps
 //     the main loop of chunk i+1); smem ring of STAGES stages guarded by full/empty mbarriers;
 //     tcgen05.commit releases smem stages and publishes finished accumulators.
@@ -71,7 +75,10 @@ struct GemmArgs {
   float* C;
   int64_t ldc;
   int32_t tiles_m, tiles_n;
+  int32_t* tile_counter;  // zeroed before the launch; next tile index to hand out
 };
+
+constexpr int SCHED_SLOTS = 4;
 
 // Tile rasterisation: groups of GROUP_M tile-rows are swept along n with m fastest inside the group,
 // so the ~148 tiles in flight form a compact GROUP_M x ~9 block whose operand panels (per K chunk) stay
@@ -196,7 +203,7 @@ struct Cfg {
   static constexpr uint32_t NSPLIT = KindT<KIND>::NSPLIT;
   static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * NSPLIT;
   static constexpr int STAGES = (int)(196608u / STAGE_BYTES);  // 192 KB of operand ring
-  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 /*align*/ + 512 /*barriers, tile ring*/;
   static constexpr uint32_t TMEM_COLS = 2 * BN;  // two accumulator stages
 };
 
@@ -216,7 +223,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   uint64_t* empty = bars + STAGES;           // [STAGES]
   uint64_t* tfull = bars + 2 * STAGES;       // [2]
   uint64_t* tempty = bars + 2 * STAGES + 2;  // [2]
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  uint64_t* sfull = bars + 2 * STAGES + 4;                 // [SCHED_SLOTS] tile index published
+  uint64_t* sempty = bars + 2 * STAGES + 4 + SCHED_SLOTS;  // [SCHED_SLOTS] tile index consumed by all readers
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4 + 2 * SCHED_SLOTS);
+  volatile int32_t* sched_tile = (volatile int32_t*)(tmem_slot + 2);  // [SCHED_SLOTS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = g.tiles_m * g.tiles_n;
@@ -225,6 +235,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 128); }
+    for (int q = 0; q < SCHED_SLOTS; ++q) { mbar_init(&sfull[q], 1); mbar_init(&sempty[q], 1 + 128); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {  // TMEM allocation is warp-collective; this warp also frees it
@@ -240,11 +251,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   if (warp == 0) {
     // ===================== TMA producer =====================
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int s = 0, q = 0;
+      uint32_t ph = 0, qph = 0;
+      int t = atomicAdd(g.tile_counter, 1);
+      for (;;) {
+        // tile scheduler: publish this tile (a sentinel >= ntiles ends every role) and request the next
+        // one right away, so the atomic's round trip is hidden behind this tile's loads
+        mbar_wait(&sempty[q], qph ^ 1);
+        sched_tile[q] = t;
+        mbar_arrive(&sfull[q]);
+        if (++q == SCHED_SLOTS) { q = 0; qph ^= 1; }
+        if (t >= ntiles) break;
+        const int t_cur = t;
+        t = atomicAdd(g.tile_counter, 1);
         int tm, tn;
-        tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+        tile_coords(t_cur, g.tiles_m, g.tiles_n, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
         for (int kb = 0; kb < nkb; ++kb) {  // chunk boundaries do not concern the producer
           mbar_wait(&empty[s], ph ^ 1);
@@ -281,9 +302,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
                              ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_kstep = g.a_mn ? KT::MN_KSTEP : 32u;  // K-major: UMMA_K elements = 32 bytes
       const uint32_t b_kstep = g.b_mn ? KT::MN_KSTEP : 32u;
-      int s = 0, a = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+      int s = 0, a = 0, q = 0;
+      uint32_t ph = 0, aph = 0, qph = 0;
+      for (;;) {
+        mbar_wait(&sfull[q], qph);
+        const int t = sched_tile[q];
+        mbar_arrive(&sempty[q]);
+        if (++q == SCHED_SLOTS) { q = 0; qph ^= 1; }
+        if (t >= ntiles) break;
         for (int kb0 = 0; kb0 < nkb; kb0 += KT::KCHUNK / BK) {
           const int kb1 = min(nkb, kb0 + KT::KCHUNK / BK);
           mbar_wait(&tempty[a], aph ^ 1);
@@ -318,10 +344,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   } else {
     // ===================== epilogue (warps 2..5) =====================
     const int q = warp & 3;  // TMEM lane quadrant this warp may access
-    int a = 0;
-    uint32_t aph = 0;
+    int a = 0, sq = 0;
+    uint32_t aph = 0, sqph = 0;
     const float alpha = g.alpha;
-    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+    for (;;) {
+      mbar_wait(&sfull[sq], sqph);
+      const int t = sched_tile[sq];
+      mbar_arrive(&sempty[sq]);
+      if (++sq == SCHED_SLOTS) { sq = 0; sqph ^= 1; }
+      if (t >= ntiles) break;
       int tm, tn;
       tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
       const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
@@ -430,8 +461,22 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+struct SplitEntry {
+  const void* src;
+  int64_t rows, cols, ld_in, ld_out;
+  int kind;
+  void* hi;
+  void* lo;
+  uint64_t stamp;
+};
+
 struct GemmState {
   EncodeTiledFn encode = nullptr;
+  int32_t* tile_counter = nullptr;  // device word shared by the (stream-ordered) GEMM launches of the ctx
+  std::mutex cache_mu;              // nb_release may arrive from a finalizer thread
+  std::vector<SplitEntry> cache;    // LRU by stamp
+  uint64_t clock = 0;
+  size_t max_entries = 24;
 };
 
 GemmState* state_of(nb_ctx* ctx) {
@@ -444,6 +489,10 @@ GemmState* state_of(nb_ctx* ctx) {
       st->encode = (EncodeTiledFn)fn;
     else
       cudaGetLastError();
+    if (cudaMalloc(&st->tile_counter, 256) != cudaSuccess) {
+      cudaGetLastError();
+      st->encode = nullptr;
+    }
     ctx->gemm_state = st;
   }
   return (GemmState*)ctx->gemm_state;
@@ -472,6 +521,7 @@ int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   }
   const int ntiles = g.tiles_m * g.tiles_n;
   const int grid = ntiles < ctx->num_sms ? ntiles : ctx->num_sms;
+  NB_CUDA_OK(ctx, cudaMemsetAsync(g.tile_counter, 0, sizeof(int32_t), ctx->stream));
   kern<<<grid, NTHREADS, C_::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
@@ -493,9 +543,83 @@ int32_t run_split(nb_ctx* ctx, const float* x, int64_t rows, int64_t cols, int64
   return NB_OK;
 }
 
+// returns the cached split of (src, rows, cols, ld_in) or creates it; the entry owns hi/lo
+int32_t get_split(nb_ctx* ctx, GemmState* st, int kind, const float* src, int64_t rows, int64_t cols, int64_t ld_in,
+                  int64_t ld_out, int esize, void** hi, void** lo) {
+  const bool use_cache = !ctx->capturing;
+  if (use_cache) {
+    std::lock_guard<std::mutex> lk(st->cache_mu);
+    for (auto& e : st->cache)
+      if (e.src == src && e.rows == rows && e.cols == cols && e.ld_in == ld_in && e.kind == kind) {
+        e.stamp = ++st->clock;
+        *hi = e.hi; *lo = e.lo;
+        return NB_OK;
+      }
+  }
+  const size_t bytes = (size_t)(ld_out * cols) * esize;
+  int32_t rc = nb_pool_alloc(ctx, bytes, hi);
+  if (rc != NB_OK) return rc;
+  rc = nb_pool_alloc(ctx, bytes, lo);
+  if (rc != NB_OK) { nb_pool_release(ctx, *hi); return rc; }
+  if (kind == KIND_BF16X3)
+    rc = run_split<__nv_bfloat16>(ctx, src, rows, cols, ld_in, (__nv_bfloat16*)*hi, (__nv_bfloat16*)*lo, ld_out);
+  else
+    rc = run_split<float>(ctx, src, rows, cols, ld_in, (float*)*hi, (float*)*lo, ld_out);
+  if (rc != NB_OK) { nb_pool_release(ctx, *hi); nb_pool_release(ctx, *lo); return rc; }
+  if (use_cache) {
+    std::vector<std::pair<void*, void*>> evict;
+    {
+      std::lock_guard<std::mutex> lk(st->cache_mu);
+      if (st->cache.size() >= st->max_entries) {
+        size_t v = 0;
+        for (size_t i = 1; i < st->cache.size(); ++i)
+          if (st->cache[i].stamp < st->cache[v].stamp) v = i;
+        evict.push_back({st->cache[v].hi, st->cache[v].lo});
+        st->cache.erase(st->cache.begin() + v);
+      }
+      st->cache.push_back(SplitEntry{src, rows, cols, ld_in, ld_out, kind, *hi, *lo, ++st->clock});
+    }
+    for (auto& pr : evict) { nb_pool_release(ctx, pr.first); nb_pool_release(ctx, pr.second); }
+  }
+  return NB_OK;
+}
+
 }  // namespace
 
+// A device buffer is about to be written (or recycled): cached splits of it are stale.
+void nb_note_write(nb_ctx* ctx, const void* dst) {
+  GemmState* st = (GemmState*)ctx->gemm_state;
+  if (!st || !dst) return;
+  std::vector<std::pair<void*, void*>> drop;
+  {
+    std::lock_guard<std::mutex> lk(st->cache_mu);
+    if (st->cache.empty()) return;
+    for (size_t i = 0; i < st->cache.size();) {
+      if (st->cache[i].src == dst) {
+        drop.push_back({st->cache[i].hi, st->cache[i].lo});
+        st->cache.erase(st->cache.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+  }
+  for (auto& pr : drop) { nb_pool_release(ctx, pr.first); nb_pool_release(ctx, pr.second); }
+}
+
+void nb_split_cache_clear(nb_ctx* ctx) {
+  GemmState* st = (GemmState*)ctx->gemm_state;
+  if (!st) return;
+  std::vector<SplitEntry> all;
+  {
+    std::lock_guard<std::mutex> lk(st->cache_mu);
+    all.swap(st->cache);
+  }
+  for (auto& e : all) { nb_pool_release(ctx, e.hi); nb_pool_release(ctx, e.lo); }
+}
+
 void nb_gemm_state_free(nb_ctx* ctx) {
+  nb_split_cache_clear(ctx);
+  if (ctx->gemm_state && ((GemmState*)ctx->gemm_state)->tile_counter) cudaFree(((GemmState*)ctx->gemm_state)->tile_counter);
   delete (GemmState*)ctx->gemm_state;
   ctx->gemm_state = nullptr;
 }
@@ -528,33 +652,21 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
   const int esize = kind == KIND_BF16X3 ? 2 : 4;
   const void* src[4] = {A, A, B, B};  // A hi, A lo, B hi, B lo
   int64_t ld_a = lda, ld_b = ldb;
-  void* tmp[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* tmp[4] = {nullptr, nullptr, nullptr, nullptr};  // uncached splits (graph capture): released below
   if (kind != KIND_TF32) {
-    const int64_t pad = 16 / esize * 1;  // leading dimensions of the split copies: 16-byte multiples
+    const int64_t pad = 16 / esize;  // leading dimensions of the split copies: 16-byte multiples
     ld_a = (a_r + pad - 1) / pad * pad;
     ld_b = (b_r + pad - 1) / pad * pad;
-    for (int i = 0; i < 4; ++i) {
-      const size_t bytes = (size_t)(i < 2 ? ld_a * a_c : ld_b * b_c) * esize;
-      int32_t rc = nb_pool_alloc(ctx, bytes, &tmp[i]);
-      if (rc != NB_OK) {
-        for (int j = 0; j < i; ++j) nb_pool_release(ctx, tmp[j]);
-        return rc;
-      }
-      src[i] = tmp[i];
-    }
-    int32_t rc;
-    if (kind == KIND_BF16X3) {
-      rc = run_split<__nv_bfloat16>(ctx, A, a_r, a_c, lda, (__nv_bfloat16*)tmp[0], (__nv_bfloat16*)tmp[1], ld_a);
-      if (rc == NB_OK)
-        rc = run_split<__nv_bfloat16>(ctx, B, b_r, b_c, ldb, (__nv_bfloat16*)tmp[2], (__nv_bfloat16*)tmp[3], ld_b);
-    } else {
-      rc = run_split<float>(ctx, A, a_r, a_c, lda, (float*)tmp[0], (float*)tmp[1], ld_a);
-      if (rc == NB_OK) rc = run_split<float>(ctx, B, b_r, b_c, ldb, (float*)tmp[2], (float*)tmp[3], ld_b);
-    }
+    void *ah, *al, *bh, *bl;
+    int32_t rc = get_split(ctx, st, kind, A, a_r, a_c, lda, ld_a, esize, &ah, &al);
+    if (rc != NB_OK) return rc;
+    rc = get_split(ctx, st, kind, B, b_r, b_c, ldb, ld_b, esize, &bh, &bl);
     if (rc != NB_OK) {
-      for (int i = 0; i < 4; ++i) nb_pool_release(ctx, tmp[i]);
+      if (ctx->capturing) { nb_pool_release(ctx, ah); nb_pool_release(ctx, al); }
       return rc;
     }
+    src[0] = ah; src[1] = al; src[2] = bh; src[3] = bl;
+    if (ctx->capturing) { tmp[0] = ah; tmp[1] = al; tmp[2] = bh; tmp[3] = bl; }
   }
   const CUtensorMapDataType dt = kind == KIND_BF16X3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
   const uint32_t bk = 128 / esize, mnc = 128 / esize;
@@ -581,6 +693,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     g.C = C; g.ldc = ldc;
     g.tiles_m = (int32_t)((m + BM - 1) / BM);
     g.tiles_n = (int32_t)((n + BN - 1) / BN);
+    g.tile_counter = st->tile_counter;
     if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
     else if (kind == KIND_3XTF32) rc = BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
     else rc = BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);

@@ -689,3 +689,34 @@ def test_overlapped_sharded_gradient_single_rank_is_bitwise_the_plain_sweep(nb, 
     order = []
     nb.propagate(t, nb.reverse_tape(yn, nb.oneslike(yn)), on_final=lambda pos, rvs: order.append(pos))
     assert sorted(order) == [l.pos for l in leaves] and order[0] in (leaves[2].pos, leaves[5].pos)
+
+
+def test_split_cache_is_invalidated_by_every_writer(nb, ctx):
+    """The tensor-core GEMM caches the hi/lo copies of its operands; any write to an operand (H2D copy,
+    a kernel output, a GEMM output, buffer recycling) must drop the cached copy."""
+    from nabla_jl_b200 import kernels as K
+    rng = np.random.default_rng(8)
+    m = n = k = 256
+    A = rng.standard_normal((m, k)).astype(np.float32)
+    B = rng.standard_normal((k, n)).astype(np.float32)
+    Ad, Bd, Cd = ctx.asarray(A), ctx.asarray(B), ctx.empty((m, n), np.float32)
+
+    def check(Ah, Bh):
+        K.gemm("N", "N", 1.0, Ad, Bd, 0.0, Cd, m, n, k)
+        ref = Ah.astype(np.float64) @ Bh.astype(np.float64)
+        err = np.linalg.norm(Cd.numpy() - ref) / np.linalg.norm(ref)
+        assert err < 1e-4, err
+
+    check(A, B)
+    check(A, B)                                   # served from the cache
+    A2 = rng.standard_normal((m, k)).astype(np.float32)
+    Ad.copy_from_host(A2)                         # H2D into the cached source
+    check(A2, B)
+    K.bcast_reduce(None, [Ad], Bd, scale=2.0)     # a kernel writes the other operand (B = 2 A2; m == k == n)
+    check(A2, 2 * A2)
+    K.gemm("N", "N", 1.0, Bd, Bd, 0.0, Ad, m, n, k)   # a GEMM output overwrites a cached source
+    A3 = (2 * A2).astype(np.float64) @ (2 * A2).astype(np.float64)
+    check(A3.astype(np.float32), 2 * A2)
+    del Ad                                        # recycle the block, then reuse it with new contents
+    Ad = ctx.asarray(A)
+    check(A, 2 * A2)
