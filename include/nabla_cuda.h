@@ -179,6 +179,17 @@ int32_t nb_ger(nb_ctx* ctx, int64_t m, int64_t n, double alpha, const void* x, c
 int32_t nb_transpose(nb_ctx* ctx, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
                      int64_t ld_out, int32_t dtype);
 
+/* ---- array structure --------------------------------------------------- */
+/* dst[dst_off + r + c*ld_dst] (+)= src[src_off + r + c*ld_src] for r < rows, c < cols (offsets in elements):
+ * hcat / vcat forward and their pullbacks `copy(selectdim(ybar, ...))` (chainrules_ignored.jl:12-40),
+ * range getindex forward and its pullback (indexing.jl:3-11; ChainRules rrule(getindex)). */
+int32_t nb_copy2d(nb_ctx* ctx, int64_t rows, int64_t cols, const void* src, int64_t src_off, int64_t ld_src,
+                  void* dst, int64_t dst_off, int64_t ld_dst, int32_t dtype, int32_t accumulate);
+/* dst[i] = src[idx[i]] and dst[idx[i]] += src[i] (0-based device index vector; duplicates accumulate,
+ * test/sensitivities/indexing.jl "Overlapping indices (#139)") — getindex with an index vector. */
+int32_t nb_gather(nb_ctx* ctx, int64_t n, const void* src, const int64_t* idx_dev, void* dst, int32_t dtype);
+int32_t nb_scatter_add(nb_ctx* ctx, int64_t n, const void* src, const int64_t* idx_dev, void* dst, int32_t dtype);
+
 /* ---- batch-sharded gradients (new capability) ----------------------------- */
 int32_t nb_comm_unique_id(uint8_t id_out[128]);
 int32_t nb_comm_init(nb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id[128]);

@@ -35,6 +35,7 @@ __all__ = [
     "sum", "mean", "dot", "matmul", "transpose", "adjoint", "gemm", "gemv", "fmad",
     "broadcastsum", "broadcastsum_inplace", "Dual", "Ref", "Thunk", "InplaceableThunk",
     "unthunk", "add_bang_bang", "check_errs", "oneslike", "zeroslike",
+    "hcat", "vcat", "getindex", "reshape", "fill", "checkpoint", "R", "colon",
 ]
 
 _pysum = sum
@@ -1200,6 +1201,158 @@ def _power(a, b):
     if _isarr(a) or _isarr(b):
         raise TypeError("MethodError: ^ on arrays is out of scope; use broadcast")
     return pow_(a, b)  # noqa: F821
+
+
+# --------------------------------------------------------------------------------------------
+# Array structure: hcat / vcat / getindex / reshape / fill, and gradient checkpointing
+# 
+# --------------------------------------------------------------------------------------------
+class R:
+    """Julia's ``lo:hi`` (1-based, inclusive)."""
+
+    def __init__(self, lo, hi):
+        self.lo, self.hi = int(lo), int(hi)
+
+    def __len__(self):
+        return max(self.hi - self.lo + 1, 0)
+
+
+colon = R(1, -1)  # ``:`` — resolved against the indexed extent
+
+
+def _col2(a):
+    a = np.asarray(a)
+    return a.reshape(a.shape[0], 1) if a.ndim == 1 else a
+
+
+def _grad_hcat(n, p, y, ybar, *A):
+    # chainrules_ignored.jl:14-26: copy(u > l+1 ? selectdim(ȳ, 2, l+1:u) : selectdim(ȳ, 2, u))
+    i = n - 1
+    l = _pysum(_col2(A[j]).shape[1] for j in range(i))
+    u = l + _col2(A[i]).shape[1]
+    yb = np.asarray(unthunk(ybar))
+    return yb[:, l:u].copy() if u > l + 1 else yb[:, u - 1].copy()
+
+
+def _grad_vcat(n, p, y, ybar, *A):
+    # chainrules_ignored.jl:29-40: copy(selectdim(ȳ, 1, l+1:u))
+    i = n - 1
+    l = _pysum(np.shape(A[j])[0] for j in range(i))
+    u = l + np.shape(A[i])[0]
+    return np.asarray(unthunk(ybar))[l:u].copy()
+
+
+_hcat = Primitive("hcat", forward=lambda *A: np.hstack([_col2(a) for a in A]), grads={"any": _grad_hcat})
+_vcat = Primitive("vcat", forward=lambda *A: np.concatenate([np.asarray(a) for a in A], axis=0),
+                  grads={"any": _grad_vcat})
+
+
+def hcat(*A):
+    return _hcat(*A)
+
+
+def vcat(*A):
+    return _vcat(*A)
+
+
+def _np_index(shape, idx):
+    """Julia index tuple -> NumPy index (0-based); ints drop their dimension like Julia."""
+    if len(idx) == 1 and len(shape) > 1:  # linear indexing into a column-major array
+        raise TypeError("MethodError: linear indexing of matrices is not intercepted here")
+    out = []
+    for d, ix in enumerate(idx):
+        ext = shape[d]
+        if isinstance(ix, R):
+            hi = ext if ix is colon else ix.hi
+            lo = 1 if ix is colon else ix.lo
+            if lo < 1 or hi > ext:
+                raise IndexError(f"BoundsError: attempt to access {shape} at index [{lo}:{hi}]")
+            out.append(slice(lo - 1, hi))
+        elif isinstance(ix, (int, np.integer)):
+            if ix < 1 or ix > ext:
+                raise IndexError(f"BoundsError: attempt to access {shape} at index [{ix}]")
+            out.append(int(ix) - 1)
+        else:
+            iv = np.asarray(ix, dtype=np.int64)
+            if iv.size and (iv.min() < 1 or iv.max() > ext):
+                raise IndexError(f"BoundsError: attempt to access {shape} at index {list(iv)}")
+            out.append(iv - 1)
+    return tuple(out)
+
+
+def _rrule_getindex(x, *idx):
+    # ChainRules rrule(getindex, x::Array, inds...): x̄ = zero(x); x̄[inds...] .+= ȳ (duplicates add, #139)
+    x = np.asarray(x)
+    ni = _np_index(x.shape, idx)
+    y = x[ni]
+
+    def pb(ybar):
+        def thunk():
+            xb = np.zeros_like(x, dtype=np.result_type(x.dtype, np.float64) if x.dtype.kind in "iu" else x.dtype)
+            np.add.at(xb, ni, unthunk(ybar))
+            return xb
+        return (None, Thunk(thunk)) + (None,) * len(idx)
+    return (y.copy() if isinstance(y, np.ndarray) else y), pb
+
+
+_getindex = Primitive("getindex", rrule=_rrule_getindex)
+
+
+def getindex(x, *idx):
+    return _getindex(x, *idx)
+
+
+def _rrule_reshape(x, *dims):
+    if len(dims) == 1 and isinstance(dims[0], (tuple, list)):
+        dims = tuple(dims[0])
+    shp = np.shape(x)
+    return np.reshape(x, dims, order="F"), (lambda ybar: (None, np.reshape(unthunk(ybar), shp, order="F")) + (None,) * len(dims))
+
+
+_reshape = Primitive("reshape", rrule=_rrule_reshape)
+
+
+def reshape(x, *dims):
+    return _reshape(x, *dims)
+
+
+def _rrule_fill(x, *dims):
+    if len(dims) == 1 and isinstance(dims[0], (tuple, list)):
+        dims = tuple(dims[0])
+    return np.full(dims, x, dtype=np.result_type(x, np.float64)), (lambda ybar: (None, np.sum(unthunk(ybar))) + (None,) * len(dims))
+
+
+_fill = Primitive("fill", rrule=_rrule_fill)
+
+
+def fill(x, *dims):
+    return _fill(x, *dims)
+
+
+def _checkpoint_forward(f, *xs, **kw):
+    return f(*xs, **kw)
+
+
+def _grad_checkpoint(n, p, y, ybar, f, *xs, **kw):
+    # checkpointing.jl:22-34: re-run f on an inner tape inside the outer reverse pass
+    t = Tape()
+    xs_ = [Leaf(t, x) for x in xs]
+    yi = f(*xs_, **kw)
+    if isinstance(yi, Node):
+        df = nabla(yi, unthunk(ybar))
+        return df[xs_[n - 2]] if df.isassigned(xs_[n - 2]) else _zero(xs[n - 2])
+    return _zero(xs[n - 2])
+
+
+_checkpoint = Primitive("checkpoint", forward=_checkpoint_forward, grads={"any": _grad_checkpoint})
+
+
+def checkpoint(f, args, kwargs=None):
+    """``checkpoint(f, args::Tuple[, kwargs::NamedTuple])`` (checkpointing.jl:10-20): ``f`` must not be a
+    closure."""
+    if getattr(f, "__closure__", None):
+        raise RuntimeError("f mustn't have fields. Can not checkpoint a closure or functor.")
+    return _checkpoint(f, *args, **(kwargs or {}))
 
 
 # --------------------------------------------------------------------------------------------

@@ -720,3 +720,88 @@ def test_split_cache_is_invalidated_by_every_writer(nb, ctx):
     del Ad                                        # recycle the block, then reuse it with new contents
     Ad = ctx.asarray(A)
     check(A, 2 * A2)
+
+
+# ---------------------------------------------------------------------------------------------
+# array structure and checkpointing
+# ---------------------------------------------------------------------------------------------
+def test_hcat_vcat_known_answers(nb):
+    # test/sensitivities/array.jl:13-19
+    rng = np.random.default_rng(0)
+    a, b, c = rng.random((3, 2)), rng.random(3), rng.random((3, 3))
+    g = nb.nabla(lambda a, b, c: nb.sum(nb.hcat(2 * a, 3 * b, 4 * c)))(a, b, c)
+    for got, ref in zip(g, (2 * np.ones((3, 2)), 3 * np.ones(3), 4 * np.ones((3, 3)))):
+        np.testing.assert_array_equal(_np(got), ref)
+    a, b, c = rng.random((2, 4)), rng.random((1, 4)), rng.random((3, 4))
+    g = nb.nabla(lambda a, b, c: nb.sum(nb.vcat(2 * a, 3 * b, 4 * c)))(a, b, c)
+    for got, ref in zip(g, (2 * np.ones((2, 4)), 3 * np.ones((1, 4)), 4 * np.ones((3, 4)))):
+        np.testing.assert_array_equal(_np(got), ref)
+    y = nb.hcat(nb.Leaf(nb.Tape(), a), c[:2])
+    np.testing.assert_array_equal(_np(y), np.hstack([a, c[:2]]))
+
+
+def test_getindex_known_answers(nb):
+    # test/sensitivities/indexing.jl: Int, Vector (range), overlapping indices (#139)
+    leaf = nb.Leaf(nb.Tape(), 5.0 * np.ones(5))
+    y = nb.getindex(leaf, 1)
+    assert float(_np(y)) == 5.0
+    np.testing.assert_array_equal(_np(nb.nabla(y, 1.0)[leaf]), [1, 0, 0, 0, 0])
+    x = nb.Leaf(nb.Tape(), 10.0 * np.ones(3))
+    y = nb.getindex(x, nb.R(2, 3))
+    np.testing.assert_array_equal(_np(y), [10, 10])
+    np.testing.assert_array_equal(_np(nb.nabla(y, np.ones(2))[x]), [0, 1, 1])
+    x = nb.Leaf(nb.Tape(), 10.0 * np.ones(3))
+    y = nb.getindex(x, [2, 3, 3])
+    np.testing.assert_array_equal(_np(y), [10, 10, 10])
+    np.testing.assert_array_equal(_np(nb.nabla(y, np.ones(3))[x]), [0, 1, 2])
+    with pytest.raises(IndexError):
+        nb.getindex(x, 4)
+
+
+def test_array_structure_parity(nb, orc):
+    rng = np.random.default_rng(21)
+    r = lambda *s: rng.standard_normal(s)
+    check_case(nb, orc, lambda ns, a, b, c: ns.hcat(a, b, c), [r(6, 2), r(6), r(6, 4)], r(6, 7))
+    check_case(nb, orc, lambda ns, a, b: ns.vcat(a, b), [r(2, 5), r(4, 5)], r(6, 5))
+    check_case(nb, orc, lambda ns, a, b: ns.vcat(a, b), [r(3), r(5)], r(8))
+    check_case(nb, orc, lambda ns, a: ns.getindex(a, ns.R(2, 4), ns.colon), [r(5, 6)], r(3, 6))
+    check_case(nb, orc, lambda ns, a: ns.getindex(a, ns.colon, 3), [r(5, 6)], r(5))
+    check_case(nb, orc, lambda ns, a: ns.getindex(a, 2, ns.R(2, 5)), [r(5, 6)], r(4))
+    check_case(nb, orc, lambda ns, a: ns.getindex(a, 4, 5), [r(5, 6)], 0.7)
+    check_case(nb, orc, lambda ns, a: ns.getindex(a, [7, 1, 7, 3]), [r(9)], r(4))
+    check_case(nb, orc, lambda ns, a: ns.reshape(a, 5, 4), [r(2, 10)], r(5, 4))   # array.jl:5-11
+    check_case(nb, orc, lambda ns, a: ns.reshape(a, (5, 4)), [r(2, 10)], r(5, 4))
+    check_case(nb, orc, lambda ns, s: ns.fill(s, 4, 4), [0.3], r(4, 4))            # array.jl:21-22
+    # a slice feeding further device work: minibatch columns of a data matrix
+    check_case(nb, orc, lambda ns, W, X: ns.sum(ns.broadcast(ns.tanh, ns.matmul(W, ns.getindex(X, ns.colon, ns.R(3, 9))))),
+               [r(4, 6), r(6, 12)])
+
+
+def _ck_layer(W, h, ns=None):
+    return ns.broadcast(ns.tanh, ns.matmul(W, h))
+
+
+def test_checkpoint(nb, orc):
+    # test/checkpointing.jl
+    x = 5.0
+    assert abs(float(_np(nb.checkpoint(nb.sin, (nb.as_device(x),)))) - math.sin(5.0)) < 1e-15   # device scalar in
+    (g,) = nb.nabla(lambda x: nb.checkpoint(nb.sin, (x,)))(x)
+    assert abs(float(_np(g)) - math.cos(5.0)) < 1e-15
+    foo_ck = lambda x: nb.cos(nb.checkpoint(nb.sin, (x,)))
+    foo = lambda x: nb.cos(nb.sin(x))
+    assert float(_np(nb.nabla(foo_ck)(x)[0])) == float(_np(nb.nabla(foo)(x)[0]))
+    y = 5.0
+    with pytest.raises(RuntimeError):
+        nb.checkpoint(lambda v: v + y, (x,))
+    # a checkpointed layer inside a model: same gradients, the layer's intermediates are not kept
+    rng = np.random.default_rng(2)
+    W1, W2, X = rng.standard_normal((8, 6)), rng.standard_normal((5, 8)), rng.standard_normal((6, 7))
+
+    Xd = nb.get_context().asarray(X)
+    # kwargs variant (checkpointing.jl:37-54): `ns` travels as a keyword, so `_ck_layer` is not a closure
+    g_ck = nb.nabla(lambda W1, W2: nb.sum(nb.matmul(W2, nb.checkpoint(_ck_layer, (W1, Xd), {"ns": nb}))))(W1, W2)
+    g_ref = orc.nabla(lambda W1, W2: orc.sum(orc.matmul(W2, orc.checkpoint(_ck_layer, (W1, X), {"ns": orc}))))(W1, W2)
+    g_plain = nb.nabla(lambda W1, W2: nb.sum(nb.matmul(W2, _ck_layer(W1, Xd, ns=nb))))(W1, W2)
+    for a, b_, c in zip(g_ck, g_ref, g_plain):
+        close(_np(a), b_)
+        np.testing.assert_array_equal(_np(a), _np(c))

@@ -273,3 +273,33 @@ def test_whole_models_check_errs():
     ref = 1 - np.tanh(A + bb[:, None]) ** 2
     np.testing.assert_allclose(gA, ref, rtol=1e-14)
     np.testing.assert_allclose(gb, ref.sum(1), rtol=1e-13)
+
+
+def test_array_structure_and_checkpoint_known_answers():
+    # test/sensitivities/array.jl:5-26, test/sensitivities/indexing.jl, test/checkpointing.jl
+    rng = np.random.default_rng(0)
+    a, b, c = rng.random((3, 2)), rng.random(3), rng.random((3, 3))
+    g = o.nabla(lambda a, b, c: o.sum(o.hcat(2 * a, 3 * b, 4 * c)))(a, b, c)
+    assert all((x == v).all() and x.shape == s for x, v, s in zip(g, (2, 3, 4), ((3, 2), (3,), (3, 3))))
+    a, b, c = rng.random((2, 4)), rng.random((1, 4)), rng.random((3, 4))
+    g = o.nabla(lambda a, b, c: o.sum(o.vcat(2 * a, 3 * b, 4 * c)))(a, b, c)
+    assert all((x == v).all() and x.shape == s for x, v, s in zip(g, (2, 3, 4), ((2, 4), (1, 4), (3, 4))))
+    leaf = o.Leaf(o.Tape(), 5.0 * np.ones(5))
+    y = o.getindex(leaf, 1)
+    assert o.unbox(y) == 5 and (o.nabla(y, 1.0)[leaf] == [1, 0, 0, 0, 0]).all()
+    x = o.Leaf(o.Tape(), 10.0 * np.ones(3))
+    y = o.getindex(x, o.R(2, 3))
+    assert (o.unbox(y) == [10, 10]).all() and (o.nabla(y, np.ones(2))[x] == [0, 1, 1]).all()
+    x = o.Leaf(o.Tape(), 10.0 * np.ones(3))
+    y = o.getindex(x, [2, 3, 3])          # overlapping indices (#139)
+    assert (o.unbox(y) == [10, 10, 10]).all() and (o.nabla(y, np.ones(3))[x] == [0, 1, 2]).all()
+    xr = rng.standard_normal((2, 10))
+    assert o.check_errs(lambda v: o.reshape(v, 5, 4), rng.standard_normal((5, 4)), xr, rng.standard_normal((2, 10)))
+    assert o.check_errs(lambda v: o.reshape(v, (5, 4)), rng.standard_normal((5, 4)), xr, rng.standard_normal((2, 10)))
+    assert o.check_errs(lambda v: o.fill(v, 4, 4), rng.standard_normal((4, 4)), rng.standard_normal(), rng.standard_normal())
+    assert o.checkpoint(o.sin, (5.0,)) == math.sin(5.0)
+    assert o.nabla(lambda v: o.checkpoint(o.sin, (v,)))(5.0) == (math.cos(5.0),)
+    assert o.nabla(lambda v: o.cos(o.checkpoint(o.sin, (v,))))(5.0) == o.nabla(lambda v: o.cos(o.sin(v)))(5.0)
+    yy = 5.0
+    with pytest.raises(RuntimeError):
+        o.checkpoint(lambda v: v + yy, (5.0,))
