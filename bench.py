@@ -126,6 +126,15 @@ def oracle_eval_seconds(dims, B_full, dtype, sample_cols, reps):
     return a + c * B_full, {"cols": list(sample_cols), "seconds": ts}
 
 
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU reference is entitled to every host core."""
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count() or 1)   # BLAS and OpenMP pools
+    except Exception:
+        pass
+
+
 def host_threads():
     try:
         from threadpoolctl import threadpool_info
@@ -144,6 +153,7 @@ def run_reference(args):
     dtype = np.float32 if args.dtype == "f32" else np.float64
     B = args.batch
     cols = (args.cpu_cols, 3 * args.cpu_cols)
+    use_all_host_threads()
     for _ in range(args.warmup):
         oracle_eval_seconds(WIDE_DIMS, B, dtype, cols, 1)
     t0 = time.perf_counter()
@@ -336,6 +346,7 @@ def run_gpu(args):
     peaks = load_peaks()
     dist = None
     if n > 1:
+        os.environ.setdefault("NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         import torch
         import torch.distributed as dist
         torch.cuda.set_device(local)
@@ -464,6 +475,7 @@ def run_gpu(args):
         "roofline": roof,
     }
     if rank == 0 and n == 1 and not args.no_cpu:
+        use_all_host_threads()
         sec, detail = oracle_eval_seconds(dims, B, dtype, (args.cpu_cols, 3 * args.cpu_cols), 2)
         line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "evals/s", "cores": host_threads(), "kind": "port",
                                 "sample": f"NumPy oracle (op-for-op port of the reference sweep) at B={args.cpu_cols} "
