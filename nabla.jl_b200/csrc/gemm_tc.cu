@@ -401,6 +401,243 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   }
 }
 
+// =================================================================================================
+// CTA-pair variant (cta_group::2): two CTAs of one cluster — two SMs of one TPC — share a 256 x 256
+// tile.  Each CTA stages its own 128 rows of A and its own 128 columns of B; one thread of the leader
+// issues tcgen05.mma.cta_group::2 (M = 256), which reads both halves of B through the pair's shared
+// memories and writes rows 0-127 / 128-255 of the accumulator into the two CTAs' TMEM.  Per CTA and K
+// block the smem traffic drops from 240 KB (144 KB of operand reads + 96 KB of TMA writes, above the
+// 128 B/clk port) to 160 KB, which is what capped the one-CTA kernel at ~75 % tensor-pipe activity.
+//   full[s]   (leader)      : both producers' TMA bytes (cta_group::2 loads signal the leader's barrier)
+//   empty[s]  (both CTAs)   : tcgen05.commit multicast to the pair
+//   tfull[a]  (both CTAs)   : tcgen05.commit multicast — each CTA drains its own TMEM half
+//   tempty[a] (leader)      : 256 epilogue threads (the peer's arrive remotely)
+// =================================================================================================
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  // non-.aligned forms: the role loops leave the lanes of warps 0 and 1 diverged
+  asm volatile("barrier.cluster.arrive.release;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(void* dst, const CUtensorMap* map, uint64_t* leader_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"((uint64_t)map), "r"(smem_u32(leader_bar) & PEER_BIT_MASK), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"((uint16_t)3)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}"
+      ::"r"(smem_u32(bar)), "r"(cta)
+      : "memory");
+}
+__device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                 uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
+struct Cfg2 {
+  static constexpr int BN = 256;                                  // pair tile: 256 x 256
+  static constexpr uint32_t A_BYTES = 128 * 128;                  // this CTA's 128 rows of A
+  static constexpr uint32_t B_BYTES = 128 * 128;                  // this CTA's 128 columns of B
+  static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * 2;  // hi + lo
+  static constexpr int STAGES = 3;
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 512;
+  static constexpr uint32_t TMEM_COLS = 512;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
+k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
+               const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1, const GemmArgs g) {
+  constexpr int KIND = KIND_BF16X3;
+  using KT = KindT<KIND>;
+  using C_ = Cfg2;
+  constexpr int STAGES = C_::STAGES, BN = C_::BN;
+  constexpr int BK = KT::BK, MNC = KT::MN_CHUNK;
+  constexpr uint32_t CHUNK_BYTES = KT::CHUNK_BYTES;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + STAGES * C_::STAGE_BYTES);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + STAGES;
+  uint64_t* tfull = bars + 2 * STAGES;
+  uint64_t* tempty = bars + 2 * STAGES + 2;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
+  const int ntiles = g.tiles_m * g.tiles_n;  // pair tiles (256 x 256)
+  const int nkb = (int)((g.K + BK - 1) / BK);
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 256); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                 "r"(C_::TMEM_COLS));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+  }
+  tc_fence_before();
+  cluster_sync_all();  // barriers of both CTAs initialised, TMEM allocated in both
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================== TMA producer (both CTAs, each its own halves) =====================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        int tm, tn;
+        tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+        const int m0 = tm * 256 + (int)rank * 128, n0 = tn * BN + (int)rank * 128;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          if (leader) mbar_expect_tx(&full[s], 2 * C_::STAGE_BYTES);  // both CTAs' bytes land on this barrier
+          uint8_t* st = smem + s * C_::STAGE_BYTES;
+          const int k0 = kb * BK;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            uint8_t* a_dst = st + h * C_::A_BYTES;
+            uint8_t* b_dst = st + 2 * C_::A_BYTES + h * C_::B_BYTES;
+            const CUtensorMap* ma = h ? &mA1 : &mA0;
+            const CUtensorMap* mb = h ? &mB1 : &mB0;
+            if (g.a_mn) {
+#pragma unroll
+              for (int c = 0; c < 128 / MNC; ++c)
+                tma_load_2d_pair(a_dst + c * CHUNK_BYTES, ma, &full[s], m0 + MNC * c, k0);
+            } else {
+              tma_load_2d_pair(a_dst, ma, &full[s], k0, m0);
+            }
+            if (g.b_mn) {
+#pragma unroll
+              for (int c = 0; c < 128 / MNC; ++c)
+                tma_load_2d_pair(b_dst + c * CHUNK_BYTES, mb, &full[s], n0 + MNC * c, k0);
+            } else {
+              tma_load_2d_pair(b_dst, mb, &full[s], k0, n0);
+            }
+          }
+          if (++s == STAGES) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer (leader CTA only) =====================
+    if (leader && lane == 0) {
+      const uint32_t idesc = (1u << 4) | (KT::FMT << 7) | (KT::FMT << 10) | ((uint32_t)g.a_mn << 15) |
+                             ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      const uint32_t a_kstep = g.a_mn ? KT::MN_KSTEP : 32u;
+      const uint32_t b_kstep = g.b_mn ? KT::MN_KSTEP : 32u;
+      int s = 0, a = 0;
+      uint32_t ph = 0, aph = 0;
+      for (int t = pair; t < ntiles; t += npairs) {
+        for (int kb0 = 0; kb0 < nkb; kb0 += KT::KCHUNK / BK) {
+          const int kb1 = min(nkb, kb0 + KT::KCHUNK / BK);
+          mbar_wait(&tempty[a], aph ^ 1);
+          tc_fence_after();
+          const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+          for (int kb = kb0; kb < kb1; ++kb) {
+            mbar_wait(&full[s], ph);
+            tc_fence_after();
+            const uint32_t st = smem_u32(smem + s * C_::STAGE_BYTES);
+            const uint32_t a_hi = st, a_lo = st + C_::A_BYTES;
+            const uint32_t b_hi = st + 2 * C_::A_BYTES, b_lo = b_hi + C_::B_BYTES;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+              const uint32_t ab = p == 0 ? a_lo : a_hi;
+              const uint32_t bb = p == 1 ? b_lo : b_hi;
+#pragma unroll
+              for (int kk = 0; kk < BK / KT::UMMA_K; ++kk) {
+                tc_mma_bf16_pair(d_tmem, make_desc<KIND>(ab + kk * a_kstep, g.a_mn),
+                                 make_desc<KIND>(bb + kk * b_kstep, g.b_mn), idesc,
+                                 (uint32_t)(((kb - kb0) | p | kk) != 0));
+              }
+            }
+            tc_commit_pair(&empty[s]);  // frees the stage in BOTH CTAs
+            if (++s == STAGES) { s = 0; ph ^= 1; }
+          }
+          tc_commit_pair(&tfull[a]);    // accumulator halves ready in both CTAs
+          if (++a == 2) { a = 0; aph ^= 1; }
+        }
+      }
+    }
+  } else {
+    // ===================== epilogue (warps 2..5 of both CTAs): this CTA's 128 rows =====================
+    const int q = warp & 3;
+    int a = 0;
+    uint32_t aph = 0;
+    const float alpha = g.alpha;
+    for (int t = pair; t < ntiles; t += npairs) {
+      int tm, tn;
+      tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+      const int64_t m0 = (int64_t)tm * 256 + (int64_t)rank * 128, n0 = (int64_t)tn * BN;
+      for (int kb0 = 0; kb0 < nkb; kb0 += KT::KCHUNK / BK) {
+        const float beta = kb0 == 0 ? g.beta : 1.f;
+        mbar_wait(&tfull[a], aph);
+        tc_fence_after();
+        const int64_t gm = m0 + q * 32 + lane;
+        const bool row_ok = gm < g.M;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t v[32];
+          tmem_ld32(tmem_base + (uint32_t)(a * BN + c * 32) + ((uint32_t)(q * 32) << 16), v);
+          const int64_t nb = n0 + c * 32;
+          if (nb < g.N && row_ok) {
+            float* cp = g.C + gm + nb * g.ldc;
+            const int jmax = (int)min((int64_t)32, g.N - nb);
+            if (beta == 0.f) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < jmax) cp[(int64_t)j * g.ldc] = alpha * __uint_as_float(v[j]);
+            } else {
+              float old[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) old[j] = j < jmax ? __ldcg(cp + (int64_t)j * g.ldc) : 0.f;
+#pragma unroll
+              for (int j = 0; j < 32; ++j)
+                if (j < jmax) cp[(int64_t)j * g.ldc] = alpha * __uint_as_float(v[j]) + beta * old[j];
+            }
+          }
+        }
+        tc_fence_before();
+        mbar_arrive_cta(&tempty[a], 0);  // the leader's barrier collects both CTAs' epilogues
+        if (++a == 2) { a = 0; aph ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  cluster_sync_all();  // neither CTA may exit (or free TMEM) while the pair still works
+  if (warp == 1) {
+    __syncwarp();
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(C_::TMEM_COLS));
+  }
+}
+
 // ---- operand splits: column-major (rows x cols, ld_in) -> hi, lo with leading dimension ld_out --------
 // tf32: hi = round-to-nearest tf32(x) (low 13 mantissa bits zero), lo = x - hi (exact), stored as f32
 __device__ __forceinline__ void split1(float x, float& hi, float& lo) {
@@ -527,6 +764,20 @@ int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   return NB_OK;
 }
 
+int32_t launch_pair(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
+  static bool attr_done = false;
+  if (!attr_done) {
+    NB_CUDA_OK(ctx, cudaFuncSetAttribute(k_gemm_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM));
+    attr_done = true;
+  }
+  const int ntiles = g.tiles_m * g.tiles_n;
+  const int max_pairs = ctx->num_sms / 2;
+  const int pairs = ntiles < max_pairs ? ntiles : max_pairs;
+  k_gemm_tc_pair<<<2 * pairs, NTHREADS, Cfg2::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
+  NB_LAUNCH_CHECK(ctx);
+  return NB_OK;
+}
+
 template <typename O>
 int32_t run_split(nb_ctx* ctx, const float* x, int64_t rows, int64_t cols, int64_t ld_in, O* hi, O* lo,
                   int64_t ld_out) {
@@ -649,6 +900,14 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     if (n <= 128) BN = 128;
     if (const char* e = getenv("NB_GEMM_BN")) BN = atoi(e) == 128 ? 128 : 256;
   }
+  // CTA-pair kernel (256 x 256 tiles) for BF16x3 when there are enough pair tiles to fill the 74 pairs
+  bool use_pair = false;
+  if (kind == KIND_BF16X3) {
+    const int64_t pt = ((m + 255) / 256) * ((n + 255) / 256);
+    use_pair = pt >= ctx->num_sms / 2;
+    if (const char* e = getenv("NB_GEMM_2CTA")) use_pair = atoi(e) != 0;
+    if (use_pair) BN = 256;
+  }
   const int esize = kind == KIND_BF16X3 ? 2 : 4;
   const void* src[4] = {A, A, B, B};  // A hi, A lo, B hi, B lo
   int64_t ld_a = lda, ld_b = ldb;
@@ -673,7 +932,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
   // MN-major -> inner dim is the MN extent, box {mnc, bk}; K-major -> inner dim k, box {bk, tile rows}
   const CUtensorMapSwizzle swz_mn = kind == KIND_BF16X3 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
   const uint32_t abox0 = a_mn ? mnc : bk, abox1 = a_mn ? bk : BM;
-  const uint32_t bbox0 = b_mn ? mnc : bk, bbox1 = b_mn ? bk : (uint32_t)BN;
+  const uint32_t bbox0 = b_mn ? mnc : bk, bbox1 = b_mn ? bk : (use_pair ? 128u : (uint32_t)BN);
   CUtensorMap maps[4];
   bool ok = true;
   for (int i = 0; i < 4 && ok; ++i) {
@@ -694,7 +953,10 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     g.tiles_m = (int32_t)((m + BM - 1) / BM);
     g.tiles_n = (int32_t)((n + BN - 1) / BN);
     g.tile_counter = st->tile_counter;
-    if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
+    if (use_pair) {
+      g.tiles_m = (int32_t)((m + 255) / 256);
+      rc = launch_pair(ctx, maps, g);
+    } else if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
     else if (kind == KIND_3XTF32) rc = BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
     else rc = BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);
   }
