@@ -179,6 +179,18 @@ int32_t nb_ger(nb_ctx* ctx, int64_t m, int64_t n, double alpha, const void* x, c
 int32_t nb_transpose(nb_ctx* ctx, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
                      int64_t ld_out, int32_t dtype);
 
+/* ---- symmetric / triangular BLAS family (blas.jl:60-328) -------------------
+ * nb_tri materialises the structured operand or finishes a pullback:
+ *   op 0/1  dst = tril(src) / triu(src); diag 0 keeps, 1 zeroes ('U' pullbacks), 2 sets the diagonal to one
+ *   op 2/3  dst = the symmetric matrix stored in the lower / upper triangle of src (symm, symv operands)
+ *   op 4/5  dst = tril / triu of (src + src' - Diagonal(src))            (symm pullback, blas.jl:78-80)
+ * nb_trsm overwrites B with alpha*op(A)^-1*B (side 'L') or alpha*B*op(A)^-1 (side 'R'), A triangular:
+ * BLAS.trsm; with n == 1 it is BLAS.trsv. */
+int32_t nb_tri(nb_ctx* ctx, int32_t op, int32_t diag, int64_t n, const void* src, int64_t ld_src, void* dst,
+               int64_t ld_dst, int32_t dtype);
+int32_t nb_trsm(nb_ctx* ctx, char side, char ul, char ta, char diag, int64_t m, int64_t n, double alpha,
+                const void* A, int64_t lda, void* B, int64_t ldb, int32_t dtype);
+
 /* ---- array structure --------------------------------------------------- */
 /* dst[dst_off + r + c*ld_dst] (+)= src[src_off + r + c*ld_src] for r < rows, c < cols (offsets in elements):
  * hcat / vcat forward and their pullbacks `copy(selectdim(ybar, ...))` (chainrules_ignored.jl:12-40),

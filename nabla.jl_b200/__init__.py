@@ -17,6 +17,7 @@ from .scalar import CATALOGUE, Program, ScalarFn, Sym, compile_scalar
 from .rules import (Ref, adjoint, broadcast, dot, gemm, gemv, ldivide, map_, mapfoldl, mapfoldr,
                     mapreduce, matmul, mean, sum, transpose)
 
+from .blasrules import symm, symv, trmm, trmv, trsm, trsv
 from .arrayrules import R, checkpoint, colon, fill, getindex, hcat, reshape, vcat
 from .sweep import (CapturedGradient, Communicator, OverlappedShardedGradient, ShardedGradient,
                     shard_bounds)

@@ -98,6 +98,8 @@ _SIGS = {
     "nb_gemv": ([_p, C.c_char, _i64, _i64, _dbl, _p, _i64, _p, _dbl, _p, _i32], _i32),
     "nb_ger": ([_p, _i64, _i64, _dbl, _p, _p, _dbl, _p, _i64, _i32], _i32),
     "nb_transpose": ([_p, _i64, _i64, _p, _i64, _p, _i64, _i32], _i32),
+    "nb_tri": ([_p, _i32, _i32, _i64, _p, _i64, _p, _i64, _i32], _i32),
+    "nb_trsm": ([_p, C.c_char, C.c_char, C.c_char, C.c_char, _i64, _i64, _dbl, _p, _i64, _p, _i64, _i32], _i32),
     "nb_copy2d": ([_p, _i64, _i64, _p, _i64, _i64, _p, _i64, _i64, _i32, _i32], _i32),
     "nb_gather": ([_p, _i64, _p, _p, _p, _i32], _i32),
     "nb_scatter_add": ([_p, _i64, _p, _p, _p, _i32], _i32),

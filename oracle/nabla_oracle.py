@@ -36,6 +36,7 @@ __all__ = [
     "broadcastsum", "broadcastsum_inplace", "Dual", "Ref", "Thunk", "InplaceableThunk",
     "unthunk", "add_bang_bang", "check_errs", "oneslike", "zeroslike",
     "hcat", "vcat", "getindex", "reshape", "fill", "checkpoint", "R", "colon",
+    "symm", "symv", "trmm", "trmv", "trsm", "trsv",
 ]
 
 _pysum = sum
@@ -1353,6 +1354,191 @@ def checkpoint(f, args, kwargs=None):
     if getattr(f, "__closure__", None):
         raise RuntimeError("f mustn't have fields. Can not checkpoint a closure or functor.")
     return _checkpoint(f, *args, **(kwargs or {}))
+
+
+# --------------------------------------------------------------------------------------------
+# Symmetric / triangular BLAS family (src/sensitivities/linalg/blas.jl:60-328)
+# --------------------------------------------------------------------------------------------
+def _U(c):
+    return str(c).upper()
+
+
+def _sym(ul, A):
+    A = np.asarray(A)
+    return np.tril(A) + np.tril(A, -1).T if _U(ul) == "L" else np.triu(A) + np.triu(A, 1).T
+
+
+def _tri(ul, dA, A):
+    A = np.asarray(A)
+    T = np.tril(A) if _U(ul) == "L" else np.triu(A)
+    if _U(dA) == "U":
+        T = T - np.diag(np.diag(T)) + np.eye(A.shape[0], dtype=A.dtype)
+    return T
+
+
+def _g(ul, M, dA="N"):
+    """``tril!``/``triu!`` (and a zeroed diagonal for unit-triangular operands)."""
+    M = np.tril(M) if _U(ul) == "L" else np.triu(M)
+    if _U(dA) == "U":
+        M = M - np.diag(np.diag(M))
+    return M
+
+
+def _op(ta, M):
+    return M if _U(ta) == "N" else M.T
+
+
+def _flip(ta):
+    return "T" if _U(ta) == "N" else "N"
+
+
+def _symm_raw(side, ul, alpha, A, B):
+    S = _sym(ul, A)
+    return alpha * (S @ B) if _U(side) == "L" else alpha * (B @ S)
+
+
+def _symm_split(rest):
+    return rest if len(rest) == 3 else (1.0,) + tuple(rest)
+
+
+def _symm_fwd(side, ul, *rest):
+    return _symm_raw(side, ul, *_symm_split(rest))
+
+
+def _symm_grad(n, p, Y, Yb, side, ul, *rest):
+    has_alpha = len(rest) == 3
+    alpha, A, B = _symm_split(rest)
+    Yb = unthunk(Yb)
+    k = n - 3 - (1 if has_alpha else 0)   # 0: A, 1: B
+    if has_alpha and n == 3:
+        return np.sum(Yb * Y) / alpha                                        # blas.jl:65-71
+    if k == 0:
+        B2, Yb2 = np.atleast_2d(B.T).T, np.atleast_2d(Yb.T).T
+        tmp = Yb2 @ B2.T if _U(side) == "L" else B2.T @ Yb2                   # blas.jl:78-80
+        return alpha * _g(ul, tmp + tmp.T - np.diag(np.diag(tmp)))
+    return _symm_raw(side, ul, alpha, A, Yb)                                 # blas.jl:95-101
+
+
+_symm = Primitive("symm", forward=_symm_fwd, grads={"any": _symm_grad})
+
+
+def symm(side, ul, *rest):
+    return _symm(side, ul, *rest)
+
+
+def _symv_fwd(ul, *rest):
+    alpha, A, x = _symm_split(rest)
+    return alpha * (_sym(ul, A) @ x)
+
+
+def _symv_grad(n, p, y, yb, ul, *rest):
+    has_alpha = len(rest) == 3
+    alpha, A, x = _symm_split(rest)
+    yb = unthunk(yb)
+    if has_alpha and n == 2:
+        return np.dot(yb, y) / alpha                                         # blas.jl:146-151
+    k = n - 2 - (1 if has_alpha else 0)
+    if k == 0:
+        tmp = np.outer(yb, x)                                                # symm rule with side 'L'
+        return alpha * _g(ul, tmp + tmp.T - np.diag(np.diag(tmp)))
+    return alpha * (_sym(ul, A) @ yb)
+
+
+_symv = Primitive("symv", forward=_symv_fwd, grads={"any": _symv_grad})
+
+
+def symv(ul, *rest):
+    return _symv(ul, *rest)
+
+
+def _trmm_raw(side, ul, ta, dA, alpha, A, B):
+    T = _op(ta, _tri(ul, dA, A))
+    return alpha * (T @ B) if _U(side) == "L" else alpha * (B @ T)
+
+
+def _trmm_grad(n, p, Y, Yb, side, ul, ta, dA, alpha, A, B):
+    Yb = unthunk(Yb)
+    if n == 5:
+        return np.sum(Yb * Y) / alpha
+    if n == 6:                                                               # blas.jl:217-231
+        if _U(side) == "L":
+            full = alpha * (Yb @ B.T) if _U(ta) == "N" else alpha * (B @ Yb.T)
+        else:
+            full = alpha * (B.T @ Yb) if _U(ta) == "N" else alpha * (Yb.T @ B)
+        return _g(ul, full, dA)
+    return _trmm_raw(side, ul, _flip(ta), dA, alpha, A, Yb)                  # blas.jl:232-244
+
+
+_trmm = Primitive("trmm", forward=_trmm_raw, grads={"any": _trmm_grad})
+
+
+def trmm(side, ul, ta, dA, alpha, A, B):
+    return _trmm(side, ul, ta, dA, alpha, A, B)
+
+
+def _trmv_raw(ul, ta, dA, A, b):
+    return _op(ta, _tri(ul, dA, A)) @ b
+
+
+def _trmv_grad(n, p, y, yb, ul, ta, dA, A, b):
+    yb = unthunk(yb)
+    if n == 4:                                                               # blas.jl:252-260
+        return _g(ul, np.outer(yb, b) if _U(ta) == "N" else np.outer(b, yb), dA)
+    return _trmv_raw(ul, _flip(ta), dA, A, yb)
+
+
+_trmv = Primitive("trmv", forward=_trmv_raw, grads={"any": _trmv_grad})
+
+
+def trmv(ul, ta, dA, A, b):
+    return _trmv(ul, ta, dA, A, b)
+
+
+def _trsm_raw(side, ul, ta, dA, alpha, A, X):
+    T = _op(ta, _tri(ul, dA, A))
+    X2 = np.atleast_2d(np.asarray(X).T).T
+    out = alpha * np.linalg.solve(T, X2) if _U(side) == "L" else alpha * np.linalg.solve(T.T, X2.T).T
+    return out.reshape(np.shape(X))
+
+
+def _trsm_grad(n, p, Y, Yb, side, ul, ta, dA, alpha, A, X):
+    Yb = unthunk(Yb)
+    if n == 5:
+        return np.sum(Yb * Y) / alpha
+    if n == 6:                                                               # blas.jl:280-294
+        Y2, Yb2 = np.atleast_2d(np.asarray(Y).T).T, np.atleast_2d(np.asarray(Yb).T).T
+        if _U(side) == "L":
+            full = (_trsm_raw("L", ul, "T", dA, -1.0, A, Yb2 @ Y2.T) if _U(ta) == "N"
+                    else _trsm_raw("R", ul, "T", dA, -1.0, A, Y2 @ Yb2.T))
+        else:
+            full = (_trsm_raw("R", ul, "T", dA, -1.0, A, Y2.T @ Yb2) if _U(ta) == "N"
+                    else _trsm_raw("L", ul, "T", dA, -1.0, A, Yb2.T @ Y2))
+        return _g(ul, full, dA)
+    return _trsm_raw(side, ul, _flip(ta), dA, alpha, A, Yb)                  # blas.jl:295-307
+
+
+_trsm = Primitive("trsm", forward=_trsm_raw, grads={"any": _trsm_grad})
+
+
+def trsm(side, ul, ta, dA, alpha, A, X):
+    return _trsm(side, ul, ta, dA, alpha, A, X)
+
+
+def _trsv_raw(ul, ta, dA, A, x):
+    return _trsm_raw("L", ul, ta, dA, 1.0, A, x)
+
+
+def _trsv_grad(n, p, y, yb, ul, ta, dA, A, x):
+    if n == 4:                                                               # blas.jl:315-323
+        return _trsm_grad(6, p, y, yb, "L", ul, ta, dA, 1.0, A, x)
+    return _trsv_raw(ul, _flip(ta), dA, A, unthunk(yb))
+
+
+_trsv = Primitive("trsv", forward=_trsv_raw, grads={"any": _trsv_grad})
+
+
+def trsv(ul, ta, dA, A, x):
+    return _trsv(ul, ta, dA, A, x)
 
 
 # --------------------------------------------------------------------------------------------

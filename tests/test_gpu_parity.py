@@ -805,3 +805,49 @@ def test_checkpoint(nb, orc):
     for a, b_, c in zip(g_ck, g_ref, g_plain):
         close(_np(a), b_)
         np.testing.assert_array_equal(_np(a), _np(c))
+
+
+# ---------------------------------------------------------------------------------------------
+# symmetric / triangular BLAS family (test/sensitivities/linalg/blas.jl:63-135)
+# ---------------------------------------------------------------------------------------------
+def test_symm_symv(nb, orc):
+    import itertools
+    rng = np.random.default_rng(123456)
+    r = lambda *s: rng.standard_normal(s)
+    for N in (10, 100):
+        for side, ul in itertools.product("LR", "LU"):
+            A, B = r(N, N), r(N, N)
+            check_case(nb, orc, lambda ns, a, A, B: ns.symm(side, ul, a, A, B), [float(r()), A, B], r(N, N))
+            check_case(nb, orc, lambda ns, A, B: ns.symm(side, ul, A, B), [A, B], r(N, N))
+        for ul in "LU":
+            check_case(nb, orc, lambda ns, a, A, x: ns.symv(ul, a, A, x), [float(r()), r(N, N), r(N)], r(N))
+            check_case(nb, orc, lambda ns, A, x: ns.symv(ul, A, x), [r(N, N), r(N)], r(N))
+
+
+def test_trmm_trmv(nb, orc):
+    import itertools
+    rng = np.random.default_rng(123456)
+    r = lambda *s: rng.standard_normal(s)
+    N = 10
+    for side, ul, tA, dA in itertools.product("LR", "LU", "NT", "UN"):
+        check_case(nb, orc, lambda ns, a, A, B: ns.trmm(side, ul, tA, dA, a, A, B), [float(r()), r(N, N), r(N, N)], r(N, N))
+    for ul, tA, dA in itertools.product("LU", "NT", "UN"):
+        check_case(nb, orc, lambda ns, A, b: ns.trmv(ul, tA, dA, A, b), [r(N, N), r(N)], r(N))
+    check_case(nb, orc, lambda ns, a, A, B: ns.trmm("L", "U", "T", "N", a, A, B), [0.7, r(70, 70), r(70, 33)], r(70, 33))
+
+
+def test_trsm_trsv(nb, orc):
+    import itertools
+    rng = np.random.default_rng(123456)
+    r = lambda *s: rng.standard_normal(s)
+    N = 10
+    for side, ul, tA, dA in itertools.product("LR", "LU", "NT", "UN"):
+        A = r(N, N) + 3 * np.eye(N)
+        check_case(nb, orc, lambda ns, a, A, X: ns.trsm(side, ul, tA, dA, a, A, X), [float(r()), A, r(N, N)], r(N, N), scale=100.0)
+    for ul, tA, dA in itertools.product("LU", "NT", "UN"):
+        A = r(N, N) + np.eye(N)
+        A = A.T @ A
+        check_case(nb, orc, lambda ns, A, x: ns.trsv(ul, tA, dA, A, x), [A, r(N)], r(N), scale=1000.0)
+    A = r(150, 150) + 12 * np.eye(150)
+    check_case(nb, orc, lambda ns, a, A, X: ns.trsm("L", "L", "N", "N", a, A, X), [1.3, A, r(150, 40)], r(150, 40), scale=100.0)
+    check_case(nb, orc, lambda ns, a, A, X: ns.trsm("R", "U", "T", "N", a, A, X), [1.3, A, r(40, 150)], r(40, 150), scale=100.0)

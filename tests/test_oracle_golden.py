@@ -303,3 +303,32 @@ def test_array_structure_and_checkpoint_known_answers():
     yy = 5.0
     with pytest.raises(RuntimeError):
         o.checkpoint(lambda v: v + yy, (5.0,))
+
+
+def test_structured_blas_check_errs():
+    # test/sensitivities/linalg/blas.jl:63-135 — every flag permutation, the reference's FD method
+    import itertools
+    rng = np.random.default_rng(123456)
+    r = lambda *s: rng.standard_normal(s)
+    N = 10
+    for side, ul in itertools.product("LR", "LU"):
+        A, B, VA, VB = r(N, N), r(N, N), r(N, N), r(N, N)
+        assert o.check_errs(lambda a, A, B: o.symm(side, ul, a, A, B), r(N, N), (r(), A, B), (r(), VA, VB))
+        assert o.check_errs(lambda A, B: o.symm(side, ul, A, B), r(N, N), (A, B), (VA, VB))
+    for ul in "LU":
+        A, VA, x, vx = r(N, N), r(N, N), r(N), r(N)
+        assert o.check_errs(lambda a, A, x: o.symv(ul, a, A, x), r(N), (r(), A, x), (r(), VA, vx))
+        assert o.check_errs(lambda A, x: o.symv(ul, A, x), r(N), (A, x), (VA, vx))
+    for side, ul, tA, dA in itertools.product("LR", "LU", "NT", "UN"):
+        A, B, VA, VB = r(N, N), r(N, N), r(N, N), r(N, N)
+        assert o.check_errs(lambda a, A, B: o.trmm(side, ul, tA, dA, a, A, B), r(N, N), (r(), A, B), (r(), VA, VB))
+        X, VX = r(N, N), r(N, N)
+        A3 = r(N, N) + 3 * np.eye(N)
+        assert o.check_errs(lambda a, A, X: o.trsm(side, ul, tA, dA, a, A, X), r(N, N), (r(), A3, X), (r(), VA, VX),
+                            eps_abs=1e-7, eps_rel=1e-5)
+    for ul, tA, dA in itertools.product("LU", "NT", "UN"):
+        A, VA, b, vb = r(N, N), r(N, N), r(N), r(N)
+        assert o.check_errs(lambda A, b: o.trmv(ul, tA, dA, A, b), r(N), (A, b), (VA, vb))
+        A1 = r(N, N) + np.eye(N)
+        A1 = A1.T @ A1
+        assert o.check_errs(lambda A, x: o.trsv(ul, tA, dA, A, x), r(N), (A1, b), (VA, vb), eps_abs=1e-7, eps_rel=1e-5)
