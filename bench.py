@@ -446,8 +446,16 @@ def run_gpu(args):
         achieved = flop / (gemm_ms_total * 1e-3) / 1e12
         ratio = {"bf16x3": 1.0, "3xtf32": 0.5, "tf32": 0.5, "fp32": 0.5}[args.math] if args.dtype == "f32" else 0.5
         peak = peaks["bf16_sustained"] * ratio
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+        if args.math == "bf16x3" and args.dtype == "f32" and n == 1 and B == 32768 and os.path.exists(tpath):
+            # one `ncu` capture of the same kernel at the dominant shape (never taken during a timed run)
+            t = json.load(open(tpath))["per_gemm_call"]["NN_8192x32768x8192"]
+            traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None,
+                "frac": achieved / peak, "traffic": traffic,
+                "traffic_note": "DRAM bytes per GEMM launch (8192x32768x8192) from profiles/r1_gemm_traffic.json; "
+                                "algorithmic bytes 2.42e9" if traffic else None,
                 "kernel": "nb_gemm (dense GEMM sensitivities: forward A*B, Abar=Ybar*B', Bbar=A'*Ybar)",
                 "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s x {ratio} "
                              "(kind::f16 for bf16x3, kind::tf32 at half that rate otherwise); achieved counts "

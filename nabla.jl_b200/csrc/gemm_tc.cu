@@ -76,19 +76,22 @@ struct GemmArgs {
   int64_t ldc;
   int32_t tiles_m, tiles_n;
   int32_t* tile_counter;  // zeroed before the launch; next tile index to hand out
+  int32_t group_m;        // tile-rows per rasterisation group (see tile_coords)
+  int64_t k_begin, k_end; // K range of this launch (multiples of the K step except at the very end)
 };
 
 constexpr int SCHED_SLOTS = 4;
 
-// Tile rasterisation: groups of GROUP_M tile-rows are swept along n with m fastest inside the group,
-// so the ~148 tiles in flight form a compact GROUP_M x ~9 block whose operand panels (per K chunk) stay
-// resident in the 126 MB L2 even when the CTAs drift apart.
-constexpr int GROUP_M = 16;
-__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int& tm, int& tn) {
-  const int per_group = GROUP_M * tiles_n;
+// Tile rasterisation: groups of `group_m` tile-rows are swept along n with m fastest inside the group.
+// The A panel of one group (group_m x tile rows x K range) is re-used by every tile column of the sweep,
+// so the host sizes group_m to keep that panel (~48 MB) resident in the 126 MB L2 and launches long K
+// in ranges of 8192 (ncu on the first version, group of 16 x 256 rows x K = 8192: 27.7 GB of DRAM traffic
+// for 2.4 GB of algorithmic bytes — the panel did not fit and A was re-read for every tile column).
+__device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
+  const int per_group = group_m * tiles_n;
   const int group = t / per_group;
-  const int first_m = group * GROUP_M;
-  const int gsize = min(tiles_m - first_m, GROUP_M);
+  const int first_m = group * group_m;
+  const int gsize = min(tiles_m - first_m, group_m);
   const int r = t - group * per_group;
   tm = first_m + r % gsize;
   tn = r / gsize;
@@ -230,7 +233,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ntiles = g.tiles_m * g.tiles_n;
-  const int nkb = (int)((g.K + BK - 1) / BK);
+  const int nkb = (int)((g.k_end - g.k_begin + BK - 1) / BK);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -265,13 +268,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         const int t_cur = t;
         t = atomicAdd(g.tile_counter, 1);
         int tm, tn;
-        tile_coords(t_cur, g.tiles_m, g.tiles_n, tm, tn);
+        tile_coords(t_cur, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
         for (int kb = 0; kb < nkb; ++kb) {  // chunk boundaries do not concern the producer
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], C_::STAGE_BYTES);
           uint8_t* st = smem + s * C_::STAGE_BYTES;
-          const int k0 = kb * BK;
+          const int k0 = (int)g.k_begin + kb * BK;
 #pragma unroll
           for (int h = 0; h < (int)C_::NSPLIT; ++h) {
             uint8_t* a_dst = st + h * C_::A_BYTES;
@@ -354,7 +357,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       if (++sq == SCHED_SLOTS) { sq = 0; sqph ^= 1; }
       if (t >= ntiles) break;
       int tm, tn;
-      tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+      tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
       const int64_t m0 = (int64_t)tm * BM, n0 = (int64_t)tn * BN;
       for (int kb0 = 0; kb0 < nkb; kb0 += KT::KCHUNK / BK) {
         const float beta = kb0 == 0 ? g.beta : 1.f;  // later chunks accumulate onto the first
@@ -488,7 +491,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   const bool leader = rank == 0;
   const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int ntiles = g.tiles_m * g.tiles_n;  // pair tiles (256 x 256)
-  const int nkb = (int)((g.K + BK - 1) / BK);
+  const int nkb = (int)((g.k_end - g.k_begin + BK - 1) / BK);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
@@ -512,13 +515,13 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       uint32_t ph = 0;
       for (int t = pair; t < ntiles; t += npairs) {
         int tm, tn;
-        tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+        tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
         const int m0 = tm * 256 + (int)rank * 128, n0 = tn * BN + (int)rank * 128;
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full[s], 2 * C_::STAGE_BYTES);  // both CTAs' bytes land on this barrier
           uint8_t* st = smem + s * C_::STAGE_BYTES;
-          const int k0 = kb * BK;
+          const int k0 = (int)g.k_begin + kb * BK;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
             uint8_t* a_dst = st + h * C_::A_BYTES;
@@ -592,7 +595,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     const float alpha = g.alpha;
     for (int t = pair; t < ntiles; t += npairs) {
       int tm, tn;
-      tile_coords(t, g.tiles_m, g.tiles_n, tm, tn);
+      tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
       const int64_t m0 = (int64_t)tm * 256 + (int64_t)rank * 128, n0 = (int64_t)tn * BN;
       for (int kb0 = 0; kb0 < nkb; kb0 += KT::KCHUNK / BK) {
         const float beta = kb0 == 0 ? g.beta : 1.f;
@@ -950,15 +953,26 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     g.a_mn = a_mn; g.b_mn = b_mn;
     g.alpha = alpha; g.beta = beta;
     g.C = C; g.ldc = ldc;
-    g.tiles_m = (int32_t)((m + BM - 1) / BM);
+    const int tile_rows = use_pair ? 256 : BM;
+    g.tiles_m = (int32_t)((m + tile_rows - 1) / tile_rows);
     g.tiles_n = (int32_t)((n + BN - 1) / BN);
     g.tile_counter = st->tile_counter;
-    if (use_pair) {
-      g.tiles_m = (int32_t)((m + 255) / 256);
-      rc = launch_pair(ctx, maps, g);
-    } else if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
-    else if (kind == KIND_3XTF32) rc = BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
-    else rc = BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);
+    // long K is launched in ranges so that the operand panel of a rasterisation group fits the L2
+    const int64_t KRANGE = 8192;
+    const int nsplit_bytes = esize * (kind == KIND_TF32 ? 1 : 2);
+    for (int64_t kb = 0; kb < k && rc == NB_OK; kb += KRANGE) {
+      g.k_begin = kb;
+      g.k_end = kb + KRANGE < k ? kb + KRANGE : k;
+      if (kb > 0) g.beta = 1.f;
+      const int64_t panel = (int64_t)tile_rows * (g.k_end - g.k_begin) * nsplit_bytes;
+      int64_t gm = (48ll << 20) / (panel > 0 ? panel : 1);
+      g.group_m = (int32_t)(gm < 1 ? 1 : gm > 16 ? 16 : gm);
+      if (const char* e = getenv("NB_GEMM_GROUP_M")) g.group_m = atoi(e) > 0 ? atoi(e) : g.group_m;
+      if (use_pair) rc = launch_pair(ctx, maps, g);
+      else if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
+      else if (kind == KIND_3XTF32) rc = BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
+      else rc = BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);
+    }
   }
   for (int i = 0; i < 4; ++i)
     if (tmp[i]) nb_pool_release(ctx, tmp[i]);
