@@ -169,6 +169,35 @@ int32_t nb_bcast_reduce(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const n
 int32_t nb_gemm(nb_ctx* ctx, char tA, char tB, int64_t m, int64_t n, int64_t k, double alpha,
                 const void* A, int64_t lda, const void* B, int64_t ldb, double beta, void* C,
                 int64_t ldc, int32_t dtype, int32_t math_mode);
+/* The product with the Branches around it fused into the GEMM epilogue (tape-level
+ * fusion; the reference tapes `f.(W*X .+ b)` as three Branches with three full-size arrays,
+ * functional.jl:48-51, and walks them one by one in reverse, core.jl:140-158):
+ *   kind 1 (forward)   C = f.(alpha*op(A)*op(B) .+ bias)          bias: length m, nullable
+ *   kind 2 (pullback)  C = (alpha*op(A)*op(B)) .* f'(y)            y: the saved forward value f(...) (m x n, ldy);
+ *                      f must be a catalogue function whose derivative is a function of y alone
+ *                      (identity, tanh, logistic, exp, sqrt, inv, ...: DiffRules forms used by fmad, core.jl:285-292)
+ *   rowsum (nullable)  rowsum[i] (+)= sum_j C[i,j]                 the bias sensitivity: unbroadcast of the
+ *                      `.+` pullback (functional.jl:61-63), deterministic two-phase sum
+ *   emit_split         also keep the tensor-core operand split of C for the products that consume it next
+ * Only the Float32 tensor-core path implements it: NB_ERR_UNSUPPORTED (nothing launched) otherwise, and the
+ * caller runs the unfused sequence nb_gemm + nb_bcast_fwd / nb_bcast_pullback. */
+typedef struct nb_gemm_epilogue {
+  int32_t kind;        /* 0 none, 1 forward, 2 pullback */
+  int32_t op;          /* unary nb_op code */
+  const void* bias;
+  const void* y;
+  int64_t ldy;
+  void* rowsum;
+  int32_t rowsum_acc;
+  int32_t emit_split;
+} nb_gemm_epilogue;
+/* Which inputs the partial derivative of catalogue op `op` w.r.t. operand `wrt` (0 = a, 1 = b) reads:
+ * bit 0 operand a, bit 1 operand b, bit 2 the saved forward value y (host logic uses it to decide what a
+ * pullback launch must be handed; no GPU needed). */
+int32_t nb_op_partial_needs(int32_t op, int32_t wrt);
+int32_t nb_gemm_fused(nb_ctx* ctx, char tA, char tB, int64_t m, int64_t n, int64_t k, double alpha,
+                      const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                      int32_t dtype, int32_t math_mode, const nb_gemm_epilogue* epi);
 /* y = alpha*op(A)*x + beta*y   (A is m x n) — matrix*vector and BLAS.gemv (blas.jl tests :49-61) */
 int32_t nb_gemv(nb_ctx* ctx, char tA, int64_t m, int64_t n, double alpha, const void* A,
                 int64_t lda, const void* x, double beta, void* y, int32_t dtype);

@@ -95,6 +95,9 @@ _SIGS = {
     "nb_bcast_reduce": ([_p, _p, _i32, _tp, _dbl, _tp, _i32], _i32),
     "nb_gemm": ([_p, C.c_char, C.c_char, _i64, _i64, _i64, _dbl, _p, _i64, _p, _i64, _dbl, _p, _i64,
                  _i32, _i32], _i32),
+    "nb_op_partial_needs": ([_i32, _i32], _i32),
+    "nb_gemm_fused": ([_p, C.c_char, C.c_char, _i64, _i64, _i64, _dbl, _p, _i64, _p, _i64, _p, _i64, _i32, _i32,
+                       _p], _i32),
     "nb_gemv": ([_p, C.c_char, _i64, _i64, _dbl, _p, _i64, _p, _dbl, _p, _i32], _i32),
     "nb_ger": ([_p, _i64, _i64, _dbl, _p, _p, _dbl, _p, _i64, _i32], _i32),
     "nb_transpose": ([_p, _i64, _i64, _p, _i64, _p, _i64, _i32], _i32),

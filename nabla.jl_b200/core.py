@@ -287,6 +287,12 @@ def propagate(fwd_tape, rvs_tape, on_final=None):
         for leaf_pos in finals.get(delta, ()):
             if rvs_tape.tape[leaf_pos - 1] is not UNDEF:
                 on_final(leaf_pos, rvs_tape)
+    # launches deferred by fusion.py that owe a value to a second array (a fused bias sensitivity) are made
+    # before the sweep returns: every slot of the reverse tape is then final
+    for node in fwd_tape.tape[:1]:
+        v = unbox(node)
+        if isinstance(v, DevArray):
+            v.ctx.flush_deferred(only_side_outputs=True)
     return rvs_tape
 
 

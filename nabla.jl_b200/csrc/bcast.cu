@@ -22,47 +22,10 @@
 //   k_short  rows <= 32         one thread per column (10 x B output layers)
 //   k_nd     >2 collapsed dims  generic fallback, one thread per output element
 #include "ops.cuh"
+#include "bcast_types.cuh"
 
 namespace {
-
-enum { OM_ELEM = 0, OM_KEEP_ROWS = 1, OM_KEEP_COLS = 2, OM_ALL = 3 };
-
-struct Opnd {
-  const void* p;
-  int64_t rs, cs;  // element strides along rows / cols of the collapsed space (rs in {0,1})
-};
-
-struct OutS {
-  void* p;
-  int64_t rs, cs;
-  int32_t mode;
-  int32_t acc;     // fused +=
-  int32_t wrt;     // generic: operand index; fast: bit0 -> d/da, bit1 -> d/db
-  int32_t active;  // handled by this launch
-  void* partial;
-};
-
-#define NB_FAST_NIN 2
-struct MRP {
-  int64_t rows, cols;
-  int32_t nargs;     // operands to load (fast: 2 = A,B; generic: program operands)
-  int32_t nout;
-  int32_t pullback;
-  int32_t op;        // fast path opcode
-  int32_t load_mask; // which operands are actually read
-  int32_t has_ybar, has_y, need_y;
-  int32_t vec_ok;    // all contiguous operands 16B-aligned with compatible strides
-  double cval[NB_FAST_NIN];  // fast: value of a constant operand
-  int32_t is_const[NB_FAST_NIN];
-  double scale;
-  Opnd arg[NB_MAX_ARGS];
-  Opnd ybar, ys;
-  OutS out[NB_MAX_ARGS];
-};
-
-template <typename T> struct VecOf;
-template <> struct VecOf<float> { static constexpr int V = 4; using type = float4; };
-template <> struct VecOf<double> { static constexpr int V = 2; using type = double2; };
+using namespace nbb;
 
 template <typename T, int V>
 __device__ __forceinline__ void load_vals(const void* base, int64_t off, bool contig, int nvalid,
@@ -197,29 +160,6 @@ struct GenEv {
     }
   }
 };
-
-template <typename T>
-__device__ __forceinline__ T warp_sum(T v) {
-#pragma unroll
-  for (int s = 16; s > 0; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-  return v;
-}
-
-// block-wide sum of one value per thread; result valid in thread 0.  smem: >= 32 T
-template <typename T>
-__device__ __forceinline__ T block_sum(T v, T* smem) {
-  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  const int nw = (blockDim.x * blockDim.y + 31) >> 5;
-  v = warp_sum(v);
-  __syncthreads();
-  if (lane == 0) smem[w] = v;
-  __syncthreads();
-  if (w == 0) {
-    v = lane < nw ? smem[lane] : T(0);
-    v = warp_sum(v);
-  }
-  return v;
-}
 
 // ---- k_flat: cols == 1 ---------------------------------------------------------------------
 template <typename T, template <typename, int> class EvT>
@@ -587,21 +527,23 @@ struct Call {
 static inline int64_t ext_of(const nb_tensor* t, int d) { return d < t->ndim ? t->shape[d] : 1; }
 
 template <typename T>
-struct LeanFlatF {
-  const MRP& P; int64_t nvec; unsigned blocks; cudaStream_t st;
-  template <int OP, int MODE> void operator()() { lean_launch_flat<T, OP, MODE>(P, nvec, blocks, st); }
-};
-template <typename T>
-struct LeanTallF {
-  const MRP& P; dim3 grid, block; size_t smem; int64_t cps; cudaStream_t st;
-  template <int OP, int MODE> void operator()() { lean_launch_tall<T, OP, MODE>(P, grid, block, smem, cps, st); }
+struct LeanKindF {
+  int kind; const MRP& P; const LeanLaunch& a; cudaStream_t st;
+  template <int OP, int MODE> void operator()() {
+    if (kind == 0) lean_launch_flat<T, OP, MODE>(P, a.nvec, a.blocks, st);
+    else if (kind == 1) lean_launch_tall<T, OP, MODE>(P, a.grid, a.block, a.smem, a.cps, st);
+    else lean_launch_wcol<T, OP, MODE>(P, a.blocks, st);
+  }
 };
 
+// hot primitives: kernels of this translation unit; the rest of the catalogue: bcast_lean_cold_*.cu
 template <typename T>
-struct LeanWcolF {
-  const MRP& P; unsigned blocks; cudaStream_t st;
-  template <int OP, int MODE> void operator()() { lean_launch_wcol<T, OP, MODE>(P, blocks, st); }
-};
+bool lean_any(int kind, int mode, const MRP& P, const LeanLaunch& a, cudaStream_t st) {
+  if (lean_hot_op(P.op)) return lean_dispatch<T>(P.op, mode, LeanKindF<T>{kind, P, a, st});
+  if (nb_op_is_unary(P.op))
+    return sizeof(T) == 4 ? nb_lean_cold_un_f32(kind, P.op, mode, P, a, st) : nb_lean_cold_un_f64(kind, P.op, mode, P, a, st);
+  return sizeof(T) == 4 ? nb_lean_cold_bin_f32(kind, P.op, mode, P, a, st) : nb_lean_cold_bin_f64(kind, P.op, mode, P, a, st);
+}
 
 // lean_mode: LM_* when the call qualifies for the compile-time-specialised kernels, -1 otherwise
 template <typename T, template <typename, int> class Ev>
@@ -645,7 +587,7 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
       }
     }
     if (lean_mode >= 0 && P.rows % V == 0 &&
-        lean_dispatch<T>(P.op, lean_mode, LeanFlatF<T>{P, P.rows / V, (unsigned)blocks, st})) {
+        lean_any<T>(0, lean_mode, P, LeanLaunch{P.rows / V, (unsigned)blocks, dim3(), dim3(), 0, 0}, st)) {
       NB_LAUNCH_CHECK(ctx);
       return finish();
     }
@@ -701,7 +643,7 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
       int64_t blocks = (P.cols + 7) / 8;
       const int64_t cap = (int64_t)sms * 8;
       if (blocks > cap) blocks = cap;
-      if (lean_dispatch<T>(P.op, lean_mode, LeanWcolF<T>{P, (unsigned)blocks, st})) {
+      if (lean_any<T>(2, lean_mode, P, LeanLaunch{0, (unsigned)blocks, dim3(), dim3(), 0, 0}, st)) {
         NB_LAUNCH_CHECK(ctx);
         return NB_OK;
       }
@@ -732,7 +674,7 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
     dim3 grid((unsigned)rblocks, (unsigned)slabs), block(TX, TY);
     const size_t smem = (size_t)256 * V * sizeof(T);
     if (!(lean_mode >= 0 && !any_wcol && P.rows % V == 0 &&
-          lean_dispatch<T>(P.op, lean_mode, LeanTallF<T>{P, grid, block, smem, cps, st})))
+          lean_any<T>(1, lean_mode, P, LeanLaunch{0, 0, grid, block, smem, cps}, st)))
       k_tall<T, Ev><<<grid, block, smem, st>>>(P, G, cps);
     NB_LAUNCH_CHECK(ctx);
     int32_t rc = finish();
@@ -932,7 +874,7 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
     // Lean eligibility: hot single primitive, vectorisable, saved y present when the partial needs it,
     // and the wanted sensitivities are plain d/da, d/db (or both, in operand order).
     int lean_mode = -1;
-    if (fast && P.vec_ok && lean_hot_op(P.op)) {
+    if (fast && P.vec_ok && (nb_op_is_unary(P.op) || nb_op_is_binary(P.op))) {
       if (!C.pullback) lean_mode = LM_FWD;
       else if (P.nout == 1 && (P.out[0].wrt == 1 || P.out[0].wrt == 2)) lean_mode = P.out[0].wrt;
       else if (P.nout == 2 && P.out[0].wrt == 1 && P.out[1].wrt == 2) lean_mode = LM_PULL_AB;

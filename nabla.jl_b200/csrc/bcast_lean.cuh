@@ -82,10 +82,10 @@ struct LeanPack {
       const T bv = (NEED & 2) ? b[(NEED & 2) ? i : 0] : T(0);
       const T yv = (NEED & 4) ? y[(NEED & 4) ? i : 0] : T(0);
       if constexpr (MODE == LM_FWD) {
-        o[0][i] = nb_eval<T>(OP, av, bv);
+        o[0][i] = nb_eval_full<T>(OP, av, bv);
         o[1][i] = T(0);
       } else if constexpr (!lean_is_binary(OP)) {
-        o[0][i] = yb[i] * nb_dunary<T>(OP, av, yv);
+        o[0][i] = yb[i] * nb_dunary_full<T>(OP, av, yv);
         o[1][i] = T(0);
       } else if constexpr (MODE == LM_PULL_A) {
         o[0][i] = yb[i] * nb_dbinary<T>(OP, 0, av, bv, yv);

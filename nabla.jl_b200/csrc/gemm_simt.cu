@@ -5,7 +5,7 @@
 //
 // Reference: ChainRules rrule(*) / BLAS.gemm adjoints reached through
 // src/sensitivities/chainrules.jl:179-191,286 and src/sensitivities/linalg/blas.jl:224-228.
-#include "common.cuh"
+#include "ops.cuh"
 
 // implemented in gemm_f64.cu / gemm_tf32.cu; return NB_ERR_UNSUPPORTED when the shape does not fit
 int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha,
@@ -13,7 +13,7 @@ int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_
                      double* C, int64_t ldc);
 int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, float alpha,
                         const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
-                        float* C, int64_t ldc, int32_t math_mode);
+                        float* C, int64_t ldc, int32_t math_mode, const nb_gemm_epilogue* epi);
 
 namespace {
 
@@ -158,11 +158,36 @@ int32_t nb_gemm(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k
   }
   if (math_mode != NB_MATH_FP32) {
     int32_t rc = nb_gemm_tcgen05(ctx, tA, tB, m, n, k, (float)alpha, (const float*)A, lda,
-                                 (const float*)B, ldb, (float)beta, (float*)C, ldc, math_mode);
+                                 (const float*)B, ldb, (float)beta, (float*)C, ldc, math_mode, nullptr);
     if (rc != NB_ERR_UNSUPPORTED) return rc;
   }
   return launch_simt<float>(ctx, tA, tB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
 }
+
+int32_t nb_gemm_fused(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k, double alpha,
+                      const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
+                      int32_t dtype, int32_t math_mode, const nb_gemm_epilogue* epi) {
+  NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
+  NB_REQUIRE(ctx, (is_t(tAc) || is_n(tAc)) && (is_t(tBc) || is_n(tBc)), NB_ERR_INVALID,
+             "nb_gemm_fused: transpose flags must be 'N', 'T' or 'C'");
+  NB_REQUIRE(ctx, epi && (epi->kind == 1 || epi->kind == 2), NB_ERR_INVALID, "nb_gemm_fused: bad epilogue kind");
+  NB_REQUIRE(ctx, epi->op >= 0 && epi->op < NB_OP_UNARY_END, NB_ERR_INVALID, "nb_gemm_fused: op must be unary");
+  NB_REQUIRE(ctx, epi->kind != 2 || (epi->y && epi->ldy >= m), NB_ERR_INVALID, "nb_gemm_fused: pullback needs y");
+  NB_REQUIRE(ctx, epi->kind != 2 || (nb_partial_needs(epi->op, 0) & 3) == 0, NB_ERR_INVALID,
+             "nb_gemm_fused: f' must be a function of y alone");
+  const bool tA = is_t(tAc), tB = is_t(tBc);
+  NB_REQUIRE(ctx, m > 0 && n > 0 && k > 0, NB_ERR_UNSUPPORTED, "nb_gemm_fused: empty product");
+  NB_REQUIRE(ctx, lda >= (tA ? k : m) && ldb >= (tB ? n : k) && ldc >= m, NB_ERR_SHAPE,
+             "nb_gemm_fused: leading dimension too small (DimensionMismatch)");
+  NB_REQUIRE(ctx, A && B && C, NB_ERR_INVALID, "nb_gemm_fused: NULL matrix");
+  if (dtype != NB_F32 || math_mode == NB_MATH_FP32 || alpha == 0.0) return NB_ERR_UNSUPPORTED;
+  nb_note_write(ctx, C);
+  if (epi->rowsum) nb_note_write(ctx, epi->rowsum);
+  return nb_gemm_tcgen05(ctx, tA, tB, m, n, k, (float)alpha, (const float*)A, lda, (const float*)B, ldb, 0.f,
+                         (float*)C, ldc, math_mode, epi);
+}
+
+int32_t nb_op_partial_needs(int32_t op, int32_t wrt) { return nb_partial_needs(op, wrt); }
 
 int32_t nb_transpose(nb_ctx* ctx, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
                      int64_t ld_out, int32_t dtype) {

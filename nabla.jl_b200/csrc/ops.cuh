@@ -68,9 +68,10 @@ template <typename T> __device__ __forceinline__ T nb_rsqrt(T x);
 template <> __device__ __forceinline__ float nb_rsqrt<float>(float x) { return 1.0f / sqrtf(x); }
 template <> __device__ __forceinline__ double nb_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
 
-// value of a catalogue op (full table; out-of-line so the hot kernels stay small)
+// value of a catalogue op: full table, inlined (folds to one expression when `op` is a compile-time
+// constant, as in the lean kernels)
 template <typename T>
-__device__ __noinline__ T nb_eval_cold(int op, T a, T b) {
+__device__ __forceinline__ T nb_eval_full(int op, T a, T b) {
   const T one = T(1);
   const T d2r = T(NB_D2R), r2d = T(NB_R2D);
   switch (op) {
@@ -146,9 +147,13 @@ __device__ __noinline__ T nb_eval_cold(int op, T a, T b) {
   }
 }
 
+// the same table out of line, so kernels with a RUNTIME opcode stay small
+template <typename T>
+__device__ __noinline__ T nb_eval_cold(int op, T a, T b) { return nb_eval_full<T>(op, a, b); }
+
 // d/da of a unary op; y is f(a) (valid only if nb_partial_needs says Y)
 template <typename T>
-__device__ __noinline__ T nb_dunary_cold(int op, T a, T y) {
+__device__ __forceinline__ T nb_dunary_full(int op, T a, T y) {
   const T one = T(1);
   const T d2r = T(NB_D2R), r2d = T(NB_R2D);
   switch (op) {
@@ -214,6 +219,8 @@ __device__ __noinline__ T nb_dunary_cold(int op, T a, T y) {
   }
 }
 
+template <typename T>
+__device__ __noinline__ T nb_dunary_cold(int op, T a, T y) { return nb_dunary_full<T>(op, a, y); }
 
 // Hot ops are inlined into the kernels; the long tail of the catalogue goes through one call.
 template <typename T>

@@ -28,6 +28,8 @@ class Context:
         self.math_mode = _lib.MATH_DEFAULT
         self._progs = {}
         self.nranks, self.rank = 1, 0
+        self._deferred = []   # weak references to launches that have been deferred (fusion.py)
+        self.fuse = os.environ.get("NB_FUSE", "1") != "0"
 
     def close(self):
         if self.h:
@@ -39,6 +41,28 @@ class Context:
 
     def sync(self):
         check(self.L.nb_sync(self.h), self.h)
+
+    def scratch_ptr(self):
+        """A small valid device address (256 B) for descriptors whose data is never read."""
+        if getattr(self, "_scratch", None) is None:
+            self._scratch = DevArray(self, (64,), np.float32)
+        return self._scratch.ptr
+
+    def flush_deferred(self, only_side_outputs=False):
+        """Launch what fusion.py has deferred.  With ``only_side_outputs`` only the launches that owe a value to
+        somebody besides their own result array (a fused bias sensitivity) are forced."""
+        if not self._deferred:
+            return
+        live = []
+        for r in self._deferred:
+            d = r()
+            if d is None or d.done:
+                continue
+            if only_side_outputs and not d.has_side_outputs():
+                live.append(r)
+                continue
+            d.flush()
+        self._deferred = live
 
     def stats(self):
         s = _lib.nb_stats()
@@ -142,10 +166,10 @@ class DevArray:
     e.g. when a rule returns ȳ itself; the accumulate path copies instead of mutating it
     (SURVEY.md §7 hard part 5; reference pin: test/core.jl:211-224)."""
 
-    __slots__ = ("ctx", "ptr", "shape", "dtype", "shared", "adjvec", "_base", "__weakref__")
+    __slots__ = ("ctx", "_ptr", "shape", "dtype", "shared", "adjvec", "_base", "pending", "__weakref__")
     __array_priority__ = 3000.0
 
-    def __init__(self, ctx, shape, dtype, ptr=None, base=None):
+    def __init__(self, ctx, shape, dtype, ptr=None, base=None, lazy=False):
         if len(shape) > NB_MAX_DIMS:
             raise ValueError(f"DevArray supports at most {NB_MAX_DIMS} dimensions, got {shape}")
         if np.dtype(dtype) not in _DT:
@@ -156,17 +180,33 @@ class DevArray:
         self.shared = False
         self.adjvec = False
         self._base = base
-        if ptr is None:
-            p = C.c_void_p()
-            check(ctx.L.nb_alloc(ctx.h, max(self.nbytes, 1), C.byref(p)), ctx.h)
-            self.ptr = p.value
+        self.pending = None  # fusion.Deferred: the launch that will produce this value (see `ptr`)
+        if ptr is not None:
+            self._ptr = ptr
+        elif lazy:
+            self._ptr = None  # allocated when the deferred launch is made (or never, if nobody reads it)
         else:
-            self.ptr = ptr
+            self._alloc()
+
+    def _alloc(self):
+        p = C.c_void_p()
+        check(self.ctx.L.nb_alloc(self.ctx.h, max(self.nbytes, 1), C.byref(p)), self.ctx.h)
+        self._ptr = p.value
+
+    @property
+    def ptr(self):
+        """Device address of the value.  Reading it is what forces a deferred product (fusion.py): every
+        consumer that hands the buffer to a kernel, a copy or a collective goes through here."""
+        if self.pending is not None:
+            self.pending.flush()
+        if self._ptr is None:
+            self._alloc()
+        return self._ptr
 
     def __del__(self):
         try:
-            if self._base is None and self.ptr and self.ctx.h:
-                self.ctx.L.nb_release(self.ctx.h, self.ptr)
+            if self._base is None and self._ptr and self.ctx.h:
+                self.ctx.L.nb_release(self.ctx.h, self._ptr)
         except Exception:
             pass
 
@@ -219,6 +259,7 @@ class DevArray:
             a = np.asfortranarray(a)
         if a.shape != self.shape:
             raise ValueError(f"DimensionMismatch: {a.shape} vs {self.shape}")
+        self.ctx.flush_deferred()  # a deferred launch may still read this buffer
         if self.nbytes:
             # pageable source: the copy is complete (staged) when the call returns
             check(self.ctx.L.nb_h2d(self.ctx.h, self.ptr, a.ctypes.data, self.nbytes), self.ctx.h)
@@ -229,6 +270,7 @@ class DevArray:
         """Asynchronous H2D from pinned host memory on the ctx stream (no host synchronisation)."""
         if pinned.nbytes != self.nbytes:
             raise ValueError(f"DimensionMismatch: {pinned.shape} vs {self.shape}")
+        self.ctx.flush_deferred()
         check(self.ctx.L.nb_h2d(self.ctx.h, self.ptr, pinned.ptr, self.nbytes), self.ctx.h)
         return self
 

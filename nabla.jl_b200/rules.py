@@ -7,6 +7,7 @@ import numbers
 
 import numpy as np
 
+from . import fusion
 from . import kernels as K
 from ._lib import OPCODES, DimensionMismatch
 from .core import (UNDEF, Branch, Node, Primitive, accumulate, as_device, own, unbox)
@@ -91,8 +92,10 @@ def _mr_forward(fn, *operands, reduce=False, dims=None, mean=False, same_shape=F
     full = K.jl_broadcast_shape(*[d.shape for d in dev])
     dtype = dev[0].dtype
     if not reduce:
-        out = ctx.empty(full, dtype)
-        K.bcast_fwd(prog, dev, out)
+        out = fusion.try_forward(prog, dev) if ctx.fuse else None  # `.+ bias` / `f.` after a deferred product
+        if out is None:
+            out = ctx.empty(full, dtype)
+            K.bcast_fwd(prog, dev, out)
         scale = 1.0
     else:
         out = ctx.empty(_reduced_shape(full, dims), dtype)
@@ -128,6 +131,17 @@ def _mr_fused(y, ybar, rvs):
         K.bcast_reduce(None, [yb], scaled, scale=scale)
         ybar = scaled
     y_saved = None if reduce else y.val
+    kdev = dev
+    if any(d.pending is not None for d in dev) or (y_saved is not None and y_saved.pending is not None):
+        # hand the kernel only what the partials read: a deferred forward value (W*X, W*X .+ b) that nothing
+        # reads is never launched
+        wanted = [k for k, j in enumerate(dev_pos) if isinstance(y.args[j + 1], Node)]
+        reads = fusion.pullback_reads(prog, wanted)
+        if reads is not None:
+            read_ops, read_y = reads
+            if not read_y:
+                y_saved = None
+            kdev = [d if (d.pending is None or k in read_ops) else fusion.Shadow(d) for k, d in enumerate(dev)]
     outs = [None] * len(dev)
     acc = [False] * len(dev)
     seen = {}
@@ -156,10 +170,35 @@ def _mr_fused(y, ybar, rvs):
             outs[k], acc[k] = o, True
             d_tape[xid - 1] = o
             seen[xid] = k
+    if ctx_fuse(dev) and not reduce and scale == 1.0 and not post:
+        _join_deferred(prog, ybar, y_saved, dev, outs, acc, d_tape, y, dev_pos)
     if any(o is not None for o in outs):
-        K.bcast_pullback(prog, ybar, y_saved, dev, outs, acc)
+        K.bcast_pullback(prog, ybar, y_saved, kdev, outs, acc)
     for xid, tmp in post:
         d_tape[xid - 1] = accumulate(d_tape[xid - 1], tmp)
+
+
+def ctx_fuse(dev):
+    return bool(dev) and dev[0].ctx.fuse
+
+
+def _join_deferred(prog, ybar, y_saved, dev, outs, acc, d_tape, y, dev_pos):
+    """Reverse-side joins of fusion.py: a fresh `ȳ .* f'(y)` becomes the epilogue of the deferred product that
+    produces ȳ, and a bias sensitivity becomes its row-sum output.  Joined outputs are removed from ``outs``."""
+    if not isinstance(ybar, DevArray) or ybar.pending is None:
+        return
+    for k, o in enumerate(outs):
+        if o is None:
+            continue
+        if len(dev) == 1 and not acc[k] and o.pending is None:
+            lazy = fusion.try_pullback_act(prog, ybar, y_saved, dev[k])
+            if lazy is not None:
+                xid = y.args[dev_pos[k] + 1].pos
+                d_tape[xid - 1] = lazy   # replaces the buffer allocated for the unfused launch
+                outs[k] = None
+        elif prog.single_op == _ADD and len(dev) == 2 and tuple(ybar.shape) != tuple(o.shape):
+            if fusion.try_rowsum(ybar, o, acc[k]):
+                outs[k] = None
 
 
 def _make_mr(name, **fixed):
@@ -286,8 +325,10 @@ def _matmul_forward(A, B):
         k2, n = B.shape
         if k != k2:
             raise DimensionMismatch(6, f"A has dimensions {A.shape} but B has dimensions {B.shape}")
-        out = ctx.empty((m, n), A.dtype)
-        K.gemm("N", "N", 1.0, A, B, 0.0, out, m, n, k)
+        out = fusion.defer_product("N", "N", 1.0, A, B, m, n, k)   # launched when somebody reads it
+        if out is None:
+            out = ctx.empty((m, n), A.dtype)
+            K.gemm("N", "N", 1.0, A, B, 0.0, out, m, n, k)
         return out, ("mm", A, B)
     if A.ndim == 2 and B.ndim == 1:
         m, k = A.shape
@@ -322,8 +363,12 @@ def _matmul_fused(y, ybar, rvs):
             out, beta = _slot_target(d_tape, An.pos, A.shape, ctx, dt)
             K.gemm("N", "T", 1.0, ybar, B, beta, out, m, k, n)      # Ȳ (m×n) · Bᵀ (n×k)
         if isinstance(Bn, Node):
-            out, beta = _slot_target(d_tape, Bn.pos, B.shape, ctx, dt)
-            K.gemm("T", "N", 1.0, A, ybar, beta, out, k, n, m)      # Aᵀ (k×m) · Ȳ (m×n)
+            lazy = fusion.defer_product("T", "N", 1.0, A, ybar, k, n, m) if d_tape[Bn.pos - 1] is UNDEF else None
+            if lazy is not None:   # the pullback of the Branch that produced B may join this launch
+                d_tape[Bn.pos - 1] = lazy
+            else:
+                out, beta = _slot_target(d_tape, Bn.pos, B.shape, ctx, dt)
+                K.gemm("T", "N", 1.0, A, ybar, beta, out, k, n, m)      # Aᵀ (k×m) · Ȳ (m×n)
     elif kind == "mv":
         m, k = A.shape
         if isinstance(An, Node):

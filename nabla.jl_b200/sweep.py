@@ -39,10 +39,14 @@ class CapturedGradient:
             # capture itself makes no cudaMalloc
             self._evaluate(f)
             self.ctx.sync()
+        self.ctx.flush_deferred()
         check(L.nb_graph_begin(h), h)
+        self.ctx.capturing = True   # no deferred launches inside a capture (fusion.py): the graph is the fusion
         try:
             self.y, self.grads, self._tape = self._evaluate(f)
+            self.ctx.capturing = False
         except BaseException:
+            self.ctx.capturing = False
             g = C.c_void_p()
             L.nb_graph_end(h, C.byref(g))
             if g:

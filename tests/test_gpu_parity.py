@@ -202,6 +202,38 @@ def test_binary_catalogue_and_scalar_mixes(nb, orc, dtype):
             raise AssertionError(f"{name} ({np.dtype(dtype).name}): {e}") from e
 
 
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_catalogue_on_lean_kernels(nb, orc, dtype):
+    # The same scalar catalogue at vector-friendly sizes (multiples of the 128-bit vector, 16-byte aligned
+    # buffers), where every single primitive runs on the compile-time-specialised lean kernels
+    # (bcast_lean.cuh, bcast_lean_cold.inc): flat for the unary functions, flat / tall / warp-per-column
+    # with the fused unbroadcast for the binary ones.  Also sum(f, A) (reducedim.jl:23-39) on the same kernels.
+    for name in orc.UNARY_NAMES:
+        lo, hi = _domain(orc, name)
+        pad = 0.02 * (hi - lo)
+        rng = np.random.default_rng(zlib.crc32(name.encode()) + 1)
+        x = rng.uniform(lo + pad, hi - pad, (64, 36))
+        if name == "abs":
+            x = np.where(np.abs(x) > 1e-3, x, 0.5)
+        ybar = rng.standard_normal(x.shape)
+        try:
+            check_case(nb, orc, lambda ns, a: ns.broadcast(_fn(ns, name), a), [x], ybar, dtype)
+            check_case(nb, orc, lambda ns, a: ns.sum(_fn(ns, name), a), [x], None, dtype, accumulate=False)
+        except AssertionError as e:
+            raise AssertionError(f"{name} ({np.dtype(dtype).name}): {e}") from e
+    rng = np.random.default_rng(8)
+    A = rng.uniform(0.3, 2.0, (256, 64))
+    ybar = rng.standard_normal(A.shape)
+    for name in orc.BINARY_NAMES:
+        for other in (rng.uniform(0.3, 2.0, (256, 64)), rng.uniform(0.3, 2.0, (256,)),
+                      rng.uniform(0.3, 2.0, (1, 64)), 1.3):
+            try:
+                check_case(nb, orc, lambda ns, a, b: ns.broadcast(_fn(ns, name), a, b), [A, other], ybar, dtype)
+                check_case(nb, orc, lambda ns, a, b: ns.broadcast(_fn(ns, name), b, a), [A, other], ybar, dtype)
+            except AssertionError as e:
+                raise AssertionError(f"{name} {np.shape(other)} ({np.dtype(dtype).name}): {e}") from e
+
+
 SHAPES = [
     ((5, 7), (5, 7)),        # same shape
     ((5, 7), (5,)),          # bias: reduce over columns (functional.jl:61-63)
@@ -851,3 +883,110 @@ def test_trsm_trsv(nb, orc):
     A = r(150, 150) + 12 * np.eye(150)
     check_case(nb, orc, lambda ns, a, A, X: ns.trsm("L", "L", "N", "N", a, A, X), [1.3, A, r(150, 40)], r(150, 40), scale=100.0)
     check_case(nb, orc, lambda ns, a, A, X: ns.trsm("R", "U", "T", "N", a, A, X), [1.3, A, r(40, 150)], r(40, 150), scale=100.0)
+
+
+# ---------------------------------------------------------------------------------------------
+# tape-level fusion around products: nb_gemm_fused + fusion.py
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("3xtf32", 2e-5)])
+def test_gemm_fused_epilogue_c_abi(nb, ctx, mode, tol):
+    """nb_gemm_fused through the C ABI against NumPy Float64: forward f.(A*B .+ bias) and pullback
+    (A*B) .* f'(y), all four transposes, ragged tails, K beyond one chunk and beyond one launch range,
+    row sums fresh and accumulated."""
+    import ctypes as C
+    from nabla_jl_b200 import fusion
+    rng = np.random.default_rng(5)
+    old = ctx.math_mode
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "bf16x3": nb.MATH_BF16X3}[mode]
+    acts = {"tanh": (np.tanh, lambda y: 1 - y * y), "logistic": (lambda x: 1 / (1 + np.exp(-x)), lambda y: y * (1 - y)),
+            "identity": (lambda x: x, lambda y: np.ones_like(y)), "exp": (np.exp, lambda y: y)}
+    try:
+        for (m, n, k) in ((256, 512, 256), (300, 200, 150), (128, 1030, 4200), (520, 260, 8192 + 72), (10, 2048, 1030)):
+            for tA in "NT":
+                for tB in "NT":
+                    A = (rng.standard_normal((k, m) if tA == "T" else (m, k)) / np.sqrt(k)).astype(np.float32)
+                    B = rng.standard_normal((n, k) if tB == "T" else (k, n)).astype(np.float32)
+                    bias = rng.standard_normal(m).astype(np.float32)
+                    P = (A.T if tA == "T" else A).astype(np.float64) @ (B.T if tB == "T" else B).astype(np.float64)
+                    Ad, Bd, bd = ctx.asarray(A), ctx.asarray(B), ctx.asarray(bias)
+                    for name, (f, df) in acts.items():
+                        for kind in (1, 2):
+                            y = np.tanh(rng.standard_normal((m, n))).astype(np.float32) * 0.9
+                            yd = ctx.asarray(y)
+                            rs0 = rng.standard_normal(m).astype(np.float32)
+                            for acc in (0, 1):
+                                out = ctx.empty((m, n), np.float32)
+                                rs = ctx.asarray(rs0)
+                                epi = fusion.nb_gemm_epilogue()
+                                epi.kind, epi.op = kind, nb._lib.OPCODES[name]
+                                epi.bias = bd.ptr if kind == 1 else None
+                                epi.y, epi.ldy = (yd.ptr, m) if kind == 2 else (None, 0)
+                                epi.rowsum, epi.rowsum_acc, epi.emit_split = rs.ptr, acc, 1
+                                st = ctx.L.nb_gemm_fused(ctx.h, tA.encode(), tB.encode(), m, n, k, 1.0, Ad.ptr,
+                                                         k if tA == "T" else m, Bd.ptr, n if tB == "T" else k,
+                                                         out.ptr, m, out.nb_dtype, ctx.math_mode, C.byref(epi))
+                                assert st == 0, f"status {st}"
+                                ref = f(P + bias[:, None].astype(np.float64)) if kind == 1 else P * df(y.astype(np.float64))
+                                got = out.numpy().astype(np.float64)
+                                tag = f"{mode} {tA}{tB} {m}x{n}x{k} {name} kind={kind} acc={acc}"
+                                err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+                                assert err < tol, f"{tag}: rel err {err:.3e}"
+                                rref = got.sum(axis=1) + (rs0 if acc else 0)
+                                rerr = np.linalg.norm(rs.numpy() - rref) / max(np.linalg.norm(rref), 1e-30)
+                                assert rerr < 1e-5, f"{tag}: row sums rel err {rerr:.3e}"
+                                # the emitted operand split must be what a later product of `out` uses
+                                D = rng.standard_normal((n, 64)).astype(np.float32)
+                                Dd, E = ctx.asarray(D), ctx.empty((m, 64), np.float32)
+                                from nabla_jl_b200 import kernels as K
+                                K.gemm("N", "N", 1.0, out, Dd, 0.0, E, m, 64, n)
+                                eref = got @ D.astype(np.float64)
+                                eerr = np.linalg.norm(E.numpy() - eref) / np.linalg.norm(eref)
+                                assert eerr < tol, f"{tag}: product from the emitted split rel err {eerr:.3e}"
+    finally:
+        ctx.math_mode = old
+
+
+def test_fused_dense_layers(nb, orc, ctx):
+    """f.(W*X .+ b) chains (examples/mlp.jl:79-82) with the product launches deferred and the `.+` / `f.`
+    Branches joined to their epilogues: same tape, same gradients as the unfused sweep and as the oracle,
+    fewer launches, and the intermediates W*X and W*X .+ b stay unallocated."""
+    import nabla_jl_b200.workloads as wl
+    dims, B = (96, 256, 192, 128, 10), 512
+    W, b, X, Y = wl.mlp_inputs(dims, B, np.float32, seed=12)
+    nl = len(dims) - 1
+    ref = orc.nabla(wl.mlp_objective(orc, X.astype(np.float64), Y.astype(np.float64), 1e-3, nl))(
+        *[w.astype(np.float64) for w in W], *[v.astype(np.float64) for v in b])
+    Xd, Yd = ctx.asarray(X), ctx.asarray(Y)
+    res = {}
+    for fuse in (True, False):
+        ctx.fuse = fuse
+        try:
+            n0 = ctx.stats()["kernel_launches"]
+            g = nb.nabla(wl.mlp_objective(nb, Xd, Yd, 1e-3, nl))(*W, *b)
+            res[fuse] = ([x.numpy() for x in g], ctx.stats()["kernel_launches"] - n0)
+        finally:
+            ctx.fuse = True
+    for a, r in zip(res[True][0], ref):
+        close(a, r, np.float32)
+    for a, u in zip(res[True][0], res[False][0]):
+        close(a, u, np.float32, scale=0.2)
+    assert res[True][1] < res[False][1], f"fusion must save launches: {res[True][1]} vs {res[False][1]}"
+
+    # the tape itself is unchanged: three Branches per layer, and reading a deferred intermediate works
+    t = nb.Tape()
+    Wn, bn = nb.Leaf(t, W[0]), nb.Leaf(t, b[0])
+    z = nb.matmul(Wn, Xd)
+    t1 = nb.broadcast(nb.add, z, bn)
+    h = nb.broadcast(nb.tanh, t1)
+    assert [type(x).__name__ for x in t.tape] == ["Leaf", "Leaf", "Branch", "Branch", "Branch"]
+    assert z.val.pending is not None and t1.val.pending is not None and z.val._ptr is None
+    s = nb.sum(h)
+    rt = nb.nabla(s)
+    Z = W[0].astype(np.float64) @ X.astype(np.float64)
+    Hh = np.tanh(Z + b[0][:, None])
+    close(rt[Wn].numpy(), (1 - Hh * Hh) @ X.astype(np.float64).T, np.float32)
+    close(rt[bn].numpy(), (1 - Hh * Hh).sum(axis=1), np.float32)
+    assert z.val._ptr is None and t1.val._ptr is None, "unread intermediates are never launched or allocated"
+    close(z.val.numpy(), Z, np.float32)          # reading one forces just that product
+    close(t1.val.numpy(), Z + b[0][:, None], np.float32)
+    close(rt[z].numpy(), 1 - Hh * Hh, np.float32)  # the sensitivity of an intermediate Branch is readable too

@@ -94,3 +94,32 @@ def test_julia_broadcast_shape_rule():
     assert jl_broadcast_shape((), (3, 1, 2)) == (3, 1, 2)
     with pytest.raises(nb.DimensionMismatch):
         jl_broadcast_shape((5,), (7,))
+
+
+def test_partial_needs_table_matches_the_kernels():
+    """fusion.partial_needs (host) decides which operands a pullback launch is handed; it must equal the
+    table the kernels use (csrc/ops.cuh nb_partial_needs, exported as nb_op_partial_needs)."""
+    import nabla_jl_b200 as nb
+    from nabla_jl_b200 import fusion
+    L = nb._lib.lib()
+    for name, op in nb._lib.OPCODES.items():
+        if name.endswith("_end"):
+            continue
+        for wrt in (0, 1):
+            assert fusion.partial_needs(op, wrt) == L.nb_op_partial_needs(op, wrt), (name, wrt)
+
+
+def test_pullback_reads():
+    import nabla_jl_b200 as nb
+    from nabla_jl_b200 import fusion
+    add = nb.compile_scalar(nb.CATALOGUE["add"], 2)
+    assert fusion.pullback_reads(add, [0, 1]) == (set(), False)
+    mul = nb.compile_scalar(nb.CATALOGUE["mul"], 2)
+    assert fusion.pullback_reads(mul, [0]) == ({1}, False)
+    assert fusion.pullback_reads(mul, [0, 1]) == ({0, 1}, False)
+    tanh = nb.compile_scalar(nb.CATALOGUE["tanh"], 1)
+    assert fusion.pullback_reads(tanh, [0]) == (set(), True)
+    sin = nb.compile_scalar(nb.CATALOGUE["sin"], 1)
+    assert fusion.pullback_reads(sin, [0]) == ({0}, False)
+    comp = nb.compile_scalar(lambda a, b: nb.tanh(a) * b, 2)
+    assert fusion.pullback_reads(comp, [0]) is None

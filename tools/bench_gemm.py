@@ -27,6 +27,10 @@ shapes = {
     "Bbar TN W'*Ybar    ": lambda: K.gemm("T", "N", 1.0, W, Y, 0.0, Xb, D, Bc, D),
 }
 flops = 2.0 * D * D * Bc
+if os.environ.get("SHAPES"):
+    sel = os.environ["SHAPES"].split(",")
+    shapes = {k: v for k, v in shapes.items() if any(k.lower().startswith(x) for x in sel)}
+TAIL = int(os.environ.get("TAIL", "0"))  # report only the last TAIL reps (power-capped steady state)
 for mode in modes:
     ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "bf16x3": nb.MATH_BF16X3, "f64": nb.MATH_DEFAULT}[mode]
     for name, fn in shapes.items():
@@ -39,7 +43,11 @@ for mode in modes:
             fn()
             ctx.record(evs[i + 1])
         ctx.sync()
-        ts = sorted(ctx.elapsed_ms(evs[i], evs[i + 1]) for i in range(reps))
+        ts = [ctx.elapsed_ms(evs[i], evs[i + 1]) for i in range(reps)]
+        if TAIL:
+            ts = ts[-TAIL:]
+        ts = sorted(ts)
+        reps = len(ts)
         ms = sum(ts) / reps
         print(f"{mode:7s} {name} B={Bc}: avg {ms:8.3f} ms  min {ts[0]:8.3f}  med {ts[reps // 2]:8.3f}  max {ts[-1]:8.3f}  "
               f"{flops / ms / 1e9:8.1f} TFLOP/s (algorithmic)", flush=True)
