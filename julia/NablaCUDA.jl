@@ -115,6 +115,30 @@ function ChainRulesCore.rrule(::typeof(*), A::DevArray{T,2}, B::DevArray{T,2}) w
     return Y, times_pullback
 end
 
+# ---- tape-level fusion around a product (SURVEY §8(f) rank 1; the tested mirror is nabla.jl_b200/fusion.py):
+#      the launch of a Float32 product can be deferred so that a following `.+ bias` / `f.` (forward) or
+#      `.* f'(y)` / bias row sum (reverse) joins its epilogue.  This is the C entry point those hooks call.
+struct NbGemmEpilogue
+    kind::Int32          # 1 forward  C = f.(αAB .+ bias);  2 pullback  C = (αAB) .* f'(y)
+    op::Int32            # unary nb_op code
+    bias::Ptr{Cvoid}
+    y::Ptr{Cvoid}
+    ldy::Int64
+    rowsum::Ptr{Cvoid}   # nullable: rowsum[i] (+)= Σ_j C[i,j]  (the bias sensitivity)
+    rowsum_acc::Int32
+    emit_split::Int32
+end
+function gemm_fused!(tA::Char, tB::Char, α, A::DevArray{Float32}, B::DevArray{Float32}, C::DevArray{Float32}, m, n, k,
+                     epi::NbGemmEpilogue)
+    st = ccall((:nb_gemm_fused, LIB), Int32,
+               (Ptr{Cvoid}, Cchar, Cchar, Int64, Int64, Int64, Float64, Ptr{Cvoid}, Int64, Ptr{Cvoid}, Int64,
+                Ptr{Cvoid}, Int64, Int32, Int32, Ref{NbGemmEpilogue}),
+               C.ctx.h, tA, tB, m, n, k, α, A.ptr, size(A, 1), B.ptr, size(B, 1), C.ptr, m, nbdtype(Float32), 0, epi)
+    st == 4 && return nothing      # NB_ERR_UNSUPPORTED: the caller runs the unfused launches
+    check(st, C.ctx)
+    return C
+end
+
 # ---- family (1): broadcast.  Scalar functions are lowered to device programs by `program(f, nargs)`
 #      (catalogue opcode for Base functions; a tracer over a symbolic scalar type for user lambdas,
 #      mirroring nabla.jl_b200/scalar.py); unknown primitives throw MethodError — no CPU fallback. ----

@@ -105,6 +105,7 @@ struct GemmArgs {
   int64_t k_begin, k_end; // K range of this launch (multiples of the K step except at the very end)
   int32_t kchunk_kb;      // K blocks accumulated in TMEM before the epilogue folds them into C
   uint64_t hint_a, hint_b;  // L2 eviction policies of the operand loads (0 = none)
+  int32_t vec_store;        // epilogue may use 16-byte accesses along the rows (alignment checked on the host)
   EpiArgs epi;
 };
 
@@ -292,8 +293,124 @@ struct EpiAcc {
     }
   }
 
+  // 4 x 4 transpose inside a quad of lanes: on entry lane 4a+i holds v[c] = X[row 4a+i][col c]; on exit lane 4a+b
+  // holds v[i] = X[row 4a+i][col b] — four consecutive rows of ONE column, i.e. a 16-byte vector of column-major C.
+  static __device__ __forceinline__ void quad_transpose(float (&v)[4], int b) {
+    const bool hi2 = (b & 2) != 0, hi1 = (b & 1) != 0;
+    float s0 = hi2 ? v[0] : v[2], s1 = hi2 ? v[1] : v[3];
+    s0 = __shfl_xor_sync(0xffffffffu, s0, 2);
+    s1 = __shfl_xor_sync(0xffffffffu, s1, 2);
+    if (hi2) { v[0] = s0; v[1] = s1; } else { v[2] = s0; v[3] = s1; }
+    s0 = hi1 ? v[0] : v[1];
+    s1 = hi1 ? v[2] : v[3];
+    s0 = __shfl_xor_sync(0xffffffffu, s0, 1);
+    s1 = __shfl_xor_sync(0xffffffffu, s1, 1);
+    if (hi1) { v[0] = s0; v[2] = s1; } else { v[1] = s0; v[3] = s1; }
+  }
+
+  // Vector form of `store` (M, the leading dimensions and the base addresses are multiples of 4 elements / 16 bytes;
+  // chosen per launch on the host).  The row-per-lane layout that tcgen05.ld delivers makes every access a 4-byte
+  // column-strided one: 512 memory instructions per thread and tile, and with 8 warps per SM the fused epilogues
+  // (y loads, C, hi, lo stores) could not keep up with the MMA of the next tile.  After a quad transpose each lane
+  // owns 4 consecutive rows of every 4th column: 16-byte loads/stores, a quarter of the instructions.
+  // gw = first row of this warp's 32; rows 4a .. 4a+3, columns == b (mod 4).
+  __device__ __forceinline__ void store_vec(const GemmArgs& g, int64_t gw, int64_t n0, int part, int lane) {
+    using SplitT = typename std::conditional<KIND == KIND_BF16X3, __nv_bfloat16, float>::type;
+    const int a = lane >> 2, b = lane & 3;
+    const int64_t R0 = gw + 4 * a;
+    const bool row_ok = R0 < g.M;
+    const float alpha = g.alpha, beta = g.beta;
+    const int ek = g.epi.last_launch ? g.epi.kind : EPI_NONE;
+    float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ek == EPI_FWD && g.epi.bias && row_ok) bias4 = __ldg(reinterpret_cast<const float4*>(g.epi.bias + R0));
+    float rs[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int SB = 16;
+#pragma unroll
+    for (int c = 0; c < NCOL / SB; ++c) {
+      const int64_t nb = n0 + c * SB;  // warp-uniform
+      if (nb >= g.N) break;
+      float x[SB / 4][4];
+#pragma unroll
+      for (int gq = 0; gq < SB / 4; ++gq) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) x[gq][i] = alpha * r[c * SB + gq * 4 + i];
+        quad_transpose(x[gq], b);
+      }
+      if (!row_ok) continue;
+      if (beta != 0.f) {
+        float4 old[SB / 4];
+#pragma unroll
+        for (int gq = 0; gq < SB / 4; ++gq) {
+          const int64_t col = nb + gq * 4 + b;
+          old[gq] = col < g.N ? __ldcg(reinterpret_cast<const float4*>(g.C + R0 + col * g.ldc)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int gq = 0; gq < SB / 4; ++gq) {
+          x[gq][0] += beta * old[gq].x; x[gq][1] += beta * old[gq].y;
+          x[gq][2] += beta * old[gq].z; x[gq][3] += beta * old[gq].w;
+        }
+      }
+      if (ek == EPI_FWD) {
+        const int op = g.epi.op;
+#pragma unroll
+        for (int gq = 0; gq < SB / 4; ++gq) {
+          x[gq][0] = epi_act(op, x[gq][0] + bias4.x); x[gq][1] = epi_act(op, x[gq][1] + bias4.y);
+          x[gq][2] = epi_act(op, x[gq][2] + bias4.z); x[gq][3] = epi_act(op, x[gq][3] + bias4.w);
+        }
+      } else if (ek == EPI_PULL) {
+        const int op = g.epi.op;
+        float4 ys[SB / 4];
+#pragma unroll
+        for (int gq = 0; gq < SB / 4; ++gq) {
+          const int64_t col = nb + gq * 4 + b;
+          ys[gq] = col < g.N ? __ldcs(reinterpret_cast<const float4*>(g.epi.y + R0 + col * g.epi.ldy)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int gq = 0; gq < SB / 4; ++gq) {
+          x[gq][0] *= nb_dunary<float>(op, 0.f, ys[gq].x); x[gq][1] *= nb_dunary<float>(op, 0.f, ys[gq].y);
+          x[gq][2] *= nb_dunary<float>(op, 0.f, ys[gq].z); x[gq][3] *= nb_dunary<float>(op, 0.f, ys[gq].w);
+        }
+      }
+#pragma unroll
+      for (int gq = 0; gq < SB / 4; ++gq) {
+        const int64_t col = nb + gq * 4 + b;
+        if (col < g.N) {
+          *reinterpret_cast<float4*>(g.C + R0 + col * g.ldc) = make_float4(x[gq][0], x[gq][1], x[gq][2], x[gq][3]);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) rs[i] += x[gq][i];
+          if (ek != EPI_NONE && g.epi.s_hi) {
+            __align__(16) SplitT h[4];
+            __align__(16) SplitT l[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) split1(x[gq][i], h[i], l[i]);
+            SplitT* hp = (SplitT*)g.epi.s_hi + R0 + col * g.epi.ld_s;
+            SplitT* lp = (SplitT*)g.epi.s_lo + R0 + col * g.epi.ld_s;
+            if (sizeof(SplitT) == 2) {
+              *reinterpret_cast<uint2*>(hp) = *reinterpret_cast<const uint2*>(h);
+              *reinterpret_cast<uint2*>(lp) = *reinterpret_cast<const uint2*>(l);
+            } else {
+              *reinterpret_cast<uint4*>(hp) = *reinterpret_cast<const uint4*>(h);
+              *reinterpret_cast<uint4*>(lp) = *reinterpret_cast<const uint4*>(l);
+            }
+          }
+        }
+      }
+    }
+    if (ek != EPI_NONE && g.epi.rowsum_partial) {
+      // this lane summed columns == b (mod 4); the quad's four lanes together cover the row
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 1);
+        rs[i] += __shfl_xor_sync(0xffffffffu, rs[i], 2);
+      }
+      if (b == 0 && row_ok)
+        *reinterpret_cast<float4*>(g.epi.rowsum_partial + (int64_t)part * g.M + R0) = make_float4(rs[0], rs[1], rs[2], rs[3]);
+    }
+  }
+
   // C[gm, n0 .. n0+NCOL) = epilogue(alpha * r + beta * C); `part` indexes this thread's row-sum partial
-  __device__ __forceinline__ void store(const GemmArgs& g, int64_t gm, int64_t n0, int part) {
+  __device__ __forceinline__ void store(const GemmArgs& g, int64_t gm, int64_t n0, int part, int lane) {
+    if (g.vec_store) { store_vec(g, gm - lane, n0, part, lane); return; }
     using SplitT = typename std::conditional<KIND == KIND_BF16X3, __nv_bfloat16, float>::type;
     if (gm >= g.M) return;
     const float alpha = g.alpha, beta = g.beta;
@@ -531,7 +648,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         mbar_arrive(&tempty[a]);  // the accumulator is free as soon as it is in registers
         if (++a == 2) { a = 0; aph ^= 1; }
       }
-      acc.store(g, (int64_t)tm * BM + q * 32 + lane, (int64_t)tn * BN + half * (BN / 2), tn * 2 + half);
+      acc.store(g, (int64_t)tm * BM + q * 32 + lane, (int64_t)tn * BN + half * (BN / 2), tn * 2 + half, lane);
     }
   }
 
@@ -758,7 +875,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         if (++a == 2) { a = 0; aph ^= 1; }
       }
       acc.store(g, (int64_t)tm * 256 + (int64_t)rank * 128 + q * 32 + lane, (int64_t)tn * BN + half * (BN / 2),
-                tn * 2 + half);
+                tn * 2 + half, lane);
     }
   }
 
@@ -891,7 +1008,8 @@ int32_t launch_pair(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
     attr_done = true;
   }
   const int ntiles = g.tiles_m * g.tiles_n;
-  const int max_pairs = ctx->num_sms / 2;
+  int max_pairs = ctx->num_sms / 2;
+  if (const char* e = getenv("NB_GEMM_PAIRS")) max_pairs = atoi(e) > 0 && atoi(e) < max_pairs ? atoi(e) : max_pairs;
   const int pairs = ntiles < max_pairs ? ntiles : max_pairs;
   k_gemm_tc_pair<<<2 * pairs, NTHREADS, Cfg2::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
   NB_LAUNCH_CHECK(ctx);
@@ -1107,6 +1225,18 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
         }
         g.epi.s_hi = e_hi; g.epi.s_lo = e_lo; g.epi.ld_s = e_ld;
       }
+    }
+    {
+      auto al16 = [](const void* p) { return ((uintptr_t)p & 15) == 0; };
+      bool v = (m % 4 == 0) && (ldc % 4 == 0) && al16(C);
+      if (fused) {
+        if (g.epi.bias) v = v && al16(g.epi.bias);
+        if (g.epi.y) v = v && al16(g.epi.y) && (g.epi.ldy % 4 == 0);
+        if (g.epi.rowsum_partial) v = v && al16(g.epi.rowsum_partial);
+        if (g.epi.s_hi) v = v && al16(g.epi.s_hi) && al16(g.epi.s_lo) && (g.epi.ld_s % 8 == 0);
+      }
+      if (const char* e = getenv("NB_GEMM_VEC_STORE")) v = v && atoi(e) != 0;
+      g.vec_store = v ? 1 : 0;
     }
     // long K is launched in ranges so that the operand panel of a rasterisation group fits the L2
     int64_t KRANGE = 8192;
