@@ -111,11 +111,13 @@ struct GemmArgs {
 
 constexpr int SCHED_SLOTS = 4;
 
-// Tile rasterisation: groups of `group_m` tile-rows are swept along n with m fastest inside the group.
-// The A panel of one group (group_m x tile rows x K range) is re-used by every tile column of the sweep,
-// so the host sizes group_m to keep that panel (~48 MB) resident in the 126 MB L2 and launches long K
-// in ranges of 8192 (ncu on the first version, group of 16 x 256 rows x K = 8192: 27.7 GB of DRAM traffic
-// for 2.4 GB of algorithmic bytes — the panel did not fit and A was re-read for every tile column).
+// Tile rasterisation: groups of `group_m` tile-rows are swept along n with m fastest inside the group, so the
+// ~74 tiles in flight form a group_m x ~9 block that shares group_m A panels and ~9 B panels; long K is launched
+// in ranges of 8192.  Measured (ncu, 8192x32768x8192 BF16x3, tools/gemm_knob_ab.sh): the operands are still read
+// ~6x from DRAM (14-18 GB for 2.4 GB algorithmic, 88 GB of L2->SM traffic) for every group size, L2 eviction
+// hint and K range tried — the panel set of a wave (17 panels x 8.4 MB) exceeds what the two-partition L2 keeps
+// of data shared by all SMs — but DRAM runs at ~2 TB/s of 6.5 and the tensor pipe stays 99.6 % active; group_m = 8
+// is 3 % faster than 5 under the power cap.
 __device__ __forceinline__ void tile_coords(int t, int tiles_m, int tiles_n, int group_m, int& tm, int& tn) {
   const int per_group = group_m * tiles_n;
   const int group = t / per_group;
@@ -1251,7 +1253,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
       if (h & 2) g.hint_b = L2_EVICT_LAST;
       if (h & 4) { if (!(h & 1)) g.hint_a = L2_EVICT_FIRST; if (!(h & 2)) g.hint_b = L2_EVICT_FIRST; }
     }
-    int64_t panel_budget = 48ll << 20;
+    int64_t panel_budget = 70ll << 20;  // group of 8 pair-tile rows at K = 8192 (A/B on the forward shape: 3 % faster than 5)
     if (const char* e = getenv("NB_GEMM_PANEL_MB")) panel_budget = (int64_t)atoi(e) << 20;
     const int nsplit_bytes = esize * (kind == KIND_TF32 ? 1 : 2);
     for (int64_t kb = 0; kb < k && rc == NB_OK; kb += KRANGE) {

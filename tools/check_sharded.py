@@ -56,6 +56,24 @@ if rank == 0:
     print(f"world={world} overlapped: max rel grad err {err:.3e}, objective rel err {yerr:.3e}", flush=True)
     assert err < 1e-10 and yerr < 1e-10
 dist.barrier()
+# Float32 with the deferred / fused product launches (fusion.py): sharded vs single-rank, both drivers
+W, b, X, Y = wl.mlp_inputs((784, 512, 256, 10), 2048, np.float32, seed=1)
+lo, hi = nb.shard_bounds(2048, rank, world)
+Xd, Yd = ctx.asarray(X[:, lo:hi]), ctx.asarray(Y[:, lo:hi])
+params = [ctx.asarray(p) for p in (*W, *b)]
+sg = nb.ShardedGradient(lambda ps: wl.mlp_objective(nb, Xd, Yd, 1e-3, 3, prior_scale=ps), params, comm)
+og = nb.OverlappedShardedGradient(wl.mlp_data_objective(nb, Xd, Yd, 3), wl.mlp_prior_objective(nb, 1e-3, 3), params, comm)
+for name, drv in (("sharded", sg), ("overlapped", og)):
+    for it in range(2):
+        y, grads = drv.step()
+    ctx.sync()
+    if rank == 0:
+        Xf, Yf = ctx.asarray(X), ctx.asarray(Y)
+        yr, gr = nb.nabla(wl.mlp_objective(nb, Xf, Yf, 1e-3, 3), get_output=True)(*params)
+        err = max(np.linalg.norm(g.numpy() - r.numpy()) / np.linalg.norm(r.numpy()) for g, r in zip(grads, gr))
+        print(f"world={world} f32 fused {name}: max rel grad err {err:.3e}", flush=True)
+        assert err < 1e-4
+    dist.barrier()
 comm.close()
 dist.destroy_process_group()
 if rank == 0:
