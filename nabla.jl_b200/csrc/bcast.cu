@@ -161,6 +161,143 @@ struct GenEv {
   }
 };
 
+// Composite programs, shared-memory interpreter.  The previous evaluator (GenEv above, kept for programs whose
+// slots do not fit) holds the slot values of a thread in local memory and decodes with compare chains: ncu
+// (profiles/: k_tall<float, GenEv> on (a,b)->tanh(a+b)) counted 142 thread-instructions per ELEMENT for a
+// two-instruction program, a quarter of them ISETP/BRA, at 10-12 % of the HBM peak.  Here
+//   * every thread owns a 16-byte column per slot in dynamic shared memory (slot s of thread t at
+//     base[(s*NT + t)*V]: conflict-free 128-bit accesses, no local memory),
+//   * the opcode switch is a dense jump table (nb_prog::hop), decoded once per V elements,
+//   * the reverse sweep reads only what each partial needs and stores — instead of zero-filling and
+//     accumulating — the first contribution to every adjoint (nb_prog::rflags, computed once on the host).
+template <typename T, int V>
+struct GenEvS {
+  static constexpr int MAXOUT = NB_MAX_ARGS;
+  using VT = typename std::conditional<V == 1, T, typename VecOf<T>::type>::type;
+
+  static __device__ __forceinline__ void run(const MRP& P, const nb_prog& G, int64_t r, int64_t c,
+                                             int nvalid, T (&o)[MAXOUT][V]) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int NT = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
+    VT* base = reinterpret_cast<VT*>(smem_raw + P.slot_off) + tid;
+    const int na = G.nargs, n = G.n_instr, nslots = na + n;
+    auto ld = [&](int s, T (&x)[V]) {
+      const VT v = base[(size_t)s * NT];
+      const T* e = reinterpret_cast<const T*>(&v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) x[i] = e[i];
+    };
+    auto st = [&](int s, const T (&x)[V]) {
+      VT v;
+      T* e = reinterpret_cast<T*>(&v);
+#pragma unroll
+      for (int i = 0; i < V; ++i) e[i] = x[i];
+      base[(size_t)s * NT] = v;
+    };
+    auto get = [&](int idx, T (&x)[V]) {  // slot value or constant
+      if (idx >= 0) ld(idx, x);
+      else {
+        const T cst = T(G.consts[-idx - 1]);
+#pragma unroll
+        for (int i = 0; i < V; ++i) x[i] = cst;
+      }
+    };
+    const bool vok = P.vec_ok;
+    T last[V];
+    for (int k = 0; k < na; ++k) {
+      load_vals<T, V>(P.arg[k].p, r * P.arg[k].rs + c * P.arg[k].cs, P.arg[k].rs != 0, nvalid, vok, last);
+      st(k, last);
+    }
+    // forward
+    for (int i = 0; i < n; ++i) {
+      T a[V], b[V];
+      get(G.a[i], a);
+      if (G.hop[i] >= NB_HOP_ADD && G.hop[i] != NB_HOP_COLD_UN) get(G.b[i], b);
+      else {
+#pragma unroll
+        for (int v = 0; v < V; ++v) b[v] = T(0);
+      }
+      nb_eval_hop<T, V>(G.hop[i], G.op[i], a, b, last);
+      st(na + i, last);
+    }
+    if (!P.pullback) {
+#pragma unroll
+      for (int i = 0; i < V; ++i) o[0][i] = last[i];
+      return;
+    }
+    // reverse: adjoint of slot s lives in slot nslots + s
+    for (int i = n - 1; i >= 0; --i) {
+      const int fl = G.rflags[i];
+      if (!(fl & NB_RF_LIVE)) continue;
+      const int ia = G.a[i], ib = G.b[i];
+      T g[V], a[V], b[V], y[V], da[V], db[V];
+      if (i == n - 1) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) g[v] = T(1);
+      } else {
+        ld(nslots + na + i, g);
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) { a[v] = T(0); b[v] = T(0); y[v] = T(0); }
+      if (fl & NB_RF_NEED_A) get(ia, a);
+      if (fl & NB_RF_NEED_B) get(ib, b);
+      if (fl & NB_RF_NEED_Y) ld(na + i, y);
+      nb_partials_hop<T, V>(G.hop[i], G.op[i], a, b, y, da, db);
+      if (fl & NB_RF_SLOT_A) {
+        const bool same = (fl & NB_RF_SLOT_B) && ib == ia;  // f(x, x): both partials go to one adjoint
+        T t[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) t[v] = g[v] * (same ? da[v] + db[v] : da[v]);
+        if (!(fl & NB_RF_FIRST_A)) {
+          T old[V];
+          ld(nslots + ia, old);
+#pragma unroll
+          for (int v = 0; v < V; ++v) t[v] += old[v];
+        }
+        st(nslots + ia, t);
+      }
+      if ((fl & NB_RF_SLOT_B) && ib != ia) {
+        T t[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) t[v] = g[v] * db[v];
+        if (!(fl & NB_RF_FIRST_B)) {
+          T old[V];
+          ld(nslots + ib, old);
+#pragma unroll
+          for (int v = 0; v < V; ++v) t[v] += old[v];
+        }
+        st(nslots + ib, t);
+      }
+    }
+    T yb[V];
+#pragma unroll
+    for (int i = 0; i < V; ++i) yb[i] = T(1);
+    if (P.has_ybar) load_vals<T, V>(P.ybar.p, r * P.ybar.rs + c * P.ybar.cs, P.ybar.rs != 0, nvalid, vok, yb);
+#pragma unroll
+    for (int k = 0; k < MAXOUT; ++k)
+      if (k < P.nout) {
+        const int w = P.out[k].wrt;
+        if (n == 0) {
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[k][i] = yb[i];
+        } else if (G.arg_live & (1u << w)) {
+          T adj[V];
+          ld(nslots + w, adj);
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[k][i] = yb[i] * adj[i];
+        } else {
+#pragma unroll
+          for (int i = 0; i < V; ++i) o[k][i] = T(0);
+        }
+      }
+  }
+};
+
+// bytes of slot storage one thread needs (values + adjoints)
+template <typename T, int V>
+static inline size_t gen_slot_bytes_per_thread(const nb_prog& G) { return (size_t)2 * (G.nargs + G.n_instr) * V * sizeof(T); }
+constexpr size_t GEN_SMEM_LIMIT = 160 * 1024;
+
 // ---- k_flat: cols == 1 ---------------------------------------------------------------------
 template <typename T, template <typename, int> class EvT>
 __global__ void __launch_bounds__(256) k_flat(const MRP P, const nb_prog G) {
@@ -547,10 +684,25 @@ bool lean_any(int kind, int mode, const MRP& P, const LeanLaunch& a, cudaStream_
 
 // lean_mode: LM_* when the call qualifies for the compile-time-specialised kernels, -1 otherwise
 template <typename T, template <typename, int> class Ev>
-int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_mode) {
+int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_mode, bool prog_lean = false) {
   constexpr int V = VecOf<T>::V;
   cudaStream_t st = ctx->stream;
   const int sms = ctx->num_sms;
+  // shared-memory interpreter: slot storage behind the kernel's own dynamic shared memory
+  constexpr bool IS_S = std::is_same<Ev<T, 1>, GenEvS<T, 1>>::value;
+  auto with_slots = [&](auto kern, size_t own, int nthreads, int veff) -> size_t {
+    if (!IS_S) return own;
+    const size_t off = (own + 15) & ~(size_t)15;
+    P.slot_off = (int32_t)off;
+    const size_t total = off + (size_t)2 * (G.nargs + G.n_instr) * veff * sizeof(T) * nthreads;
+    if (total > 32 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)total);
+    return total;
+  };
+  // lean kernels: single primitives (this file and bcast_lean_cold_*.cu) or whole programs (bcast_prog.cu)
+  auto lean_try = [&](int kind, const LeanLaunch& LL) -> bool {
+    if (prog_lean) return nb_lean_prog(sizeof(T) == 4 ? NB_F32 : NB_F64, kind, lean_mode, P, G, LL, st);
+    return lean_any<T>(kind, lean_mode, P, LL, st);
+  };
   struct Pending { void* partial; int64_t nparts, count; int k; };
   std::vector<Pending> pend;
   auto finish = [&]() -> int32_t {
@@ -587,11 +739,14 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
       }
     }
     if (lean_mode >= 0 && P.rows % V == 0 &&
-        lean_any<T>(0, lean_mode, P, LeanLaunch{P.rows / V, (unsigned)blocks, dim3(), dim3(), 0, 0}, st)) {
+        lean_try(0, LeanLaunch{P.rows / V, (unsigned)blocks, dim3(), dim3(), 0, 0})) {
       NB_LAUNCH_CHECK(ctx);
       return finish();
     }
-    k_flat<T, Ev><<<(unsigned)blocks, 256, 0, st>>>(P, G);
+    {
+      const size_t sm = with_slots(k_flat<T, Ev>, 0, 256, V);
+      k_flat<T, Ev><<<(unsigned)blocks, 256, sm, st>>>(P, G);
+    }
     NB_LAUNCH_CHECK(ctx);
     return finish();
   }
@@ -621,7 +776,7 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
         if (P.out[k].mode == OM_ALL) rc = alloc_partial(k, blocks, 1);
         if (rc != NB_OK) return rc;
       }
-      const size_t smem = nkr * per_kr + 32 * sizeof(T);
+      const size_t smem = with_slots(k_short<T, Ev>, nkr * per_kr + 32 * sizeof(T), BT, 1);
       k_short<T, Ev><<<(unsigned)blocks, BT, smem, st>>>(P, G);
       NB_LAUNCH_CHECK(ctx);
       int32_t rc = finish();
@@ -643,7 +798,7 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
       int64_t blocks = (P.cols + 7) / 8;
       const int64_t cap = (int64_t)sms * 8;
       if (blocks > cap) blocks = cap;
-      if (lean_any<T>(2, lean_mode, P, LeanLaunch{0, (unsigned)blocks, dim3(), dim3(), 0, 0}, st)) {
+      if (lean_try(2, LeanLaunch{0, (unsigned)blocks, dim3(), dim3(), 0, 0})) {
         NB_LAUNCH_CHECK(ctx);
         return NB_OK;
       }
@@ -674,8 +829,11 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
     dim3 grid((unsigned)rblocks, (unsigned)slabs), block(TX, TY);
     const size_t smem = (size_t)256 * V * sizeof(T);
     if (!(lean_mode >= 0 && !any_wcol && P.rows % V == 0 &&
-          lean_any<T>(1, lean_mode, P, LeanLaunch{0, 0, grid, block, smem, cps}, st)))
-      k_tall<T, Ev><<<grid, block, smem, st>>>(P, G, cps);
+          lean_try(1, LeanLaunch{0, 0, grid, block, smem, cps})))
+    {
+      const size_t sm = with_slots(k_tall<T, Ev>, smem, 256, V);
+      k_tall<T, Ev><<<grid, block, sm, st>>>(P, G, cps);
+    }
     NB_LAUNCH_CHECK(ctx);
     int32_t rc = finish();
     if (rc != NB_OK) return rc;
@@ -685,7 +843,8 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
     int64_t blocks = (P.cols + 7) / 8;
     const int64_t cap = (int64_t)sms * 8;
     if (blocks > cap) blocks = cap;
-    k_wcol<T, Ev><<<(unsigned)blocks, 256, 0, st>>>(P, G);
+    const size_t sm = with_slots(k_wcol<T, Ev>, 0, 256, V);
+    k_wcol<T, Ev><<<(unsigned)blocks, 256, sm, st>>>(P, G);
     NB_LAUNCH_CHECK(ctx);
   }
   return NB_OK;
@@ -889,10 +1048,22 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
         P.has_y = C.ysaved != nullptr;
       }
     }
+    // composite programs with one or two array operands: the interpreter inside the lean kernels (bcast_prog.cu)
+    int pmode = -1;
+    if (!fast && P.vec_ok && C.nargs <= 2 && !getenv("NB_GEN_NOLEAN")) {
+      if (!C.pullback) pmode = LM_FWD;
+      else if (C.nout == 1 && (C.out_wrt[0] == 0 || C.out_wrt[0] == 1)) pmode = C.out_wrt[0] == 0 ? LM_PULL_A : LM_PULL_B;
+      else if (C.nout == 2 && C.out_wrt[0] == 0 && C.out_wrt[1] == 1) pmode = LM_PULL_AB;
+      if (pmode == LM_PULL_B && C.nargs == 1) pmode = -1;
+    }
+    // otherwise: shared-memory interpreter when the slots of a 256-thread CTA fit
+    const bool use_s = (size_t)2 * (G.nargs + G.n_instr) * 16 * 256 <= GEN_SMEM_LIMIT && !getenv("NB_GEN_LOCAL");
     if (dt == NB_F32) return fast ? launch_all<float, FastEv>(ctx, P, G, ng, lean_mode)
-                                  : launch_all<float, GenEv>(ctx, P, G, ng, -1);
+                           : use_s ? launch_all<float, GenEvS>(ctx, P, G, ng, pmode, true)
+                                   : launch_all<float, GenEv>(ctx, P, G, ng, pmode, true);
     return fast ? launch_all<double, FastEv>(ctx, P, G, ng, lean_mode)
-                : launch_all<double, GenEv>(ctx, P, G, ng, -1);
+         : use_s ? launch_all<double, GenEvS>(ctx, P, G, ng, pmode, true)
+                 : launch_all<double, GenEv>(ctx, P, G, ng, pmode, true);
   }
 
   // ---- generic N-D fallback: one launch per output ------------------------------------------
@@ -969,6 +1140,7 @@ int32_t nb_prog_create(int32_t nargs, int32_t n_instr, const int32_t* ops, const
     }
     p->op[i] = op; p->a[i] = a[i]; p->b[i] = bi ? b[i] : 0;
   }
+  nb_prog_derive(*p);
   *out = p;
   return NB_OK;
 }

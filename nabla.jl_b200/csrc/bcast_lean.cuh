@@ -43,13 +43,24 @@ __device__ __forceinline__ void lean_ld(const Opnd& o, int64_t r, int64_t c, T (
   }
 }
 
+struct LeanNoExtra {};
+
 template <typename T, int V, int OP, int MODE>
 struct LeanPack {
+  using Extra = LeanNoExtra;
+  static constexpr int NOUT = MODE == LM_PULL_AB ? 2 : 1;
+  static constexpr int U = 4;  // independent vectors in flight per thread
   static constexpr int NEED = LeanNeeds<OP, MODE>::value;
   T a[(NEED & 1) ? V : 1], b[(NEED & 2) ? V : 1], y[(NEED & 4) ? V : 1], yb[MODE != LM_FWD ? V : 1];
 
+  template <int N>
+  static __device__ __forceinline__ void compute_many(const MRP&, const Extra&, const LeanPack (&x)[N], T (&o)[N][2][V]) {
+#pragma unroll
+    for (int u = 0; u < N; ++u) x[u].compute(o[u]);
+  }
+
   // recompute flag: the partial needs y but no saved forward value was passed -> needs a and b
-  __device__ __forceinline__ void load(const MRP& P, int64_t r, int64_t c) {
+  __device__ __forceinline__ void load(const MRP& P, const Extra&, int64_t r, int64_t c) {
     if constexpr ((NEED & 1) != 0) {
       if (P.load_mask & 1) lean_ld<T, V>(P.arg[0], r, c, a);
       else {
@@ -119,12 +130,11 @@ __device__ __forceinline__ void lean_store(const OutS& out, int64_t off, const T
 }
 
 // ---- flat: cols == 1, N = P.rows elements, N % V == 0 handled by the caller (tail launch) ----------
-template <typename T, int OP, int MODE>
-__global__ void __launch_bounds__(256) k_flat_lean(const MRP P, int64_t nvec) {
+template <typename T, typename Pk>
+__global__ void __launch_bounds__(256) k_flat_lean(const MRP P, int64_t nvec, const typename Pk::Extra X) {
   constexpr int V = VecOf<T>::V;
-  constexpr int U = 4;
-  constexpr int NOUT = MODE == LM_PULL_AB ? 2 : 1;
-  using Pk = LeanPack<T, V, OP, MODE>;
+  constexpr int U = Pk::U;
+  constexpr int NOUT = Pk::NOUT;
   __shared__ T red[32];
   T accs[NOUT];
 #pragma unroll
@@ -135,11 +145,12 @@ __global__ void __launch_bounds__(256) k_flat_lean(const MRP P, int64_t nvec) {
   for (; i + (U - 1) * S < nvec; i += U * S) {
     Pk x[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) x[u].load(P, (i + u * S) * V, 0);
+    for (int u = 0; u < U; ++u) x[u].load(P, X, (i + u * S) * V, 0);
+    T oo[U][2][V];
+    Pk::template compute_many<U>(P, X, x, oo);
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      T o[2][V];
-      x[u].compute(o);
+      T (&o)[2][V] = oo[u];
 #pragma unroll
       for (int k = 0; k < NOUT; ++k) {
         if (P.out[k].mode == OM_ELEM) lean_store<T, V>(P.out[k], (i + u * S) * V, o[k], scale);
@@ -151,10 +162,11 @@ __global__ void __launch_bounds__(256) k_flat_lean(const MRP P, int64_t nvec) {
     }
   }
   for (; i < nvec; i += S) {
-    Pk x;
-    x.load(P, i * V, 0);
-    T o[2][V];
-    x.compute(o);
+    Pk x1[1];
+    x1[0].load(P, X, i * V, 0);
+    T o1[1][2][V];
+    Pk::template compute_many<1>(P, X, x1, o1);
+    T (&o)[2][V] = o1[0];
 #pragma unroll
     for (int k = 0; k < NOUT; ++k) {
       if (P.out[k].mode == OM_ELEM) lean_store<T, V>(P.out[k], i * V, o[k], scale);
@@ -173,12 +185,11 @@ __global__ void __launch_bounds__(256) k_flat_lean(const MRP P, int64_t nvec) {
 }
 
 // ---- tall: rows % V == 0, threads along rows, CTAs tile rows x column slabs --------------------------
-template <typename T, int OP, int MODE>
-__global__ void __launch_bounds__(256) k_tall_lean(const MRP P, int64_t cols_per_slab) {
+template <typename T, typename Pk>
+__global__ void __launch_bounds__(256) k_tall_lean(const MRP P, int64_t cols_per_slab, const typename Pk::Extra X) {
   constexpr int V = VecOf<T>::V;
-  constexpr int U = 4;
-  constexpr int NOUT = MODE == LM_PULL_AB ? 2 : 1;
-  using Pk = LeanPack<T, V, OP, MODE>;
+  constexpr int U = Pk::U;
+  constexpr int NOUT = Pk::NOUT;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
   const int tx = threadIdx.x, ty = threadIdx.y, TX = blockDim.x, TY = blockDim.y;
@@ -197,11 +208,12 @@ __global__ void __launch_bounds__(256) k_tall_lean(const MRP P, int64_t cols_per
     for (; c + (int64_t)(U - 1) * TY < c1; c += (int64_t)U * TY) {
       Pk x[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) x[u].load(P, r0, c + (int64_t)u * TY);
+      for (int u = 0; u < U; ++u) x[u].load(P, X, r0, c + (int64_t)u * TY);
+      T oo[U][2][V];
+      Pk::template compute_many<U>(P, X, x, oo);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        T o[2][V];
-        x[u].compute(o);
+        T (&o)[2][V] = oo[u];
         const int64_t cc = c + (int64_t)u * TY;
 #pragma unroll
         for (int k = 0; k < NOUT; ++k) {
@@ -214,10 +226,11 @@ __global__ void __launch_bounds__(256) k_tall_lean(const MRP P, int64_t cols_per
       }
     }
     for (; c < c1; c += TY) {
-      Pk x;
-      x.load(P, r0, c);
-      T o[2][V];
-      x.compute(o);
+      Pk x1[1];
+      x1[0].load(P, X, r0, c);
+      T o1[1][2][V];
+      Pk::template compute_many<1>(P, X, x1, o1);
+      T (&o)[2][V] = o1[0];
 #pragma unroll
       for (int k = 0; k < NOUT; ++k) {
         if (P.out[k].mode == OM_ELEM) lean_store<T, V>(P.out[k], r0 * P.out[k].rs + c * P.out[k].cs, o[k], scale);
@@ -266,12 +279,11 @@ __global__ void __launch_bounds__(256) k_tall_lean(const MRP P, int64_t cols_per
 }
 
 // ---- wcol: one warp per column, rows % V == 0; outputs ELEM / KEEP_COLS (reduce over the rows) ------
-template <typename T, int OP, int MODE>
-__global__ void __launch_bounds__(256) k_wcol_lean(const MRP P) {
+template <typename T, typename Pk>
+__global__ void __launch_bounds__(256) k_wcol_lean(const MRP P, const typename Pk::Extra X) {
   constexpr int V = VecOf<T>::V;
-  constexpr int U = 4;
-  constexpr int NOUT = MODE == LM_PULL_AB ? 2 : 1;
-  using Pk = LeanPack<T, V, OP, MODE>;
+  constexpr int U = Pk::U;
+  constexpr int NOUT = Pk::NOUT;
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -285,11 +297,12 @@ __global__ void __launch_bounds__(256) k_wcol_lean(const MRP P) {
     for (; r + (U - 1) * STEP < P.rows; r += U * STEP) {
       Pk x[U];
 #pragma unroll
-      for (int u = 0; u < U; ++u) x[u].load(P, r + u * STEP, c);
+      for (int u = 0; u < U; ++u) x[u].load(P, X, r + u * STEP, c);
+      T oo[U][2][V];
+      Pk::template compute_many<U>(P, X, x, oo);
 #pragma unroll
       for (int u = 0; u < U; ++u) {
-        T o[2][V];
-        x[u].compute(o);
+        T (&o)[2][V] = oo[u];
 #pragma unroll
         for (int k = 0; k < NOUT; ++k) {
           if (P.out[k].mode == OM_ELEM)
@@ -302,10 +315,11 @@ __global__ void __launch_bounds__(256) k_wcol_lean(const MRP P) {
       }
     }
     for (; r < P.rows; r += STEP) {
-      Pk x;
-      x.load(P, r, c);
-      T o[2][V];
-      x.compute(o);
+      Pk x1[1];
+      x1[0].load(P, X, r, c);
+      T o1[1][2][V];
+      Pk::template compute_many<1>(P, X, x1, o1);
+      T (&o)[2][V] = o1[0];
 #pragma unroll
       for (int k = 0; k < NOUT; ++k) {
         if (P.out[k].mode == OM_ELEM) lean_store<T, V>(P.out[k], r * P.out[k].rs + c * P.out[k].cs, o[k], scale);
@@ -329,17 +343,17 @@ __global__ void __launch_bounds__(256) k_wcol_lean(const MRP P) {
 
 template <typename T, int OP, int MODE>
 void lean_launch_wcol(const MRP& P, unsigned blocks, cudaStream_t st) {
-  k_wcol_lean<T, OP, MODE><<<blocks, 256, 0, st>>>(P);
+  k_wcol_lean<T, LeanPack<T, VecOf<T>::V, OP, MODE>><<<blocks, 256, 0, st>>>(P, LeanNoExtra{});
 }
 
 // ---- dispatch ------------------------------------------------------------------------------------
 template <typename T, int OP, int MODE>
 void lean_launch_flat(const MRP& P, int64_t nvec, unsigned blocks, cudaStream_t st) {
-  k_flat_lean<T, OP, MODE><<<blocks, 256, 0, st>>>(P, nvec);
+  k_flat_lean<T, LeanPack<T, VecOf<T>::V, OP, MODE>><<<blocks, 256, 0, st>>>(P, nvec, LeanNoExtra{});
 }
 template <typename T, int OP, int MODE>
 void lean_launch_tall(const MRP& P, dim3 grid, dim3 block, size_t smem, int64_t cps, cudaStream_t st) {
-  k_tall_lean<T, OP, MODE><<<grid, block, smem, st>>>(P, cps);
+  k_tall_lean<T, LeanPack<T, VecOf<T>::V, OP, MODE>><<<grid, block, smem, st>>>(P, cps, LeanNoExtra{});
 }
 
 // F is a functor template taking <OP, MODE>; returns false when (op, mode) is not a lean combination

@@ -32,6 +32,7 @@ struct MRP {
   int32_t load_mask; // which operands are actually read
   int32_t has_ybar, has_y, need_y;
   int32_t vec_ok;    // all contiguous operands 16B-aligned with compatible strides
+  int32_t slot_off;  // GenEvS: byte offset of the interpreter's slot storage in dynamic shared memory
   double cval[NB_FAST_NIN];  // fast: value of a constant operand
   int32_t is_const[NB_FAST_NIN];
   double scale;
@@ -84,3 +85,6 @@ bool nb_lean_cold_un_f32(int kind, int op, int mode, const nbb::MRP& P, const nb
 bool nb_lean_cold_un_f64(int kind, int op, int mode, const nbb::MRP& P, const nbb::LeanLaunch& a, cudaStream_t st);
 bool nb_lean_cold_bin_f32(int kind, int op, int mode, const nbb::MRP& P, const nbb::LeanLaunch& a, cudaStream_t st);
 bool nb_lean_cold_bin_f64(int kind, int op, int mode, const nbb::MRP& P, const nbb::LeanLaunch& a, cudaStream_t st);
+// composite programs on the lean kernels (bcast_prog.cu)
+struct nb_prog;
+bool nb_lean_prog(int dtype, int kind, int mode, const nbb::MRP& P, const nb_prog& G, const nbb::LeanLaunch& a, cudaStream_t st);

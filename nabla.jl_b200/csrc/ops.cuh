@@ -16,6 +16,21 @@ struct nb_prog {
   int32_t a[NB_MAX_INSTR];
   int32_t b[NB_MAX_INSTR];
   double consts[NB_MAX_CONSTS];
+  // derived by nb_prog_create for the shared-memory interpreter (GenEvS in bcast.cu)
+  uint8_t hop[NB_MAX_INSTR];     // dense dispatch index (NB_HOP_*): the switch becomes a jump table
+  uint8_t rflags[NB_MAX_INSTR];  // NB_RF_* : what the reverse step of instruction i reads and how it writes
+  uint32_t arg_live;             // bit k: operand k reaches the result (otherwise its sensitivity is zero)
+};
+
+enum {
+  NB_HOP_IDENTITY = 0, NB_HOP_NEG, NB_HOP_ABS2, NB_HOP_SQRT, NB_HOP_INV, NB_HOP_EXP, NB_HOP_LOG, NB_HOP_TANH,
+  NB_HOP_LOGISTIC, NB_HOP_ADD, NB_HOP_SUB, NB_HOP_MUL, NB_HOP_DIV, NB_HOP_COLD_UN, NB_HOP_COLD_BIN
+};
+enum {
+  NB_RF_NEED_A = 1, NB_RF_NEED_B = 2, NB_RF_NEED_Y = 4,  // values the partials read
+  NB_RF_FIRST_A = 8, NB_RF_FIRST_B = 16,                 // first contribution to that adjoint: store, do not add
+  NB_RF_SLOT_A = 32, NB_RF_SLOT_B = 64,                  // operand is a slot (not a constant) -> gets an adjoint
+  NB_RF_LIVE = 128                                       // the instruction reaches the result
 };
 
 #define NB_PI 3.14159265358979323846
@@ -324,6 +339,99 @@ __device__ __forceinline__ void nb_prog_grad(const nb_prog& P, const T* vals, T*
       if (P.a[i] >= 0) adj[P.a[i]] += g * nb_dunary<T>(op, a, y);
     }
   }
+}
+
+// Fill the derived fields of a validated program (host, nb_prog_create).
+inline void nb_prog_derive(nb_prog& P) {
+  auto hop_of = [](int op) -> uint8_t {
+    switch (op) {
+      case NB_OP_IDENTITY: return NB_HOP_IDENTITY; case NB_OP_NEG: return NB_HOP_NEG;
+      case NB_OP_ABS2: return NB_HOP_ABS2; case NB_OP_SQRT: return NB_HOP_SQRT; case NB_OP_INV: return NB_HOP_INV;
+      case NB_OP_EXP: return NB_HOP_EXP; case NB_OP_LOG: return NB_HOP_LOG; case NB_OP_TANH: return NB_HOP_TANH;
+      case NB_OP_LOGISTIC: return NB_HOP_LOGISTIC; case NB_OP_ADD: return NB_HOP_ADD;
+      case NB_OP_SUB: return NB_HOP_SUB; case NB_OP_MUL: return NB_HOP_MUL; case NB_OP_DIV: return NB_HOP_DIV;
+      default: return nb_op_is_binary(op) ? NB_HOP_COLD_BIN : NB_HOP_COLD_UN;
+    }
+  };
+  const int n = P.n_instr, na = P.nargs;
+  bool live[NB_MAX_INSTR] = {false};
+  bool written[NB_MAX_SLOTS] = {false};
+  if (n > 0) live[n - 1] = true;
+  for (int i = n - 1; i >= 0; --i) {
+    P.hop[i] = hop_of(P.op[i]);
+    P.rflags[i] = 0;
+    if (!live[i]) continue;
+    const bool bin = nb_op_is_binary(P.op[i]);
+    const int a = P.a[i], b = bin ? P.b[i] : -1;
+    uint8_t f = NB_RF_LIVE;
+    int needs = 0;
+    if (a >= 0) { f |= NB_RF_SLOT_A; needs |= nb_partial_needs(P.op[i], 0); }
+    if (bin && b >= 0) { f |= NB_RF_SLOT_B; needs |= nb_partial_needs(P.op[i], 1); }
+    if (needs & 1) f |= NB_RF_NEED_A;
+    if (needs & 2) f |= NB_RF_NEED_B;
+    if (needs & 4) f |= NB_RF_NEED_Y;
+    if (a >= 0) {
+      if (!written[a]) { f |= NB_RF_FIRST_A; written[a] = true; }
+      if (a >= na) live[a - na] = true;
+    }
+    if (bin && b >= 0 && b != a) {
+      if (!written[b]) { f |= NB_RF_FIRST_B; written[b] = true; }
+      if (b >= na) live[b - na] = true;
+    }
+    P.rflags[i] = f;
+  }
+  P.arg_live = 0;
+  for (int k = 0; k < na; ++k)
+    if (written[k] || n == 0) P.arg_live |= 1u << k;
+}
+
+// value of instruction `hop` (dense index) on V elements: a jump table instead of a compare chain
+template <typename T, int V>
+__device__ __forceinline__ void nb_eval_hop(int hop, int op, const T (&a)[V], const T (&b)[V], T (&r)[V]) {
+#define NB_HOP_CASE(H, EXPR) \
+  case H:                    \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) { const T x = a[v], y = b[v]; (void)y; r[v] = (EXPR); } \
+    break;
+  switch (hop) {
+    NB_HOP_CASE(NB_HOP_IDENTITY, x) NB_HOP_CASE(NB_HOP_NEG, -x) NB_HOP_CASE(NB_HOP_ABS2, x * x)
+    NB_HOP_CASE(NB_HOP_SQRT, sqrt(x)) NB_HOP_CASE(NB_HOP_INV, T(1) / x) NB_HOP_CASE(NB_HOP_EXP, exp(x))
+    NB_HOP_CASE(NB_HOP_LOG, log(x)) NB_HOP_CASE(NB_HOP_TANH, tanh(x))
+    NB_HOP_CASE(NB_HOP_LOGISTIC, T(1) / (T(1) + exp(-x))) NB_HOP_CASE(NB_HOP_ADD, x + y)
+    NB_HOP_CASE(NB_HOP_SUB, x - y) NB_HOP_CASE(NB_HOP_MUL, x * y) NB_HOP_CASE(NB_HOP_DIV, x / y)
+    default:
+#pragma unroll
+      for (int v = 0; v < V; ++v) r[v] = nb_eval_cold<T>(op, a[v], b[v]);
+  }
+#undef NB_HOP_CASE
+}
+
+// partials of instruction `hop` at (a, b) with value y, V-wide
+template <typename T, int V>
+__device__ __forceinline__ void nb_partials_hop(int hop, int op, const T (&a)[V], const T (&b)[V], const T (&y)[V],
+                                                T (&da)[V], T (&db)[V]) {
+#define NB_HOP_D(H, EA, EB)  \
+  case H:                    \
+    _Pragma("unroll") for (int v = 0; v < V; ++v) { const T x = a[v], z = b[v], w = y[v]; (void)x; (void)z; (void)w; \
+      da[v] = (EA); db[v] = (EB); } \
+    break;
+  switch (hop) {
+    NB_HOP_D(NB_HOP_IDENTITY, T(1), T(0)) NB_HOP_D(NB_HOP_NEG, T(-1), T(0)) NB_HOP_D(NB_HOP_ABS2, T(2) * x, T(0))
+    NB_HOP_D(NB_HOP_SQRT, T(0.5) / w, T(0)) NB_HOP_D(NB_HOP_INV, -(w * w), T(0)) NB_HOP_D(NB_HOP_EXP, w, T(0))
+    NB_HOP_D(NB_HOP_LOG, T(1) / x, T(0)) NB_HOP_D(NB_HOP_TANH, T(1) - w * w, T(0))
+    NB_HOP_D(NB_HOP_LOGISTIC, w * (T(1) - w), T(0)) NB_HOP_D(NB_HOP_ADD, T(1), T(1)) NB_HOP_D(NB_HOP_SUB, T(1), T(-1))
+    NB_HOP_D(NB_HOP_MUL, z, x) NB_HOP_D(NB_HOP_DIV, T(1) / z, -w / z)
+    case NB_HOP_COLD_BIN:
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        da[v] = nb_dbinary<T>(op, 0, a[v], b[v], y[v]);
+        db[v] = nb_dbinary<T>(op, 1, a[v], b[v], y[v]);
+      }
+      break;
+    default:
+#pragma unroll
+      for (int v = 0; v < V; ++v) { da[v] = nb_dunary_cold<T>(op, a[v], y[v]); db[v] = T(0); }
+  }
+#undef NB_HOP_D
 }
 
 // ---- V-wide program interpreter: one opcode decode per V elements --------------------------------
