@@ -715,6 +715,30 @@ __device__ __forceinline__ void mbar_arrive_cta(uint64_t* bar, uint32_t cta) {
       ::"r"(smem_u32(bar)), "r"(cta)
       : "memory");
 }
+// wait on a LOCAL barrier whose arrivals (and the data they publish) come from the peer CTA: cluster-scope acquire
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  const long long t0 = clock64();
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if (clock64() - t0 > 20000000000LL) __trap();
+  }
+}
+__device__ __forceinline__ void st_shared_cta(const void* local_addr, uint32_t cta, int32_t v) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "st.shared::cluster.u32 [ra], %2;\n\t}"
+      ::"r"(smem_u32(local_addr)), "r"(cta), "r"(v)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                  uint32_t accumulate) {
   asm volatile(
@@ -751,18 +775,26 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   uint64_t* empty = bars + STAGES;
   uint64_t* tfull = bars + 2 * STAGES;
   uint64_t* tempty = bars + 2 * STAGES + 2;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4);
+  // tile scheduler ring: the leader's producer takes pair-tile indices from a global counter and publishes them to
+  // every role of BOTH CTAs (sched_tile / sfull in each CTA's shared memory, written remotely for the peer); all
+  // consumers release a slot on the LEADER's sempty.  A pair that shares its SMs with an NCCL kernel (the
+  // overlapped allreduce) then simply takes fewer tiles instead of delaying the whole product.
+  uint64_t* sfull = bars + 2 * STAGES + 4;                 // [SCHED_SLOTS]
+  uint64_t* sempty = bars + 2 * STAGES + 4 + SCHED_SLOTS;  // [SCHED_SLOTS] (leader's copy is the one used)
+  uint32_t* tmem_slot = (uint32_t*)(bars + 2 * STAGES + 4 + 2 * SCHED_SLOTS);
+  volatile int32_t* sched_tile = (volatile int32_t*)(tmem_slot + 2);  // [SCHED_SLOTS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int npairs = gridDim.x >> 1, pair = blockIdx.x >> 1;
   const int ntiles = g.tiles_m * g.tiles_n;  // pair tiles (256 x 256)
   const int nkb = (int)((g.k_end - g.k_begin + BK - 1) / BK);
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_THREADS); }
+    // consumers of a slot: leader MMA thread + peer producer + the epilogue threads of both CTAs
+    for (int q = 0; q < SCHED_SLOTS; ++q) { mbar_init(&sfull[q], 1); mbar_init(&sempty[q], 2 + 2 * EPI_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -780,9 +812,27 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   if (warp == 0) {
     // ===================== TMA producer (both CTAs, each its own halves) =====================
     if (lane == 0) {
-      int s = 0;
-      uint32_t ph = 0;
-      for (int t = pair; t < ntiles; t += npairs) {
+      int s = 0, q = 0;
+      uint32_t ph = 0, qph = 0;
+      int t_next = leader ? atomicAdd(g.tile_counter, 1) : 0;
+      for (;;) {
+        int t;
+        if (leader) {
+          // publish this tile (a sentinel >= ntiles ends every role) and request the next one right away
+          t = t_next;
+          mbar_wait_cluster(&sempty[q], qph ^ 1);
+          sched_tile[q] = t;
+          st_shared_cta((const void*)&sched_tile[q], 1, t);
+          mbar_arrive(&sfull[q]);
+          mbar_arrive_cta(&sfull[q], 1);  // release.cluster: the peer sees sched_tile[q]
+          if (t < ntiles) t_next = atomicAdd(g.tile_counter, 1);
+        } else {
+          mbar_wait_cluster(&sfull[q], qph);
+          t = sched_tile[q];
+          mbar_arrive_cta(&sempty[q], 0);
+        }
+        if (++q == SCHED_SLOTS) { q = 0; qph ^= 1; }
+        if (t >= ntiles) break;
         int tm, tn;
         tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
         const int m0 = tm * 256 + (int)rank * 128, n0 = tn * BN + (int)rank * 128;
@@ -823,9 +873,14 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
                              ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t a_kstep = g.a_mn ? KT::MN_KSTEP : 32u;
       const uint32_t b_kstep = g.b_mn ? KT::MN_KSTEP : 32u;
-      int s = 0, a = 0;
-      uint32_t ph = 0, aph = 0;
-      for (int t = pair; t < ntiles; t += npairs) {
+      int s = 0, a = 0, q = 0;
+      uint32_t ph = 0, aph = 0, qph = 0;
+      for (;;) {
+        mbar_wait(&sfull[q], qph);
+        const int t = sched_tile[q];
+        mbar_arrive(&sempty[q]);
+        if (++q == SCHED_SLOTS) { q = 0; qph ^= 1; }
+        if (t >= ntiles) break;
         for (int kb0 = 0; kb0 < nkb; kb0 += g.kchunk_kb) {
           const int kb1 = min(nkb, kb0 + g.kchunk_kb);
           mbar_wait(&tempty[a], aph ^ 1);
@@ -862,10 +917,15 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     // ===================== epilogue (warps 4..11 of both CTAs): this CTA's 128 rows =====================
     const int q = warp & 3;
     const int half = (warp - EPI_WARP0) >> 2;
-    int a = 0;
-    uint32_t aph = 0;
+    int a = 0, q2 = 0;
+    uint32_t aph = 0, q2ph = 0;
     EpiAcc<KIND, BN / 2> acc;
-    for (int t = pair; t < ntiles; t += npairs) {
+    for (;;) {
+      mbar_wait_cluster(&sfull[q2], q2ph);
+      const int t = sched_tile[q2];
+      mbar_arrive_cta(&sempty[q2], 0);
+      if (++q2 == SCHED_SLOTS) { q2 = 0; q2ph ^= 1; }
+      if (t >= ntiles) break;
       int tm, tn;
       tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
       for (int kb0 = 0; kb0 < nkb; kb0 += g.kchunk_kb) {
@@ -1013,6 +1073,7 @@ int32_t launch_pair(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   int max_pairs = ctx->num_sms / 2;
   if (const char* e = getenv("NB_GEMM_PAIRS")) max_pairs = atoi(e) > 0 && atoi(e) < max_pairs ? atoi(e) : max_pairs;
   const int pairs = ntiles < max_pairs ? ntiles : max_pairs;
+  NB_CUDA_OK(ctx, cudaMemsetAsync(g.tile_counter, 0, sizeof(int32_t), ctx->stream));
   k_gemm_tc_pair<<<2 * pairs, NTHREADS, Cfg2::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
