@@ -254,6 +254,11 @@ def extra_measurements(nb, ctx, peaks, quick):
             # reads A, writes Ā and the unbroadcast b̄ (2·N·s + m·s, scalar ȳ)
             "pullback_fused_tanh_add": (lambda: K.bcast_pullback(fused, one, None, [A, b], [Abar, bbar], [False, False]),
                                         2 * N * s + 2 * m * s),
+            # the same with the Branch's saved forward value, as the tape passes it (core.jl:76): tanh is not
+            # re-evaluated; reads A and y, writes Ā and b̄ (3·N·s + 2·m·s)
+            "pullback_fused_tanh_add_saved_y": (lambda: K.bcast_pullback(fused, one, y, [A, b], [Abar, bbar],
+                                                                         [False, False]), 3 * N * s + 2 * m * s),
+            "fwd_fused_tanh_add": (lambda: K.bcast_fwd(fused, [A, b], y), 2 * N * s + m * s),
         }
         res = {}
         for name, (fn, nbytes) in cases.items():

@@ -1055,6 +1055,15 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
       else if (C.nout == 1 && (C.out_wrt[0] == 0 || C.out_wrt[0] == 1)) pmode = C.out_wrt[0] == 0 ? LM_PULL_A : LM_PULL_B;
       else if (C.nout == 2 && C.out_wrt[0] == 0 && C.out_wrt[1] == 1) pmode = LM_PULL_AB;
       if (pmode == LM_PULL_B && C.nargs == 1) pmode = -1;
+      // saved forward value instead of re-evaluating a transcendental last instruction
+      P.need_y = 0;
+      if (pmode > 0 && C.ysaved && G.n_instr > 0) {
+        const int lop = G.op[G.n_instr - 1];
+        const bool y_only = nb_op_is_unary(lop) && nb_partial_needs(lop, 0) == 4;
+        const bool cheap = lop == NB_OP_SQRT || lop == NB_OP_INV;
+        if (y_only && !cheap && (G.rflags[G.n_instr - 1] & NB_RF_LIVE)) P.need_y = 1;
+      }
+      P.has_y = P.need_y;
     }
     // otherwise: shared-memory interpreter when the slots of a 256-thread CTA fit
     const bool use_s = (size_t)2 * (G.nargs + G.n_instr) * 16 * 256 <= GEN_SMEM_LIMIT && !getenv("NB_GEN_LOCAL");

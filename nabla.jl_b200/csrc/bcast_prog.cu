@@ -18,6 +18,9 @@ namespace {
 using namespace nbb;
 #include "bcast_lean.cuh"
 
+__device__ __forceinline__ void unspecified(float& x) { asm("" : "=f"(x)); }
+__device__ __forceinline__ void unspecified(double& x) { asm("" : "=d"(x)); }
+
 template <typename T, int V, int NARGS, int MODE, int UU>
 struct ProgPack {
   using Extra = nb_prog;
@@ -26,11 +29,13 @@ struct ProgPack {
   static constexpr int U = UU;
   T x[NARGS][V];
   T yb[MODE != LM_FWD ? V : 1];
+  T ys[MODE != LM_FWD ? V : 1];  // saved forward value, when it replaces the last (transcendental) instruction
 
   __device__ __forceinline__ void load(const MRP& P, const nb_prog&, int64_t r, int64_t c) {
 #pragma unroll
     for (int k = 0; k < NARGS; ++k) lean_ld<T, V>(P.arg[k], r, c, x[k]);
     if constexpr (MODE != LM_FWD) {
+      if (P.need_y) lean_ld<T, V>(P.ys, r, c, ys);
       if (P.has_ybar) lean_ld<T, V>(P.ybar, r, c, yb);
       else {
 #pragma unroll
@@ -43,21 +48,27 @@ struct ProgPack {
   static __device__ __forceinline__ void compute_many(const MRP& P, const nb_prog& G, const ProgPack (&x)[N],
                                                       T (&o)[N][2][V]) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int NT = blockDim.x * blockDim.y, tid = threadIdx.y * blockDim.x + threadIdx.x;
-    VT* base = reinterpret_cast<VT*>(smem_raw + P.slot_off) + tid;
+    // every lean kernel runs 256 threads per CTA: slot (s, u) of thread t sits at byte ((s*U + u)*256 + t)*16 of
+    // the slot area — one 32-bit multiply-add per access, shared-window addressing
+    constexpr uint32_t SLOT_STRIDE = 256 * 16;
+    const uint32_t tid = threadIdx.y * blockDim.x + threadIdx.x;
+    const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(smem_raw) + (uint32_t)P.slot_off + tid * 16u;
     const int n = G.n_instr, nslots = NARGS + n;
     auto ld = [&](int s, int u, T (&v)[V]) {
-      const VT w = base[(size_t)(s * U + u) * NT];
-      const T* e = reinterpret_cast<const T*>(&w);
-#pragma unroll
-      for (int i = 0; i < V; ++i) v[i] = e[i];
+      const uint32_t addr = sbase + (uint32_t)(s * U + u) * SLOT_STRIDE;
+      if constexpr (sizeof(T) == 4) {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "r"(addr));
+      } else {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "r"(addr));
+      }
     };
     auto st = [&](int s, int u, const T (&v)[V]) {
-      VT w;
-      T* e = reinterpret_cast<T*>(&w);
-#pragma unroll
-      for (int i = 0; i < V; ++i) e[i] = v[i];
-      base[(size_t)(s * U + u) * NT] = w;
+      const uint32_t addr = sbase + (uint32_t)(s * U + u) * SLOT_STRIDE;
+      if constexpr (sizeof(T) == 4) {
+        asm volatile("st.shared.v4.f32 [%4], {%0, %1, %2, %3};" ::"f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "r"(addr) : "memory");
+      } else {
+        asm volatile("st.shared.v2.f64 [%2], {%0, %1};" ::"d"(v[0]), "d"(v[1]), "r"(addr) : "memory");
+      }
     };
     auto get = [&](int idx, int u, T (&v)[V]) {
       if (idx >= 0) ld(idx, u, v);
@@ -72,8 +83,17 @@ struct ProgPack {
 #pragma unroll
       for (int u = 0; u < N; ++u) st(k, u, x[u].x[k]);
     // ---- forward ----
+    // In a pullback whose last instruction is a transcendental with f' = f'(y) (tanh, exp, logistic, ...) the
+    // host passes the Branch's saved value (core.jl:76) and that instruction is not re-evaluated.
+    const int nfwd = (MODE != LM_FWD && P.need_y) ? n - 1 : n;
+    if constexpr (MODE != LM_FWD) {
+      if (P.need_y) {
+#pragma unroll
+        for (int u = 0; u < N; ++u) st(NARGS + n - 1, u, x[u].ys);
+      }
+    }
     T last[N][V];
-    for (int i = 0; i < n; ++i) {
+    for (int i = 0; i < nfwd; ++i) {
       const int hop = G.hop[i], op = G.op[i], ia = G.a[i], ib = G.b[i];
       const bool bin = hop >= NB_HOP_ADD && hop != NB_HOP_COLD_UN;
 #pragma unroll
@@ -83,7 +103,7 @@ struct ProgPack {
         if (bin) get(ib, u, b);
         else {
 #pragma unroll
-          for (int v = 0; v < V; ++v) b[v] = T(0);
+          for (int v = 0; v < V; ++v) unspecified(b[v]);
         }
         nb_eval_hop<T, V>(hop, op, a, b, last[u]);
         st(NARGS + i, u, last[u]);
@@ -111,8 +131,9 @@ struct ProgPack {
           } else {
             ld(nslots + NARGS + i, u, g);
           }
+          // inputs a partial does not read stay unspecified (no fill instructions): defined for the compiler only
 #pragma unroll
-          for (int v = 0; v < V; ++v) { a[v] = T(0); b[v] = T(0); y[v] = T(0); }
+          for (int v = 0; v < V; ++v) { unspecified(a[v]); unspecified(b[v]); unspecified(y[v]); }
           if (fl & NB_RF_NEED_A) get(ia, u, a);
           if (fl & NB_RF_NEED_B) get(ib, u, b);
           if (fl & NB_RF_NEED_Y) ld(NARGS + i, u, y);

@@ -56,5 +56,8 @@ for name, f, ops, outs, bytes_pull in cases:
     bytes_fwd = (sum(o.size for o in ops) + N) * s
     t_f = timeit(lambda: K.bcast_fwd(prog, ops, Y))
     t_p = timeit(lambda: K.bcast_pullback(prog, one, None, ops, outs, [False] * len(outs)))
+    t_s = timeit(lambda: K.bcast_pullback(prog, one, Y, ops, outs, [False] * len(outs)))
+    bytes_s = bytes_pull + N * s
     print(f"{np.dtype(dt).name} {name}: fwd {t_f:.3f} ms = {bytes_fwd / t_f / 1e6:.0f} GB/s ({bytes_fwd / t_f / 1e6 / peak:.0%}), "
-          f"pullback {t_p:.3f} ms = {bytes_pull / t_p / 1e6:.0f} GB/s ({bytes_pull / t_p / 1e6 / peak:.0%})", flush=True)
+          f"pullback {t_p:.3f} ms = {bytes_pull / t_p / 1e6:.0f} GB/s ({bytes_pull / t_p / 1e6 / peak:.0%}), "
+          f"with saved y {t_s:.3f} ms = {bytes_s / t_s / 1e6:.0f} GB/s ({bytes_s / t_s / 1e6 / peak:.0%})", flush=True)
