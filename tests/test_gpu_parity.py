@@ -990,3 +990,57 @@ def test_fused_dense_layers(nb, orc, ctx):
     close(z.val.numpy(), Z, np.float32)          # reading one forces just that product
     close(t1.val.numpy(), Z + b[0][:, None], np.float32)
     close(rt[z].numpy(), 1 - Hh * Hh, np.float32)  # the sensitivity of an intermediate Branch is readable too
+
+
+def test_fusion_edge_cases(nb, orc, ctx):
+    """Deferred products under the tape shapes that must NOT fuse, or fuse only partly: every one must give the
+    oracle's values and gradients (fresh and accumulate variants)."""
+    rng = np.random.default_rng(21)
+    m, k, n = 128, 96, 160   # m*n*k >= 2^18: products are deferred
+    W = (rng.standard_normal((m, k)) / np.sqrt(k)).astype(np.float32)
+    X = rng.standard_normal((k, n)).astype(np.float32)
+    b = rng.standard_normal(m).astype(np.float32)
+    b2 = rng.standard_normal((m, 1)).astype(np.float32)
+    brow = rng.standard_normal((1, n)).astype(np.float32)
+    ybar = rng.standard_normal((m, n)).astype(np.float32)
+    V = (rng.standard_normal((64, m)) / np.sqrt(m)).astype(np.float32)
+    f32 = np.float32
+    cases = {
+        # constant (non-Node) bias: joins the forward epilogue, no row-sum in reverse
+        "const_bias": (lambda ns, w, x: ns.broadcast(ns.tanh, ns.broadcast(ns.add, ns.matmul(w, x), b)), [W, X], ybar),
+        # bias on the left, column-vector bias (m x 1), activation other than tanh
+        "bias_left": (lambda ns, w, x, c: ns.broadcast(ns.exp, ns.broadcast(ns.add, c, ns.matmul(w, x))), [W, X, b], ybar),
+        "bias_col": (lambda ns, w, x, c: ns.broadcast(orc_logistic(ns), ns.broadcast(ns.add, ns.matmul(w, x), c)), [W, X, b2], ybar),
+        # a row bias (1 x n) broadcasts along the other dimension: must not be taken for the epilogue bias
+        "bias_row": (lambda ns, w, x, c: ns.broadcast(ns.tanh, ns.broadcast(ns.add, ns.matmul(w, x), c)), [W, X, brow], ybar),
+        # activation straight on the product, and a function whose derivative needs its argument (no act fusion)
+        "act_only": (lambda ns, w, x: ns.broadcast(ns.tanh, ns.matmul(w, x)), [W, X], ybar),
+        "sin_act": (lambda ns, w, x, c: ns.broadcast(ns.sin, ns.broadcast(ns.add, ns.matmul(w, x), c)), [W, X, b], ybar),
+        # the product itself is read as well (forces it next to the fused launch)
+        "z_used_twice": (lambda ns, w, x, c: ns.broadcast(ns.add, ns.broadcast(ns.tanh, ns.broadcast(ns.add, ns.matmul(w, x), c)),
+                                                           ns.matmul(w, x)), [W, X, b], ybar),
+        # the activation is consumed twice: its sensitivity slot is accumulated, the f' join must not happen
+        "y_used_twice": (lambda ns, w, x, c: (lambda h: ns.broadcast(ns.mul, h, h))(
+            ns.broadcast(ns.tanh, ns.broadcast(ns.add, ns.matmul(w, x), c))), [W, X, b], ybar),
+        # two layers: the second product's X̄ joins the first layer's tanh pullback and bias row sum
+        "two_layers": (lambda ns, w, x, c, v: ns.matmul(v, ns.broadcast(ns.tanh, ns.broadcast(ns.add, ns.matmul(w, x), c))),
+                       [W, X, b, V], rng.standard_normal((64, n)).astype(np.float32)),
+        # composite lambda after the product: not an epilogue form
+        "lambda_after": (lambda ns, w, x: ns.broadcast(lambda t: ns.tanh(t) * t, ns.matmul(w, x)), [W, X], ybar),
+    }
+    for name, (build, xs, yb) in cases.items():
+        try:
+            check_case(nb, orc, build, xs, yb, f32)
+        except AssertionError as e:
+            raise AssertionError(f"{name}: {e}") from e
+    # single-pass TF32 goes through the same fused entry point (its own 1e-3 accuracy class)
+    old = ctx.math_mode
+    ctx.math_mode = nb.MATH_TF32
+    try:
+        check_case(nb, orc, cases["two_layers"][0], cases["two_layers"][1], cases["two_layers"][2], f32, scale=30.0)
+    finally:
+        ctx.math_mode = old
+
+
+def orc_logistic(ns):
+    return lambda x: 1.0 / (1.0 + ns.exp(-x))
