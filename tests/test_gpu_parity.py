@@ -1044,3 +1044,73 @@ def test_fusion_edge_cases(nb, orc, ctx):
 
 def orc_logistic(ns):
     return lambda x: 1.0 / (1.0 + ns.exp(-x))
+
+
+def test_gemm_cta_pair_kernel(nb, ctx):
+    """The CTA-pair kernel (cta_group::2, 256 x 256 tiles, dynamic tile ring, register-fold epilogue) is chosen
+    when a product has at least num_sms/2 pair tiles: all four transposes, ragged M / N / K tails, alpha / beta,
+    K beyond one chunk and beyond one launch range, and the fused epilogue forms, against NumPy Float64."""
+    import ctypes as C
+    from nabla_jl_b200 import fusion
+    from nabla_jl_b200 import kernels as K
+    rng = np.random.default_rng(77)
+    old = ctx.math_mode
+    ctx.math_mode = nb.MATH_BF16X3
+    try:
+        for (m, n, k) in ((2304, 4352, 520), (2100, 4401, 1000), (2560, 2304, 8192 + 136)):
+            assert ((m + 255) // 256) * ((n + 255) // 256) >= 74
+            for tA in "NT":
+                for tB in "NT":
+                    A = (rng.standard_normal((k, m) if tA == "T" else (m, k)) / np.sqrt(k)).astype(np.float32)
+                    B = rng.standard_normal((n, k) if tB == "T" else (k, n)).astype(np.float32)
+                    P = (A.T if tA == "T" else A).astype(np.float64) @ (B.T if tB == "T" else B).astype(np.float64)
+                    Ad, Bd = ctx.asarray(A), ctx.asarray(B)
+                    C0 = rng.standard_normal((m, n)).astype(np.float32)
+                    for alpha, beta in ((1.0, 0.0), (-0.7, 1.0)):
+                        Cd = ctx.asarray(C0)
+                        K.gemm(tA, tB, alpha, Ad, Bd, beta, Cd, m, n, k)
+                        ref = alpha * P + beta * C0.astype(np.float64)
+                        err = np.linalg.norm(Cd.numpy() - ref) / np.linalg.norm(ref)
+                        assert err < 3e-5, f"{tA}{tB} {m}x{n}x{k} alpha={alpha} beta={beta}: rel err {err:.3e}"
+                    if tA == "T" and tB == "T":
+                        continue  # the fused forms below: three transposes are enough
+                    bias = rng.standard_normal(m).astype(np.float32)
+                    y = (np.tanh(rng.standard_normal((m, n))) * 0.9).astype(np.float32)
+                    bd, yd = ctx.asarray(bias), ctx.asarray(y)
+                    for kind in (1, 2):
+                        out, rs = ctx.empty((m, n), np.float32), ctx.zeros((m,), np.float32)
+                        epi = fusion.nb_gemm_epilogue()
+                        epi.kind, epi.op = kind, nb._lib.OPCODES["tanh"]
+                        epi.bias = bd.ptr if kind == 1 else None
+                        epi.y, epi.ldy = (yd.ptr, m) if kind == 2 else (None, 0)
+                        epi.rowsum, epi.rowsum_acc, epi.emit_split = rs.ptr, 0, 1
+                        st = ctx.L.nb_gemm_fused(ctx.h, tA.encode(), tB.encode(), m, n, k, 1.0, Ad.ptr,
+                                                 k if tA == "T" else m, Bd.ptr, n if tB == "T" else k, out.ptr, m,
+                                                 out.nb_dtype, ctx.math_mode, C.byref(epi))
+                        assert st == 0
+                        ref = np.tanh(P + bias[:, None]) if kind == 1 else P * (1 - y.astype(np.float64) ** 2)
+                        got = out.numpy().astype(np.float64)
+                        err = np.linalg.norm(got - ref) / np.linalg.norm(ref)
+                        assert err < 3e-5, f"fused kind={kind} {tA}{tB} {m}x{n}x{k}: rel err {err:.3e}"
+                        rref = got.sum(axis=1)
+                        rerr = np.linalg.norm(rs.numpy() - rref) / np.linalg.norm(rref)
+                        assert rerr < 1e-5, f"fused kind={kind} {tA}{tB} {m}x{n}x{k}: row sums rel err {rerr:.3e}"
+                        D = rng.standard_normal((n, 64)).astype(np.float32)
+                        E = ctx.empty((m, 64), np.float32)
+                        K.gemm("N", "N", 1.0, out, ctx.asarray(D), 0.0, E, m, 64, n)   # uses the emitted split
+                        eref = got @ D.astype(np.float64)
+                        eerr = np.linalg.norm(E.numpy() - eref) / np.linalg.norm(eref)
+                        assert eerr < 3e-5, f"fused kind={kind} {tA}{tB}: product from the emitted split {eerr:.3e}"
+    finally:
+        ctx.math_mode = old
+
+
+def test_fused_dense_layers_on_the_pair_kernel(nb, orc, ctx):
+    """The wide-MLP gradient at a size whose hidden-layer products run on the CTA-pair kernel with the fused
+    epilogues (>= 74 pair tiles), against the Float64 oracle."""
+    import nabla_jl_b200.workloads as wl
+    dims, B = (200, 2304, 2304, 10), 4352
+    y, g, yr, gr = _mlp_both(nb, orc, dims, B, np.float32, seed=5)
+    np.testing.assert_allclose(y, yr, rtol=1e-4)
+    for a, b in zip(g, gr):
+        close(a, b, np.float32)
