@@ -18,7 +18,7 @@ from .rules import (Ref, adjoint, broadcast, dot, gemm, gemv, ldivide, map_, map
                     mapreduce, matmul, mean, sum, transpose)
 
 from .blasrules import symm, symv, trmm, trmv, trsm, trsv
-from .arrayrules import R, checkpoint, colon, fill, getindex, hcat, reshape, vcat
+from .arrayrules import R, checkpoint, colon, copy, fill, getindex, hcat, kron, plus_I, reshape, vcat
 from .sweep import (CapturedGradient, Communicator, OverlappedShardedGradient, ShardedGradient,
                     shard_bounds)
 

@@ -47,6 +47,98 @@ def _rc(a):
     raise TypeError("MethodError: hcat/vcat are implemented for vectors and matrices")
 
 
+# ---- generic linalg: kron, A + λI, copy (src/sensitivities/linalg/generic.jl:7-51) -------------------
+def _kron_views(A, B, Y):
+    """kron as a 4-D broadcast: Y[(i-1)K + k, (j-1)L + l] = A[i,j] B[k,l] is, column-major, the array
+    (K, I, L, J) = A viewed as (1, I, 1, J) .* B viewed as (K, 1, L, 1)."""
+    (I, J), (Kk, L) = A.shape, B.shape
+    return A.reshape((1, I, 1, J)), B.reshape((Kk, 1, L, 1)), Y.reshape((Kk, I, L, J))
+
+
+def _kron_forward(A, B):
+    A, B = _dev(A), _dev(B)
+    if A.ndim != 2 or B.ndim != 2:
+        raise TypeError("MethodError: the kron sensitivities destructure size(A), size(B) as matrices (generic.jl:19)")
+    if A.dtype != B.dtype:
+        raise TypeError("kron operands must share an element type")
+    out = A.ctx.empty((A.shape[0] * B.shape[0], A.shape[1] * B.shape[1]), A.dtype)
+    A4, B4, Y4 = _kron_views(A, B, out)
+    K.bcast_fwd(_mul_prog(), [A4, B4], Y4)
+    return out
+
+
+def _mul_prog():
+    from .rules import _MUL_PROG
+    return _MUL_PROG
+
+
+def _kron_fused(y, ybar, rvs):
+    """Both sensitivities (generic.jl:13-40: ā_ij += Σ_kl Ȳ·B, B̄_kl += Σ_ij Ȳ·a_ij) in ONE launch of the broadcast
+    pullback: the sums over the broadcast dimensions are its fused unbroadcast, `+=` its accumulate flag."""
+    from .rules import _slot_target
+    An, Bn = y.args
+    A, B = _dev(unbox(An)), _dev(unbox(Bn))
+    yb = _dev(unthunk(ybar))
+    A4, B4, Y4 = _kron_views(A, B, yb)
+    outs, acc = [None, None], [False, False]
+    d_tape = rvs.tape
+    if isinstance(An, Node):
+        o, beta = _slot_target(d_tape, An.pos, A.shape, A.ctx, A.dtype)
+        outs[0], acc[0] = o.reshape(A4.shape), beta == 1.0
+    if isinstance(Bn, Node):
+        if isinstance(An, Node) and Bn.pos == An.pos:
+            raise TypeError("kron(x, x) with the same Node on both sides is not supported")
+        o, beta = _slot_target(d_tape, Bn.pos, B.shape, B.ctx, B.dtype)
+        outs[1], acc[1] = o.reshape(B4.shape), beta == 1.0
+    K.bcast_pullback(_mul_prog(), Y4, None, [A4, B4], outs, acc)
+
+
+_kron = Primitive("kron", _kron_forward, fused=_kron_fused)
+
+
+def kron(A, B):
+    """``kron(A, B)`` (generic.jl:7-40)."""
+    return _kron(A, B)
+
+
+def _plus_I_forward(A, lam):
+    A = _dev(A)
+    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+        raise DimensionMismatch(6, "matrix is not square")
+    n = A.shape[0]
+    out = A.copy()
+    if n:
+        d = A.ctx.full((n,), float(lam), A.dtype)
+        _copy2d(1, n, d, 0, 1, out, 0, n + 1, accumulate=True)   # the diagonal is a stride-(n+1) row
+    return out
+
+
+_plus_I = Primitive("+I", _plus_I_forward)
+
+
+@_plus_I.grad(1)
+def _(p, y, ybar, A, lam):
+    return ybar   # generic.jl:43,46: the sensitivity is Ȳ itself (aliasing handled by the sweep)
+
+
+def plus_I(A, lam):
+    """``A + lam*I`` / ``lam*I + A`` with ``I`` the UniformScaling (generic.jl:42-46)."""
+    return _plus_I(A, lam)
+
+
+_copy = Primitive("copy", lambda A: _dev(A).copy())
+
+
+@_copy.grad(1)
+def _(p, y, ybar, A):
+    return _dev(unthunk(ybar)).copy()   # generic.jl:51
+
+
+def copy(A):
+    """``copy(A)`` (generic.jl:48-51)."""
+    return _copy(A)
+
+
 # ---- hcat / vcat --------------------------------------------------------------------------------
 def _hcat_forward(*A):
     A = [_dev(a) for a in A]

@@ -37,6 +37,7 @@ __all__ = [
     "unthunk", "add_bang_bang", "check_errs", "oneslike", "zeroslike",
     "hcat", "vcat", "getindex", "reshape", "fill", "checkpoint", "R", "colon",
     "symm", "symv", "trmm", "trmv", "trsm", "trsv",
+    "kron", "plus_I", "copy",
 ]
 
 _pysum = sum
@@ -1328,6 +1329,58 @@ _fill = Primitive("fill", rrule=_rrule_fill)
 
 def fill(x, *dims):
     return _fill(x, *dims)
+
+
+# ---- generic linalg: kron, A + λI, copy (src/sensitivities/linalg/generic.jl:7-51) -------------
+def _kron_check(A, B):
+    A, B = np.asarray(A), np.asarray(B)
+    if A.ndim != 2 or B.ndim != 2:
+        raise TypeError("MethodError: the kron sensitivities destructure size(A), size(B) as matrices (generic.jl:19)")
+    return A, B
+
+
+def _grad_kron(n, p, y, ybar, A, B):
+    """generic.jl:13-40 restated: the reference walks the column-major linear index m of Ȳ downwards over
+    (j, l, i, k) — Y[(i-1)K + k, (j-1)L + l] = A[i,j] B[k,l] — accumulating ā_ij += Ȳ[m] B[k,l] (Arg 1) or
+    B̄[k,l] += Ȳ[m] a_ij (Arg 2) into a zero matrix; as contractions of Ȳ viewed as (I, K, J, L)."""
+    A, B = _kron_check(A, B)
+    (I, J), (Kk, L) = A.shape, B.shape
+    Y4 = np.asarray(unthunk(ybar)).reshape(I, Kk, J, L)
+    if n == 1:
+        return np.einsum("ikjl,kl->ij", Y4, B)
+    return np.einsum("ikjl,ij->kl", Y4, A)
+
+
+_kron = Primitive("kron", forward=lambda A, B: np.kron(*_kron_check(A, B)), grads={1: _grad_kron, 2: _grad_kron})
+
+
+def kron(A, B):
+    return _kron(A, B)
+
+
+def _plus_I_forward(A, lam):
+    A = np.asarray(A)
+    if A.ndim != 2 or A.shape[0] != A.shape[1]:
+        raise ValueError("DimensionMismatch: matrix is not square")
+    return A + float(lam) * np.eye(A.shape[0], dtype=A.dtype)
+
+
+# `A + λI` / `λI + A` (generic.jl:42-46): the sensitivity of A is Ȳ itself
+_plus_I = Primitive("+I", forward=_plus_I_forward, grads={1: lambda n, p, y, ybar, A, lam: ybar})
+
+
+def plus_I(A, lam):
+    """``A + lam*I`` with ``I`` the UniformScaling (either operand order: the rule is the same)."""
+    return _plus_I(A, lam)
+
+
+# `copy` (generic.jl:48-51): Ā = copy(Ȳ)
+_copy = Primitive("copy", forward=lambda A: np.array(A, copy=True),
+                  grads={1: lambda n, p, y, ybar, A: np.array(unthunk(ybar), copy=True)})
+
+
+def copy(A):
+    return _copy(A)
 
 
 def _checkpoint_forward(f, *xs, **kw):

@@ -1114,3 +1114,21 @@ def test_fused_dense_layers_on_the_pair_kernel(nb, orc, ctx):
     np.testing.assert_allclose(y, yr, rtol=1e-4)
     for a, b in zip(g, gr):
         close(a, b, np.float32)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_kron_plus_I_copy(nb, orc, dtype):
+    # src/sensitivities/linalg/generic.jl:7-51; test/sensitivities/linalg/generic.jl:64-79
+    rng = np.random.default_rng(3)
+    for (sa, sb) in (((3, 4), (2, 5)), ((5, 5), (5, 5)), ((1, 7), (6, 1)), ((16, 8), (8, 12))):
+        A, B = rng.standard_normal(sa), rng.standard_normal(sb)
+        ybar = rng.standard_normal((sa[0] * sb[0], sa[1] * sb[1]))
+        check_case(nb, orc, lambda ns, a, b: ns.kron(a, b), [A, B], ybar, dtype)
+        check_case(nb, orc, lambda ns, a: ns.kron(a, B.astype(dtype)), [A], ybar, dtype)
+        check_case(nb, orc, lambda ns, b: ns.kron(A.astype(dtype), b), [B], ybar, dtype)
+    A = rng.standard_normal((6, 6))
+    ybar = rng.standard_normal((6, 6))
+    check_case(nb, orc, lambda ns, a: ns.plus_I(a, 0.65), [A], ybar, dtype)
+    check_case(nb, orc, lambda ns, a: ns.copy(a), [A], ybar, dtype)
+    with pytest.raises(ValueError):
+        nb.plus_I(nb.get_context().asarray(rng.standard_normal((3, 4)).astype(dtype)), 1.0)

@@ -332,3 +332,44 @@ def test_structured_blas_check_errs():
         A1 = r(N, N) + np.eye(N)
         A1 = A1.T @ A1
         assert o.check_errs(lambda A, x: o.trsv(ul, tA, dA, A, x), r(N), (A1, b), (VA, vb), eps_abs=1e-7, eps_rel=1e-5)
+
+
+def test_generic_linalg_kron_plus_I_copy():
+    """src/sensitivities/linalg/generic.jl:7-51 — kron (the reference's index loops restated literally and compared
+    with the oracle's contraction), A + λI, copy; each with the reference's own check (test/sensitivities/linalg/
+    generic.jl:64-79: check_errs = allocated + in-place variants against 5-point finite differences)."""
+    import nabla_oracle as o
+    rng = np.random.default_rng(3)
+
+    def loops(n, Yb, A, B):   # generic.jl:19-40, 1-based column-major walk of m = length(Y) .. 1
+        (I, J), (K, L) = A.shape, B.shape
+        m, Yf = Yb.size, Yb.reshape(-1, order="F")
+        Ab, Bb = np.zeros_like(A), np.zeros_like(B)
+        for j in reversed(range(J)):
+            for l in reversed(range(L)):
+                for i in reversed(range(I)):
+                    for k in reversed(range(K)):
+                        if n == 1:
+                            Ab[i, j] += Yf[m - 1] * B[k, l]
+                        else:
+                            Bb[k, l] += Yf[m - 1] * A[i, j]
+                        m -= 1
+        return Ab if n == 1 else Bb
+
+    for _ in range(5):
+        A, B = rng.standard_normal((3, 4)), rng.standard_normal((2, 5))
+        VA, VB = rng.standard_normal((3, 4)), rng.standard_normal((2, 5))
+        Yb = rng.standard_normal((6, 20))
+        np.testing.assert_allclose(o._grad_kron(1, None, None, Yb, A, B), loops(1, Yb, A, B), rtol=1e-13, atol=1e-13)
+        np.testing.assert_allclose(o._grad_kron(2, None, None, Yb, A, B), loops(2, Yb, A, B), rtol=1e-13, atol=1e-13)
+        assert o.check_errs(o.kron, Yb, (A, B), (VA, VB))
+    for _ in range(5):
+        A, VA = rng.standard_normal((5, 5)), rng.standard_normal((5, 5))
+        assert o.check_errs(lambda X: o.plus_I(X, 0.65), VA, A, 1e-1 * rng.standard_normal((5, 5)))
+        assert o.check_errs(o.copy, VA, A, 1e-1 * rng.standard_normal((5, 5)))
+    # Ā of A + λI is Ȳ itself (generic.jl:43)
+    t = o.Tape()
+    a = o.Leaf(t, rng.standard_normal((4, 4)))
+    yb = rng.standard_normal((4, 4))
+    assert o.nabla(o.plus_I(a, 2.0), yb)[a] is not None
+    np.testing.assert_array_equal(o.nabla(o.plus_I(a, 2.0), yb)[a], yb)
