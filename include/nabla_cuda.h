@@ -89,7 +89,13 @@ typedef enum nb_op {
   NB_OP_LDIV = 68,      /* x \ y == y / x */
   NB_OP_POW = 69, NB_OP_HYPOT = 70, NB_OP_MAX = 71, NB_OP_MIN = 72,
   NB_OP_ATAN2 = 73,     /* atan(y_, x_) with operand a = y_, b = x_ */
-  NB_OP_BINARY_END = 74
+  NB_OP_BETA = 74,      /* SpecialFunctions.beta(a, b) */
+  NB_OP_BINARY_END = 75,
+  /* SpecialFunctions.jl unary functions of test/runtests.jl:34-36 (second unary range) */
+  NB_OP_SF_BEGIN = 96,
+  NB_OP_GAMMA = 96, NB_OP_DIGAMMA = 97, NB_OP_TRIGAMMA = 98, NB_OP_BESSELJ0 = 99, NB_OP_BESSELJ1 = 100,
+  NB_OP_BESSELY0 = 101, NB_OP_BESSELY1 = 102, NB_OP_ERFINV = 103, NB_OP_ERFCINV = 104, NB_OP_ERFCX = 105,
+  NB_OP_SF_END = 106
 } nb_op;
 
 typedef struct nb_stats {

@@ -18,7 +18,7 @@ __host__ __device__ constexpr bool lean_hot_op(int op) {
          op == NB_OP_TANH || op == NB_OP_LOGISTIC || op == NB_OP_SQRT || op == NB_OP_INV || op == NB_OP_ADD ||
          op == NB_OP_SUB || op == NB_OP_MUL || op == NB_OP_DIV;
 }
-__host__ __device__ constexpr bool lean_is_binary(int op) { return op >= NB_OP_ADD; }
+__host__ __device__ constexpr bool lean_is_binary(int op) { return nb_op_is_binary(op); }
 
 // static operand needs: bit0 a, bit1 b, bit2 y (saved forward value)
 template <int OP, int MODE>

@@ -171,7 +171,7 @@ int32_t nb_gemm_fused(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int
   NB_REQUIRE(ctx, (is_t(tAc) || is_n(tAc)) && (is_t(tBc) || is_n(tBc)), NB_ERR_INVALID,
              "nb_gemm_fused: transpose flags must be 'N', 'T' or 'C'");
   NB_REQUIRE(ctx, epi && (epi->kind == 1 || epi->kind == 2), NB_ERR_INVALID, "nb_gemm_fused: bad epilogue kind");
-  NB_REQUIRE(ctx, epi->op >= 0 && epi->op < NB_OP_UNARY_END, NB_ERR_INVALID, "nb_gemm_fused: op must be unary");
+  NB_REQUIRE(ctx, nb_op_is_unary(epi->op), NB_ERR_INVALID, "nb_gemm_fused: op must be unary");
   NB_REQUIRE(ctx, epi->kind != 2 || (epi->y && epi->ldy >= m), NB_ERR_INVALID, "nb_gemm_fused: pullback needs y");
   NB_REQUIRE(ctx, epi->kind != 2 || (nb_partial_needs(epi->op, 0) & 3) == 0, NB_ERR_INVALID,
              "nb_gemm_fused: f' must be a function of y alone");

@@ -40,7 +40,9 @@ enum {
 #define NB_LN10 2.30258509299404568402
 #define NB_2_SQRTPI 1.12837916709551257390
 
-__host__ __device__ constexpr bool nb_op_is_unary(int op) { return op >= 0 && op < NB_OP_UNARY_END; }
+__host__ __device__ constexpr bool nb_op_is_unary(int op) {
+  return (op >= 0 && op < NB_OP_UNARY_END) || (op >= NB_OP_SF_BEGIN && op < NB_OP_SF_END);
+}
 __host__ __device__ constexpr bool nb_op_is_binary(int op) {
   return op >= NB_OP_ADD && op < NB_OP_BINARY_END;
 }
@@ -66,6 +68,9 @@ __host__ __device__ constexpr int nb_partial_needs(int op, int wrt /*0=a,1=b*/) 
     case NB_OP_POW: return wrt == 0 ? (A | B) : (A | Y);
     case NB_OP_HYPOT: return wrt == 0 ? (A | Y) : (B | Y);
     case NB_OP_MAX: case NB_OP_MIN: case NB_OP_ATAN2: return A | B;
+    case NB_OP_BETA: return A | B | Y;
+    case NB_OP_ERFINV: case NB_OP_ERFCINV: return Y;
+    case NB_OP_GAMMA: case NB_OP_ERFCX: return A | Y;
     default: return A;  // unary ops whose partial is a function of x
   }
 }
@@ -82,6 +87,73 @@ template <> __device__ __forceinline__ double nb_exp10<double>(double x) { retur
 template <typename T> __device__ __forceinline__ T nb_rsqrt(T x);
 template <> __device__ __forceinline__ float nb_rsqrt<float>(float x) { return 1.0f / sqrtf(x); }
 template <> __device__ __forceinline__ double nb_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
+
+
+// ---- SpecialFunctions.jl subset (test/runtests.jl:34-36): values from the CUDA math library, polygammas by
+// recurrence to x >= 10 + asymptotic series (|error| < 1e-15 relative there) and the reflection formulas ----
+template <typename T> __device__ __forceinline__ T nb_j0(T x);
+template <> __device__ __forceinline__ float nb_j0<float>(float x) { return j0f(x); }
+template <> __device__ __forceinline__ double nb_j0<double>(double x) { return j0(x); }
+template <typename T> __device__ __forceinline__ T nb_j1(T x);
+template <> __device__ __forceinline__ float nb_j1<float>(float x) { return j1f(x); }
+template <> __device__ __forceinline__ double nb_j1<double>(double x) { return j1(x); }
+template <typename T> __device__ __forceinline__ T nb_y0(T x);
+template <> __device__ __forceinline__ float nb_y0<float>(float x) { return y0f(x); }
+template <> __device__ __forceinline__ double nb_y0<double>(double x) { return y0(x); }
+template <typename T> __device__ __forceinline__ T nb_y1(T x);
+template <> __device__ __forceinline__ float nb_y1<float>(float x) { return y1f(x); }
+template <> __device__ __forceinline__ double nb_y1<double>(double x) { return y1(x); }
+template <typename T> __device__ __forceinline__ T nb_erfinv(T x);
+template <> __device__ __forceinline__ float nb_erfinv<float>(float x) { return erfinvf(x); }
+template <> __device__ __forceinline__ double nb_erfinv<double>(double x) { return erfinv(x); }
+template <typename T> __device__ __forceinline__ T nb_erfcinv(T x);
+template <> __device__ __forceinline__ float nb_erfcinv<float>(float x) { return erfcinvf(x); }
+template <> __device__ __forceinline__ double nb_erfcinv<double>(double x) { return erfcinv(x); }
+template <typename T> __device__ __forceinline__ T nb_erfcx(T x);
+template <> __device__ __forceinline__ float nb_erfcx<float>(float x) { return erfcxf(x); }
+template <> __device__ __forceinline__ double nb_erfcx<double>(double x) { return erfcx(x); }
+
+// polygamma(ORDER, x) for ORDER = 0 (digamma), 1 (trigamma), 2; evaluated in double for both element types
+template <int ORDER>
+__device__ __noinline__ double nb_polygamma(double x) {
+  double refl = 0.0;
+  bool reflected = false;
+  if (x <= 0.0) {
+    if (x == floor(x)) return nan("");
+    const double s = sinpi(x), c = cospi(x);
+    // psi(1-x) - psi(x) = pi cot(pi x);  psi1(1-x) + psi1(x) = pi^2 / sin^2;  psi2(1-x) - psi2(x) = 2 pi^3 cos / sin^3
+    if (ORDER == 0) refl = -NB_PI * c / s;
+    else if (ORDER == 1) refl = NB_PI * NB_PI / (s * s);
+    else refl = -2.0 * NB_PI * NB_PI * NB_PI * c / (s * s * s);
+    x = 1.0 - x;
+    reflected = true;
+  }
+  double r = 0.0;
+  while (x < 10.0) {
+    if (ORDER == 0) r -= 1.0 / x;
+    else if (ORDER == 1) r += 1.0 / (x * x);
+    else r -= 2.0 / (x * x * x);
+    x += 1.0;
+  }
+  const double f = 1.0 / (x * x);
+  double v;
+  if (ORDER == 0) {
+    v = log(x) - 0.5 / x -
+        f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132 - f * (691.0 / 32760 - f / 12))))));
+  } else if (ORDER == 1) {
+    v = 1.0 / x + 0.5 * f +
+        (f / x) * (1.0 / 6 - f * (1.0 / 30 - f * (1.0 / 42 - f * (1.0 / 30 - f * (5.0 / 66 - f * (691.0 / 2730 - f * 7.0 / 6))))));
+  } else {
+    v = -f - f / x -
+        f * f * (0.5 - f * (1.0 / 6 - f * (1.0 / 6 - f * (0.3 - f * (5.0 / 6 - f * (691.0 / 210 - f * 35.0 / 2))))));
+  }
+  v += r;
+  if (!reflected) return v;
+  // values at the original point from the values at 1 - x
+  if (ORDER == 0) return v + refl;       // psi(x)  = psi(1-x) - pi cot(pi x)
+  if (ORDER == 1) return refl - v;       // psi1(x) = pi^2/sin^2 - psi1(1-x)
+  return v + refl;                       // psi2(x) = psi2(1-x) - 2 pi^3 cos/sin^3
+}
 
 // value of a catalogue op: full table, inlined (folds to one expression when `op` is a compile-time
 // constant, as in the lean kernels)
@@ -158,6 +230,17 @@ __device__ __forceinline__ T nb_eval_full(int op, T a, T b) {
     case NB_OP_MAX: return fmax(a, b);
     case NB_OP_MIN: return fmin(a, b);
     case NB_OP_ATAN2: return atan2(a, b);
+    case NB_OP_BETA: return exp(lgamma(a) + lgamma(b) - lgamma(a + b));
+    case NB_OP_GAMMA: return tgamma(a);
+    case NB_OP_DIGAMMA: return T(nb_polygamma<0>((double)a));
+    case NB_OP_TRIGAMMA: return T(nb_polygamma<1>((double)a));
+    case NB_OP_BESSELJ0: return nb_j0<T>(a);
+    case NB_OP_BESSELJ1: return nb_j1<T>(a);
+    case NB_OP_BESSELY0: return nb_y0<T>(a);
+    case NB_OP_BESSELY1: return nb_y1<T>(a);
+    case NB_OP_ERFINV: return nb_erfinv<T>(a);
+    case NB_OP_ERFCINV: return nb_erfcinv<T>(a);
+    case NB_OP_ERFCX: return nb_erfcx<T>(a);
     default: return a;
   }
 }
@@ -230,6 +313,16 @@ __device__ __forceinline__ T nb_dunary_full(int op, T a, T y) {
     case NB_OP_LOGISTIC: return y * (one - y);
     case NB_OP_ERF: return T(NB_2_SQRTPI) * exp(-a * a);
     case NB_OP_ERFC: return -T(NB_2_SQRTPI) * exp(-a * a);
+    case NB_OP_GAMMA: return y * T(nb_polygamma<0>((double)a));
+    case NB_OP_DIGAMMA: return T(nb_polygamma<1>((double)a));
+    case NB_OP_TRIGAMMA: return T(nb_polygamma<2>((double)a));
+    case NB_OP_BESSELJ0: return -nb_j1<T>(a);
+    case NB_OP_BESSELJ1: return nb_j0<T>(a) - nb_j1<T>(a) / a;
+    case NB_OP_BESSELY0: return -nb_y1<T>(a);
+    case NB_OP_BESSELY1: return nb_y0<T>(a) - nb_y1<T>(a) / a;
+    case NB_OP_ERFINV: return T(1.0 / NB_2_SQRTPI) * exp(y * y);
+    case NB_OP_ERFCINV: return -T(1.0 / NB_2_SQRTPI) * exp(y * y);
+    case NB_OP_ERFCX: return T(2) * a * y - T(NB_2_SQRTPI);
     default: return T(0);
   }
 }
@@ -291,6 +384,10 @@ __device__ __forceinline__ T nb_dbinary(int op, int wrt, T a, T b, T y) {
     case NB_OP_ATAN2: {
       T den = a * a + b * b;
       return wrt == 0 ? b / den : -a / den;
+    }
+    case NB_OP_BETA: {
+      const double pab = nb_polygamma<0>((double)a + (double)b);
+      return y * T(nb_polygamma<0>((double)(wrt == 0 ? a : b)) - pab);
     }
     default: return T(0);
   }

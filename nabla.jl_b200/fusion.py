@@ -31,7 +31,12 @@ _A, _B, _Y = 1, 2, 4
 _NEEDS_NONE = {"identity", "neg", "deg2rad", "rad2deg"}
 _NEEDS_Y = {"tanh", "exp", "logistic", "sqrt", "inv", "tan", "exp2", "exp10", "cbrt", "cot", "coth", "tand",
             "cotd", "expm1"}
-_NEEDS_AY = {"sec", "csc", "sech", "csch", "secd", "cscd"}
+_NEEDS_Y |= {"erfinv", "erfcinv"}
+_NEEDS_AY = {"sec", "csc", "sech", "csch", "secd", "cscd", "gamma", "erfcx"}
+
+
+def _is_binary(op):
+    return OPCODES["add"] <= op < OPCODES["binary_end"]
 _NAME = {v: k for k, v in OPCODES.items()}
 
 
@@ -57,6 +62,8 @@ def partial_needs(op, wrt=0):
         return (_A | _Y) if wrt == 0 else (_B | _Y)
     if name in ("max", "min", "atan2"):
         return _A | _B
+    if name == "beta":
+        return _A | _B | _Y
     return _A
 
 
@@ -68,7 +75,7 @@ def pullback_reads(prog, wanted):
     if not prog.ops:
         return set(), False
     op, a = prog.ops[0], prog.a[0]
-    b = prog.b[0] if op >= OPCODES["add"] else None
+    b = prog.b[0] if _is_binary(op) else None
     reads, ry = set(), False
     for k in wanted:
         for side, slot in ((0, a), (1, b)):
@@ -243,7 +250,7 @@ def try_forward(prog, dev):
             e.kind, e.stage, e.bias = 1, 1, b
             return e.new_result()
         return None
-    if len(dev) == 1 and op < OPCODES["add"] and (partial_needs(op) & (_A | _B)) == 0:
+    if len(dev) == 1 and not _is_binary(op) and (partial_needs(op) & (_A | _B)) == 0:
         d = _pending(dev[0], kinds=(0, 1), max_stage=1)
         if d is None or d.kind == 2:
             return None
@@ -256,7 +263,7 @@ def try_forward(prog, dev):
 def try_pullback_act(prog, ybar, y_saved, operand):
     """``x̄ = ȳ .* f'(y)`` where ȳ is a deferred product: the lazy x̄, or None."""
     op = prog.single_op
-    if op is None or op >= OPCODES["add"] or (partial_needs(op) & (_A | _B)) != 0:
+    if op is None or _is_binary(op) or (partial_needs(op) & (_A | _B)) != 0:
         return None
     d = _pending(ybar, kinds=(0,), max_stage=0)
     if d is None or y_saved is None or tuple(y_saved.shape) != (d.m, d.n) or tuple(operand.shape) != (d.m, d.n):

@@ -14,8 +14,9 @@ import numbers
 from . import _lib
 from ._lib import NB_MAX_ARGS, NB_MAX_CONSTS, NB_MAX_INSTR, OPCODES, UnsupportedOp, check
 
-UNARY = [n for n, v in OPCODES.items() if v < OPCODES["unary_end"] and not n.endswith("_end")]
-BINARY = [n for n, v in OPCODES.items() if OPCODES["add"] <= v < OPCODES["binary_end"]]
+UNARY = [n for n, v in OPCODES.items() if not n.endswith(("_end", "_begin")) and
+         (v < OPCODES["unary_end"] or OPCODES["sf_begin"] <= v < OPCODES["sf_end"])]
+BINARY = [n for n, v in OPCODES.items() if OPCODES["add"] <= v < OPCODES["binary_end"] and not n.endswith("_end")]
 
 
 class Sym:
@@ -72,7 +73,7 @@ class ScalarFn:
         self.name = name
         self.__name__ = name
         self.opcode = OPCODES[name]
-        self.arity = 1 if self.opcode < OPCODES["unary_end"] else 2
+        self.arity = 2 if OPCODES["add"] <= self.opcode < OPCODES["binary_end"] else 1
 
     def __repr__(self):
         return f"<nabla.jl_b200 scalar fn {self.name}>"

@@ -238,6 +238,28 @@ def _cospi(x):
     return np.cos(np.pi * x)
 
 
+import scipy.special as _sp  # noqa: E402  (special functions: values only, the rules are written out below)
+
+_2_SQRTPI = 2.0 / math.sqrt(math.pi)
+
+
+def _polygamma_any(n, x):
+    """polygamma(n, x) for any real x (scipy's is defined for x > 0): reflection for x <= 0,
+    psi1(x) = pi^2/sin^2(pi x) - psi1(1-x),  psi2(x) = psi2(1-x) - 2 pi^3 cos(pi x)/sin^3(pi x)."""
+    x = np.asarray(x, dtype=np.float64)
+    pos = x > 0
+    xp = np.where(pos, x, 1.0 - x)
+    v = _sp.polygamma(n, xp)
+    with np.errstate(all="ignore"):
+        s, c = np.sin(np.pi * x), np.cos(np.pi * x)
+        if n == 1:
+            r = np.pi ** 2 / (s * s) - v
+        else:
+            r = v - 2.0 * np.pi ** 3 * c / (s ** 3)
+    out = np.where(pos, v, r)
+    return out if out.ndim else float(out)
+
+
 _UNARY = {
     # name: (f, f')  -- SURVEY.md §8(c) catalogue
     "identity": (lambda x: x, lambda x: 1.0 + 0.0 * x),
@@ -297,6 +319,19 @@ _UNARY = {
     "cospi": (_cospi, lambda x: -np.pi * _sinpi(x)),
     "deg2rad": (lambda x: _D2R * x, lambda x: _D2R + 0.0 * x),
     "rad2deg": (lambda x: _R2D * x, lambda x: _R2D + 0.0 * x),
+    # SpecialFunctions.jl (test/runtests.jl:34-36), ChainRules @scalar_rule formulas; values from scipy.special
+    "erf": (lambda x: _sp.erf(x), lambda x: _2_SQRTPI * np.exp(-x * x)),
+    "erfc": (lambda x: _sp.erfc(x), lambda x: -_2_SQRTPI * np.exp(-x * x)),
+    "erfcx": (lambda x: _sp.erfcx(x), lambda x: 2.0 * x * _sp.erfcx(x) - _2_SQRTPI),
+    "erfinv": (lambda x: _sp.erfinv(x), lambda x: np.exp(_sp.erfinv(x) ** 2) / _2_SQRTPI),
+    "erfcinv": (lambda x: _sp.erfcinv(x), lambda x: -np.exp(_sp.erfcinv(x) ** 2) / _2_SQRTPI),
+    "gamma": (lambda x: _sp.gamma(x), lambda x: _sp.gamma(x) * _sp.digamma(x)),
+    "digamma": (lambda x: _sp.digamma(x), lambda x: _polygamma_any(1, x)),
+    "trigamma": (lambda x: _polygamma_any(1, x), lambda x: _polygamma_any(2, x)),
+    "besselj0": (lambda x: _sp.j0(x), lambda x: -_sp.j1(x)),
+    "besselj1": (lambda x: _sp.j1(x), lambda x: (_sp.j0(x) - _sp.jv(2, x)) / 2.0),
+    "bessely0": (lambda x: _sp.y0(x), lambda x: -_sp.y1(x)),
+    "bessely1": (lambda x: _sp.y1(x), lambda x: (_sp.y0(x) - _sp.yv(2, x)) / 2.0),
 }
 
 _BINARY = {
@@ -312,6 +347,8 @@ _BINARY = {
     "max": (np.maximum, lambda x, y: (x > y) * 1.0, lambda x, y: (x <= y) * 1.0),
     "min": (np.minimum, lambda x, y: (x < y) * 1.0, lambda x, y: (x >= y) * 1.0),
     "atan2": (np.arctan2, lambda x, y: y / (x * x + y * y), lambda x, y: -x / (x * x + y * y)),
+    "beta": (lambda x, y: _sp.beta(x, y), lambda x, y: _sp.beta(x, y) * (_sp.digamma(x) - _sp.digamma(x + y)),
+             lambda x, y: _sp.beta(x, y) * (_sp.digamma(y) - _sp.digamma(x + y))),
 }
 
 

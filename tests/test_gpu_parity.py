@@ -218,7 +218,12 @@ def test_catalogue_on_lean_kernels(nb, orc, dtype):
         ybar = rng.standard_normal(x.shape)
         try:
             check_case(nb, orc, lambda ns, a: ns.broadcast(_fn(ns, name), a), [x], ybar, dtype)
-            check_case(nb, orc, lambda ns, a: ns.sum(_fn(ns, name), a), [x], None, dtype, accumulate=False)
+            # the sum of an odd function over a symmetric domain nearly cancels: widen the tolerance by its
+            # condition number (sum |f| / |sum f|) so the check bounds the kernel's error, not the cancellation
+            fx = np.asarray(_fn(orc, name)(x.astype(dtype).astype(np.float64)))
+            cond = float(np.abs(fx).sum() / max(abs(fx.sum()), 1e-300))
+            check_case(nb, orc, lambda ns, a: ns.sum(_fn(ns, name), a), [x], None, dtype, accumulate=False,
+                       scale=max(1.0, cond / 30.0))
         except AssertionError as e:
             raise AssertionError(f"{name} ({np.dtype(dtype).name}): {e}") from e
     rng = np.random.default_rng(8)

@@ -37,7 +37,9 @@ def test_opcodes_match_header():
     ops = _lib.OPCODES
     assert ops["identity"] == 0 and ops["tanh"] == 23 and ops["logistic"] == 55
     assert ops["add"] == 64 and ops["atan2"] == 73
-    assert len(scalar.UNARY) == 58 and len(scalar.BINARY) == 10
+    assert ops["beta"] == 74 and ops["gamma"] == 96 and ops["erfcx"] == 105
+    assert len(scalar.UNARY) == 58 + 10 and len(scalar.BINARY) == 11   # + the SpecialFunctions subset
+    assert "sf_begin" not in scalar.UNARY and "binary_end" not in scalar.BINARY
 
 
 def test_tracer_single_primitive_and_constants():
@@ -103,7 +105,7 @@ def test_partial_needs_table_matches_the_kernels():
     from nabla_jl_b200 import fusion
     L = nb._lib.lib()
     for name, op in nb._lib.OPCODES.items():
-        if name.endswith("_end"):
+        if name.endswith(("_end", "_begin")):
             continue
         for wrt in (0, 1):
             assert fusion.partial_needs(op, wrt) == L.nb_op_partial_needs(op, wrt), (name, wrt)
