@@ -130,6 +130,16 @@ def _mr_fused(y, ybar, rvs):
         scaled = yb.ctx.empty(yb.shape, yb.dtype)
         K.bcast_reduce(None, [yb], scaled, scale=scale)
         ybar = scaled
+    if reduce and prog.single_op == _ID and len(dev) == 1 and isinstance(y.args[dev_pos[0] + 1], Node):
+        # plain sum(x; dims) / mean(x; dims): x̄ is ȳ broadcast back up (ChainRules returns it as an
+        # InplaceableThunk).  A fresh slot gets the lazy BroadcastView — the consumer's pullback kernel reads ȳ
+        # in place as a broadcast operand — instead of a full-size fill (N·s written, then N·s re-read).
+        xid = y.args[dev_pos[0] + 1].pos
+        if d_tape[xid - 1] is UNDEF:
+            base = K.materialize(ybar)
+            base.shared = True
+            d_tape[xid - 1] = BroadcastView(base, dev[0].shape)
+            return
     y_saved = None if reduce else y.val
     kdev = dev
     if any(d.pending is not None for d in dev) or (y_saved is not None and y_saved.pending is not None):
