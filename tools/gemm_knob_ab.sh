@@ -12,10 +12,5 @@ run() {
      --clock-control none -k regex:k_gemm_tc -s 2 -c 1 python tools/bench_gemm.py 32768 bf16x3 2>&1 \
      | grep -E "dram__|duration|lts__|tensor" >> gpurun_out/knob_traffic.log
 }
-run base X=1
-run p72_gm8 NB_GEMM_PAIRS=72 NB_GEMM_GROUP_M=8
-run p72_gm9 NB_GEMM_PAIRS=72 NB_GEMM_GROUP_M=9
-run p70_gm7 NB_GEMM_PAIRS=70 NB_GEMM_GROUP_M=7
-run p74_gm8 NB_GEMM_GROUP_M=8
-run p64_gm8 NB_GEMM_PAIRS=64 NB_GEMM_GROUP_M=8
+for cfg in "$@"; do run $cfg; done
 cat gpurun_out/knob_time.log | grep -E "==|avg"; cat gpurun_out/knob_traffic.log
