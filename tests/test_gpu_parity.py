@@ -609,6 +609,22 @@ def test_vae_gradient_f64(nb, orc):
             close(_np(a), b)
 
 
+def test_vae_gradient_f32_fused(nb, orc):
+    """C4 in Float32 (BF16x3 tensor products with the deferred / fused launches: `tanh.(Wh*X)`, `logistic.(Vf*h)`
+    are activation-only epilogues, `exp.(Wsig*h)` feeds two consumers) against the Float64 oracle."""
+    import nabla_jl_b200.workloads as wl
+    dx, dz, dh, B = 784, 10, 500, 1024
+    params, X, noise = wl.vae_inputs(dx=dx, dz=dz, dh=dh, B=B, dtype=np.float32, seed=3)
+    kw = dict(lam=1e-3, scal=60000 / B, dz=dz)
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    ref = orc.nabla(lambda *p: wl.vae_log_joint(orc, f64(X), f64(noise), *p, **kw))(*[f64(p) for p in params])
+    ctx = nb.get_context()
+    Xd, Nd = ctx.asarray(X), ctx.asarray(noise)
+    got = nb.nabla(lambda *p: wl.vae_log_joint(nb, Xd, Nd, *p, **kw))(*params)
+    for a, b in zip(got, ref):
+        close(_np(a), b, np.float32)
+
+
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
 @pytest.mark.parametrize("row_vector", [False, True])
 def test_c3_broadcast_sum(nb, orc, dtype, row_vector):
