@@ -107,6 +107,7 @@ struct GemmArgs {
   uint64_t hint_a, hint_b;  // L2 eviction policies of the operand loads (0 = none)
   int32_t vec_store;        // epilogue may use 16-byte accesses along the rows (alignment checked on the host)
   int32_t serpentine;       // odd waves walk K backwards: the panel slices used last are still in the L2
+  int32_t dbg_extra_loads;  // experiment: re-load the A-hi tile this many extra times per K block into scratch smem
   EpiArgs epi;
 };
 
@@ -756,7 +757,8 @@ struct Cfg2 {
   static constexpr uint32_t B_BYTES = 128 * 128;                  // this CTA's 128 columns of B
   static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * 2;  // hi + lo
   static constexpr int STAGES = 3;
-  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 512;
+  static constexpr uint32_t DBG_BYTES = 16384;  // scratch for the traffic-sensitivity experiment (NB_GEMM_DBG_EXTRA_LOAD)
+  static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 1024 + DBG_BYTES;
   static constexpr uint32_t TMEM_COLS = 512;
 };
 
@@ -796,6 +798,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_THREADS); }
     // consumers of a slot: leader MMA thread + peer producer + the epilogue threads of both CTAs
     for (int q = 0; q < SCHED_SLOTS; ++q) { mbar_init(&sfull[q], 1); mbar_init(&sempty[q], 2 + 2 * EPI_THREADS); }
+    mbar_init(sempty + SCHED_SLOTS + 4, 1);  // dbg_bar
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {
@@ -814,7 +817,9 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
     // ===================== TMA producer (both CTAs, each its own halves) =====================
     if (lane == 0) {
       int s = 0, q = 0;
-      uint32_t ph = 0, qph = 0;
+      uint32_t ph = 0, qph = 0, dph = 0;
+      bool dbg_pending = false;
+      uint64_t* dbg_bar = sempty + SCHED_SLOTS + 4;  // (a spare barrier word behind the scheduler ring)
       int t_next = leader ? atomicAdd(g.tile_counter, 1) : 0;
       for (;;) {
         int t;
@@ -839,6 +844,21 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         const int m0 = tm * 256 + (int)rank * 128, n0 = tn * BN + (int)rank * 128;
         const bool flip = g.serpentine && ((t / (int)(gridDim.x >> 1)) & 1);
         for (int kb = 0; kb < nkb; ++kb) {
+          if (g.dbg_extra_loads) {
+            // L2->SM traffic sensitivity experiment: the same A-hi tile again, into scratch nobody reads
+            uint8_t* scratch = smem + STAGES * C_::STAGE_BYTES + 1024;
+            if (dbg_pending) { mbar_wait(dbg_bar, dph); dph ^= 1; }
+            const int kx = (int)g.k_begin + (flip ? nkb - 1 - kb : kb) * BK;
+            mbar_expect_tx(dbg_bar, C_::A_BYTES * (uint32_t)g.dbg_extra_loads);
+            for (int e = 0; e < g.dbg_extra_loads; ++e) {
+              if (g.a_mn) {
+                for (int c = 0; c < 128 / MNC; ++c) tma_load_2d(scratch + c * CHUNK_BYTES, &mA0, dbg_bar, m0 + MNC * c, kx, 0);
+              } else {
+                tma_load_2d(scratch, &mA0, dbg_bar, kx, m0, 0);
+              }
+            }
+            dbg_pending = true;
+          }
           mbar_wait(&empty[s], ph ^ 1);
           if (leader) mbar_expect_tx(&full[s], 2 * C_::STAGE_BYTES);  // both CTAs' bytes land on this barrier
           uint8_t* st = smem + s * C_::STAGE_BYTES;
@@ -867,6 +887,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           if (++s == STAGES) { s = 0; ph ^= 1; }
         }
       }
+      if (dbg_pending) mbar_wait(dbg_bar, dph);
     }
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
@@ -1304,6 +1325,8 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
       g.vec_store = v ? 1 : 0;
       g.serpentine = 1;  // ncu, forward 8192x32768x8192: DRAM reads 8.95 -> 7.69 GB, L2 72.8 -> 70.1 GB
       if (const char* e = getenv("NB_GEMM_SERPENTINE")) g.serpentine = atoi(e) != 0;
+      g.dbg_extra_loads = 0;
+      if (const char* e = getenv("NB_GEMM_DBG_EXTRA_LOAD")) g.dbg_extra_loads = atoi(e) > 0 && atoi(e) <= 4 ? atoi(e) : 0;
     }
     // long K is launched in ranges so that the operand panel of a rasterisation group fits the L2
     int64_t KRANGE = 8192;
