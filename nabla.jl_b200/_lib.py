@@ -8,7 +8,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libnabla_cuda.so")
+LIB_PATH = os.environ.get("NABLA_CUDA_LIB") or os.path.join(_HERE, "libnabla_cuda.so")  # (same override as julia/NablaCUDA.jl)
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nabla_cuda.h")
 
 NB_MAX_DIMS = 4

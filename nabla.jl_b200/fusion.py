@@ -214,14 +214,17 @@ class Deferred:
                            accumulate=self.rowsum_acc)
 
 
-def _fusable_ctx(ctx):
-    return ctx.fuse and ctx.math_mode != _lib.MATH_FP32 and not getattr(ctx, "capturing", False)
-
-
 def defer_product(tA, tB, alpha, A, B, m, n, k):
-    """-> a lazy (m x n) result for ``alpha*op(A)*op(B)``, or None when the product should run now."""
+    """-> a lazy (m x n) result for ``alpha*op(A)*op(B)``, or None when the product should run now.
+
+    Deferred: Float32 products on the tensor-core path (not the FP32 SIMT cross-check mode), also inside a
+    CUDA-graph capture (everything a captured sweep returns is forced before the capture ends).  Float64 products
+    are not: a fused DMMA epilogue was built and measured slower than the separate launches (the DMMA kernel is
+    not persistent, so the epilogue is a serial tail of every CTA; see csrc/gemm_simt.cu nb_gemm_fused)."""
     ctx = A.ctx
-    if not _fusable_ctx(ctx) or A.dtype.itemsize != 4 or m * n * k < (1 << 18) or min(m, n, k) < 1:
+    if not ctx.fuse or A.dtype.itemsize != 4 or m * n * k < (1 << 18) or min(m, n, k) < 1:
+        return None
+    if ctx.math_mode == _lib.MATH_FP32:
         return None
     return Deferred(ctx, tA, tB, alpha, A, B, m, n, k).new_result()
 

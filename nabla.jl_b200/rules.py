@@ -15,6 +15,7 @@ from .device import BroadcastView, DevArray, get_context
 from .scalar import CATALOGUE, Program, ScalarFn, compile_scalar
 
 _ADD, _SUB, _ID, _MUL = OPCODES["add"], OPCODES["sub"], OPCODES["identity"], OPCODES["mul"]
+_LAZY_SUM = __import__("os").environ.get("NB_LAZY_SUM", "1") != "0"
 
 
 def _is_num(x):
@@ -130,7 +131,7 @@ def _mr_fused(y, ybar, rvs):
         scaled = yb.ctx.empty(yb.shape, yb.dtype)
         K.bcast_reduce(None, [yb], scaled, scale=scale)
         ybar = scaled
-    if reduce and prog.single_op == _ID and len(dev) == 1 and isinstance(y.args[dev_pos[0] + 1], Node):
+    if reduce and prog.single_op == _ID and len(dev) == 1 and isinstance(y.args[dev_pos[0] + 1], Node) and _LAZY_SUM:
         # plain sum(x; dims) / mean(x; dims): x̄ is ȳ broadcast back up (ChainRules returns it as an
         # InplaceableThunk).  A fresh slot gets the lazy BroadcastView — the consumer's pullback kernel reads ȳ
         # in place as a broadcast operand — instead of a full-size fill (N·s written, then N·s re-read).

@@ -41,12 +41,10 @@ class CapturedGradient:
             self.ctx.sync()
         self.ctx.flush_deferred()
         check(L.nb_graph_begin(h), h)
-        self.ctx.capturing = True   # no deferred launches inside a capture (fusion.py): the graph is the fusion
         try:
             self.y, self.grads, self._tape = self._evaluate(f)
-            self.ctx.capturing = False
+            self.ctx.flush_deferred(only_side_outputs=True)   # nothing the graph owes may launch after the capture
         except BaseException:
-            self.ctx.capturing = False
             g = C.c_void_p()
             L.nb_graph_end(h, C.byref(g))
             if g:
@@ -70,6 +68,10 @@ class CapturedGradient:
         # a sensitivity that aliases another slot (a rule returned ȳ itself) gets its own buffer so
         # the in-place allreduce of ShardedGradient never sums one buffer twice
         grads = [g.copy() if g.shared else g for g in grads]
+        # deferred products (fusion.py) must be launched now — inside the capture when there is one
+        for g in grads:
+            g.ptr
+        unbox(y).ptr
         # keep the forward tape and the reverse tape alive: the graph refers to their buffers
         return unbox(y), grads, (t, df)
 

@@ -1153,3 +1153,45 @@ def test_kron_plus_I_copy(nb, orc, dtype):
     check_case(nb, orc, lambda ns, a: ns.copy(a), [A], ybar, dtype)
     with pytest.raises(ValueError):
         nb.plus_I(nb.get_context().asarray(rng.standard_normal((3, 4)).astype(dtype)), 1.0)
+
+
+def test_fused_dense_layers_inside_graph_capture(nb, orc, ctx):
+    """Deferred / fused Float32 product launches inside a CUDA-graph capture: everything the captured sweep returns
+    is forced before the capture ends, the replay reproduces the eager gradients and sees new data in the same
+    buffers; Float64 products are never deferred (the fused entry point answers NB_ERR_UNSUPPORTED)."""
+    import ctypes as C
+    import nabla_jl_b200.workloads as wl
+    from nabla_jl_b200 import fusion
+    dims, B = (96, 256, 192, 10), 512
+    W, b, X, Y = wl.mlp_inputs(dims, B, np.float32, seed=12)
+    nl = len(dims) - 1
+    f64 = lambda a: np.asarray(a, dtype=np.float64)
+    Xd, Yd = ctx.asarray(X), ctx.asarray(Y)
+    params = [ctx.asarray(p) for p in (*W, *b)]
+    eager = [g.numpy() for g in nb.nabla(wl.mlp_objective(nb, Xd, Yd, 1e-3, nl))(*params)]
+    n0 = ctx.stats()["kernel_launches"]
+    nb.nabla(wl.mlp_objective(nb, Xd, Yd, 1e-3, nl))(*params)
+    eager_launches = ctx.stats()["kernel_launches"] - n0
+    cap = nb.CapturedGradient(wl.mlp_objective(nb, Xd, Yd, 1e-3, nl), params)
+    _, g1 = cap()
+    ctx.sync()
+    for a, e in zip(g1, eager):
+        close(a.numpy(), e, np.float32, scale=0.2)
+    assert cap.launches_per_replay > 0 and eager_launches > 0
+    X2 = np.random.default_rng(9).random(X.shape).astype(np.float32)
+    Xd.copy_from_host(X2)
+    _, g2 = cap()
+    ctx.sync()
+    ref2 = orc.nabla(wl.mlp_objective(orc, f64(X2), f64(Y), 1e-3, nl))(*[f64(p) for p in (*W, *b)])
+    for a, r in zip(g2, ref2):
+        close(a.numpy(), r, np.float32)
+    # Float64
+    A64, B64 = ctx.asarray(np.ones((256, 256))), ctx.asarray(np.ones((256, 256)))
+    out = ctx.empty((256, 256), np.float64)
+    epi = fusion.nb_gemm_epilogue()
+    epi.kind, epi.op = 1, nb._lib.OPCODES["tanh"]
+    st = ctx.L.nb_gemm_fused(ctx.h, b"N", b"N", 256, 256, 256, 1.0, A64.ptr, 256, B64.ptr, 256, out.ptr, 256,
+                             out.nb_dtype, ctx.math_mode, C.byref(epi))
+    assert st == 4
+    z = nb.matmul(nb.Leaf(nb.Tape(), np.ones((256, 256))), B64)
+    assert z.val.pending is None
