@@ -166,7 +166,7 @@ class DevArray:
     e.g. when a rule returns ȳ itself; the accumulate path copies instead of mutating it
     (SURVEY.md §7 hard part 5; reference pin: test/core.jl:211-224)."""
 
-    __slots__ = ("ctx", "_ptr", "shape", "dtype", "shared", "adjvec", "_base", "pending", "__weakref__")
+    __slots__ = ("ctx", "_ptr", "shape", "dtype", "shared", "adjvec", "_base", "pending", "_tensor", "__weakref__")
     __array_priority__ = 3000.0
 
     def __init__(self, ctx, shape, dtype, ptr=None, base=None, lazy=False):
@@ -181,6 +181,7 @@ class DevArray:
         self.adjvec = False
         self._base = base
         self.pending = None  # fusion.Deferred: the launch that will produce this value (see `ptr`)
+        self._tensor = None  # cached descriptor (shape and address are fixed once the buffer exists)
         if ptr is not None:
             self._ptr = ptr
         elif lazy:
@@ -231,8 +232,19 @@ class DevArray:
         return _DT[self.dtype]
 
     def tensor(self, shape=None):
+        if self.pending is not None:
+            self.pending.flush()   # a descriptor is about to be handed to a kernel: the value must exist
+        if shape is None:
+            t = self._tensor
+            if t is not None:
+                return t
+            t = self._make_tensor(self.shape)
+            self._tensor = t
+            return t
+        return self._make_tensor(shape)
+
+    def _make_tensor(self, shp):
         t = nb_tensor()
-        shp = self.shape if shape is None else shape
         t.data = self.ptr
         t.dtype = self.nb_dtype
         t.ndim = len(shp)

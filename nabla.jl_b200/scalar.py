@@ -146,11 +146,50 @@ class Program:
         return self.ops[0] if len(self.ops) == 1 else (OPCODES["identity"] if not self.ops else None)
 
 
+_TRACE_CACHE = {}
+
+
+def _trace_key(f, nargs, const_args):
+    """Cache key of a traced function: catalogue primitives by name; Python functions by code object plus the
+    values (numbers) / identities (anything else) of their closure cells and defaults — a lambda re-created by the
+    same source line with the same captured values traces to the same program."""
+    consts = tuple(sorted((i, float(v)) for i, v in const_args.items()))
+    if isinstance(f, ScalarFn):
+        return ("prim", f.name, nargs, consts)
+    code = getattr(f, "__code__", None)
+    if code is None:
+        return None
+    cells = []
+    for c in (getattr(f, "__closure__", None) or ()):
+        try:
+            v = c.cell_contents
+        except ValueError:
+            return None
+        cells.append(("n", float(v)) if isinstance(v, numbers.Real) and not isinstance(v, bool) else ("o", id(v)))
+    if getattr(f, "__defaults__", None) or getattr(f, "__kwdefaults__", None):
+        return None
+    return ("fn", code, tuple(cells), nargs, consts)
+
+
 def compile_scalar(f, nargs, const_args=None):
     """Trace ``f`` on ``nargs`` symbolic operands -> Program.  ``const_args`` maps operand positions
     to Python numbers that are baked in as constants (non-differentiable literals such as ϵ); the
-    remaining operands are renumbered 0..k-1 in order."""
+    remaining operands are renumbered 0..k-1 in order.  Traces are cached (`_trace_key`)."""
     const_args = const_args or {}
+    key = _trace_key(f, nargs, const_args)
+    if key is not None:
+        hit = _TRACE_CACHE.get(key)
+        if hit is not None:
+            return hit[0]
+    prog = _compile_scalar(f, nargs, const_args)
+    if key is not None:
+        if len(_TRACE_CACHE) > 4096:
+            _TRACE_CACHE.clear()
+        _TRACE_CACHE[key] = (prog, f)   # (keeps f alive: ids of closure contents stay unique while cached)
+    return prog
+
+
+def _compile_scalar(f, nargs, const_args):
     syms, k = [], 0
     for i in range(nargs):
         if i in const_args:
