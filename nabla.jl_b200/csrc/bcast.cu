@@ -731,18 +731,27 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
     const int64_t cap = (int64_t)sms * 8;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    for (int k = 0; k < P.nout; ++k) {
-      P.out[k].active = 1;
-      if (P.out[k].mode == OM_ALL) {
-        int32_t rc = alloc_partial(k, blocks, 1);
-        if (rc != NB_OK) return rc;
-      }
-    }
-    if (lean_mode >= 0 && P.rows % V == 0 &&
-        lean_try(0, LeanLaunch{P.rows / V, (unsigned)blocks, dim3(), dim3(), 0, 0})) {
+    for (int k = 0; k < P.nout; ++k) P.out[k].active = 1;
+    // single primitives: the lean flat kernel takes any length (scalar tail, 0-dim operands) and, when one CTA
+    // covers the array, writes reduced results itself (no k_finish launch); programs need whole vectors
+    const bool lean_ok = lean_mode >= 0 && (prog_lean ? P.rows % V == 0 : true);
+    const bool direct = lean_ok && !prog_lean && blocks == 1;
+    if (!direct)
+      for (int k = 0; k < P.nout; ++k)
+        if (P.out[k].mode == OM_ALL) {
+          int32_t rc = alloc_partial(k, blocks, 1);
+          if (rc != NB_OK) return rc;
+        }
+    if (lean_ok && lean_try(0, LeanLaunch{P.rows / V, (unsigned)blocks, dim3(), dim3(), 0, 0})) {
       NB_LAUNCH_CHECK(ctx);
       return finish();
     }
+    if (direct)  // (not reached for catalogue ops; keeps the general kernel's contract if it ever is)
+      for (int k = 0; k < P.nout; ++k)
+        if (P.out[k].mode == OM_ALL) {
+          int32_t rc = alloc_partial(k, blocks, 1);
+          if (rc != NB_OK) return rc;
+        }
     {
       const size_t sm = with_slots(k_flat<T, Ev>, 0, 256, V);
       k_flat<T, Ev><<<(unsigned)blocks, 256, sm, st>>>(P, G);

@@ -30,6 +30,10 @@ struct LeanNeeds {
 template <typename T, int V>
 __device__ __forceinline__ void lean_ld(const Opnd& o, int64_t r, int64_t c, T (&x)[V]) {
   const T* p = (const T*)o.p + c * o.cs;
+  if constexpr (V == 1) {  // scalar form: tail elements of a flat array, 0-dim operands
+    x[0] = __ldg(o.rs ? p + r : p);
+    return;
+  }
   if (o.rs) {
     using VT = typename VecOf<T>::type;
     const VT v = __ldg(reinterpret_cast<const VT*>(p + r));
@@ -48,6 +52,8 @@ struct LeanNoExtra {};
 template <typename T, int V, int OP, int MODE>
 struct LeanPack {
   using Extra = LeanNoExtra;
+  using Scalar = LeanPack<T, 1, OP, MODE>;  // the same op on single elements (flat tails, 0-dim operands)
+  static constexpr bool HAS_TAIL = true;
   static constexpr int NOUT = MODE == LM_PULL_AB ? 2 : 1;
   static constexpr int U = 4;  // independent vectors in flight per thread
   static constexpr int NEED = LeanNeeds<OP, MODE>::value;
@@ -116,6 +122,10 @@ template <typename T, int V>
 __device__ __forceinline__ void lean_store(const OutS& out, int64_t off, const T (&v)[V], T scale) {
   using VT = typename VecOf<T>::type;
   T* p = (T*)out.p + off;
+  if constexpr (V == 1) {
+    *p = out.acc ? *p + v[0] * scale : v[0] * scale;
+    return;
+  }
   VT w;
   T* e = reinterpret_cast<T*>(&w);
   if (out.acc) {
@@ -176,11 +186,32 @@ __global__ void __launch_bounds__(256) k_flat_lean(const MRP P, int64_t nvec, co
       }
     }
   }
+  if constexpr (Pk::HAS_TAIL) {
+    // elements past the last whole vector (any length, incl. 0-dim operands: nvec == 0, one element)
+    using P1 = typename Pk::Scalar;
+    for (int64_t e = nvec * V + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < P.rows; e += S) {
+      P1 x1[1];
+      x1[0].load(P, X, e, 0);
+      T o1[1][2][1];
+      P1::template compute_many<1>(P, X, x1, o1);
+#pragma unroll
+      for (int k = 0; k < NOUT; ++k) {
+        if (P.out[k].mode == OM_ELEM) lean_store<T, 1>(P.out[k], e, o1[0][k], scale);
+        else accs[k] += o1[0][k][0];
+      }
+    }
+  }
 #pragma unroll
   for (int k = 0; k < NOUT; ++k) {
     if (P.out[k].mode != OM_ALL) continue;
     T s = block_sum<T>(accs[k], red);
-    if (threadIdx.x == 0) ((T*)P.out[k].partial)[blockIdx.x] = s;
+    if (threadIdx.x == 0) {
+      if (P.out[k].partial) ((T*)P.out[k].partial)[blockIdx.x] = s;
+      else {  // single-CTA launch: no second phase, the result is final here
+        T* dst = (T*)P.out[k].p;
+        *dst = P.out[k].acc ? *dst + s * scale : s * scale;
+      }
+    }
   }
 }
 

@@ -25,6 +25,8 @@ template <typename T, int V, int NARGS, int MODE, int UU>
 struct ProgPack {
   using Extra = nb_prog;
   using VT = typename VecOf<T>::type;
+  static constexpr bool HAS_TAIL = false;  // programs keep the whole-vector restriction
+  using Scalar = ProgPack;
   static constexpr int NOUT = MODE == LM_PULL_AB ? 2 : 1;
   static constexpr int U = UU;
   T x[NARGS][V];
