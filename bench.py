@@ -451,6 +451,12 @@ def run_gpu(args):
         achieved = flop / (gemm_ms_total * 1e-3) / 1e12
         ratio = {"bf16x3": 1.0, "3xtf32": 0.5, "tf32": 0.5, "fp32": 0.5}[args.math] if args.dtype == "f32" else 0.5
         peak = peaks["bf16_sustained"] * ratio
+        f64_peak_note = None
+        if args.dtype == "f64":
+            # Float64 runs on DMMA (mma.sync.m8n8k4.f64): no measured figure in MEASURED_PEAKS.json, so the
+            # denominator is the nominal 40 TFLOP/s FP64 tensor rate of the part (ncu: Tensor (DP) pipe 77 % active)
+            peak, ratio = 40.0, None
+            f64_peak_note = "nominal FP64 tensor (DMMA) rate 40 TFLOP/s: MEASURED_PEAKS.json has no FP64 figure"
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
         if args.math == "bf16x3" and args.dtype == "f32" and n == 1 and B == 32768 and os.path.exists(tpath):
@@ -462,12 +468,12 @@ def run_gpu(args):
                 "traffic_note": "DRAM bytes per GEMM launch (8192x32768x8192) from profiles/r1_gemm_traffic.json; "
                                 "algorithmic bytes 2.42e9" if traffic else None,
                 "kernel": "nb_gemm (dense GEMM sensitivities: forward A*B, Abar=Ybar*B', Bbar=A'*Ybar)",
-                "peak_note": f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s x {ratio} "
+                "peak_note": f64_peak_note or f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s x {ratio} "
                              "(kind::f16 for bf16x3, kind::tf32 at half that rate otherwise); achieved counts "
                              "ALGORITHMIC flops 2mnk: the split modes needed for rtol 1e-4 (bf16x3, 3xtf32) "
                              "issue three tensor passes per product, so they top out at 1/3 of this peak "
                              "(tensor_work_frac = 3 x frac)",
-                "tensor_work_frac": (3.0 if args.math in ("bf16x3", "3xtf32") else 1.0) * achieved / peak,
+                "tensor_work_frac": (3.0 if (args.dtype == "f32" and args.math in ("bf16x3", "3xtf32")) else 1.0) * achieved / peak,
                 "launches": sum(v[1] for v in by_tag.values()),
                 "share_of_step": gemm_ms_total / ms,
                 "avg_launch_ms": gemm_ms_total / max(1, sum(v[1] for v in by_tag.values())),
