@@ -453,10 +453,12 @@ def run_gpu(args):
         peak = peaks["bf16_sustained"] * ratio
         f64_peak_note = None
         if args.dtype == "f64":
-            # Float64 runs on DMMA (mma.sync.m8n8k4.f64): no measured figure in MEASURED_PEAKS.json, so the
-            # denominator is the nominal 40 TFLOP/s FP64 tensor rate of the part (ncu: Tensor (DP) pipe 77 % active)
-            peak, ratio = 40.0, None
-            f64_peak_note = "nominal FP64 tensor (DMMA) rate 40 TFLOP/s: MEASURED_PEAKS.json has no FP64 figure"
+            # Large Float64 products run as 21 exact int8 slice products on the tensor cores (csrc/ozaki.cu): the
+            # bound is the kind::i8 pipe at twice the bf16 rate, i.e. 2 x bf16 / 21 in algorithmic Float64 FLOPs
+            # (MEASURED_PEAKS.json has no int8 or FP64 figure; DMMA, used for the small products, is ~36 TFLOP/s)
+            peak, ratio = 2.0 * peaks["bf16_sustained"] / 21.0, None
+            f64_peak_note = (f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s x 2 (kind::i8) / 21 "
+                             "int8 passes per Float64 product (Ozaki split, 6 slices); small products on DMMA")
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
         if args.math == "bf16x3" and args.dtype == "f32" and n == 1 and B == 32768 and os.path.exists(tpath):

@@ -11,6 +11,8 @@
 int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
                      double* C, int64_t ldc);
+int32_t nb_gemm_ozaki(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                      int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
 int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, float alpha,
                         const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                         float* C, int64_t ldc, int32_t math_mode, const nb_gemm_epilogue* epi);
@@ -151,6 +153,14 @@ int32_t nb_gemm(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k
     return NB_OK;
   }
   if (dtype == NB_F64) {
+    // large products: exact integer slice products on the tensor cores (ozaki.cu); NB_F64_OZAKI=0 or
+    // math_mode == NB_MATH_FP32 (the "no tensor-core tricks" cross-check mode) keeps everything on DMMA
+    static const bool ozaki_on = !(getenv("NB_F64_OZAKI") && atoi(getenv("NB_F64_OZAKI")) == 0);
+    if (ozaki_on && math_mode != NB_MATH_FP32) {
+      int32_t rc = nb_gemm_ozaki(ctx, tA, tB, m, n, k, alpha, (const double*)A, lda, (const double*)B, ldb, beta,
+                                 (double*)C, ldc);
+      if (rc != NB_ERR_UNSUPPORTED) return rc;
+    }
     int32_t rc = nb_gemm_dmma(ctx, tA, tB, m, n, k, alpha, (const double*)A, lda, (const double*)B,
                               ldb, beta, (double*)C, ldc);
     if (rc != NB_ERR_UNSUPPORTED) return rc;

@@ -54,17 +54,21 @@ constexpr int EPI_THREADS = 256;
 constexpr int REGS_WG0 = 80, REGS_EPI = 208;  // 128*80 + 256*208 <= 384*168
 
 // Operand kinds.  Every staged row is 128 bytes (one swizzle row), so tile byte sizes are kind-independent.
-enum { KIND_TF32 = 0, KIND_3XTF32 = 1, KIND_BF16X3 = 2 };
+// KIND_I8: signed 8-bit operands, exact int32 accumulation (kind::i8) — the slice products of the Float64 Ozaki
+// split (ozaki.cu); K-major operands only, one pass, no K chunking (the int32 accumulator is exact).
+enum { KIND_TF32 = 0, KIND_3XTF32 = 1, KIND_BF16X3 = 2, KIND_I8 = 3 };
 template <int KIND>
 struct KindT {
-  static constexpr int ESIZE = KIND == KIND_BF16X3 ? 2 : 4;      // bytes per staged element
+  static constexpr int ESIZE = KIND == KIND_I8 ? 1 : KIND == KIND_BF16X3 ? 2 : 4;  // bytes per staged element
   static constexpr int BK = 128 / ESIZE;                          // elements of K per stage (32 / 64)
   static constexpr int UMMA_K = 32 / ESIZE;                       // K of one tcgen05.mma (8 / 16)
   static constexpr int MN_CHUNK = 128 / ESIZE;                    // MN-elements per 128-byte row (32 / 64)
   static constexpr uint32_t CHUNK_BYTES = BK * 128;               // one MN-major chunk: MN_CHUNK x BK rows
-  static constexpr int NSPLIT = KIND == KIND_TF32 ? 1 : 2;        // staged copies per operand (hi, lo)
-  static constexpr int NPASS = KIND == KIND_TF32 ? 1 : 3;
-  static constexpr uint32_t FMT = KIND == KIND_BF16X3 ? 1u : 2u;  // instruction-descriptor a/b format
+  static constexpr int NSPLIT = (KIND == KIND_TF32 || KIND == KIND_I8) ? 1 : 2;  // staged copies per operand (hi, lo)
+  static constexpr int NPASS = (KIND == KIND_TF32 || KIND == KIND_I8) ? 1 : 3;
+  // instruction-descriptor a/b format: F32F16 family 1 = bf16, 2 = tf32; S8 family 1 = signed 8 bit
+  static constexpr uint32_t FMT = (KIND == KIND_BF16X3 || KIND == KIND_I8) ? 1u : 2u;
+  static constexpr uint32_t CFMT = KIND == KIND_I8 ? 2u : 1u;     // accumulator: 1 = f32, 2 = s32
   // MN-major smem layout (see make_desc)
   static constexpr uint64_t MN_TYPE = KIND == KIND_BF16X3 ? 2 : 1;
   static constexpr uint64_t MN_SBO = KIND == KIND_BF16X3 ? 1024 : 512;
@@ -109,6 +113,11 @@ struct GemmArgs {
   int32_t serpentine;       // odd waves walk K backwards: the panel slices used last are still in the L2
   int32_t dbg_extra_loads;  // experiment: re-load the A-hi tile this many extra times per K block into scratch smem
   EpiArgs epi;
+  // KIND_I8: C64[i,j] = beta64*C64[i,j] + scale64 * row_scale[i] * col_scale[j] * (int32 accumulator)
+  double* C64;
+  const double* row_scale;
+  const double* col_scale;
+  double scale64, beta64;
 };
 
 constexpr int SCHED_SLOTS = 4;
@@ -196,7 +205,14 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 template <int KIND>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
-  if (KIND == KIND_BF16X3) {
+  if (KIND == KIND_I8) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+  } else if (KIND == KIND_BF16X3) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -412,8 +428,32 @@ struct EpiAcc {
     }
   }
 
+  // KIND_I8: r[] holds the exact int32 accumulator bits; scaled into the Float64 C (ozaki.cu)
+  __device__ __forceinline__ void store_i8(const GemmArgs& g, int64_t gm, int64_t n0) {
+    if (gm >= g.M) return;
+    const double rs = g.scale64 * g.row_scale[gm];
+    const double beta = g.beta64;
+#pragma unroll
+    for (int c = 0; c < NCOL / 8; ++c) {
+      const int64_t nb = n0 + c * 8;
+      if (nb >= g.N) break;
+      double* cp = g.C64 + gm + nb * g.ldc;
+      double old[8], cs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = nb + j < g.N;
+        cs[j] = ok ? g.col_scale[nb + j] : 0.0;
+        old[j] = (ok && beta != 0.0) ? cp[(int64_t)j * g.ldc] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (nb + j < g.N) cp[(int64_t)j * g.ldc] = beta * old[j] + rs * cs[j] * (double)__float_as_int(r[c * 8 + j]);
+    }
+  }
+
   // C[gm, n0 .. n0+NCOL) = epilogue(alpha * r + beta * C); `part` indexes this thread's row-sum partial
   __device__ __forceinline__ void store(const GemmArgs& g, int64_t gm, int64_t n0, int part, int lane) {
+    if constexpr (KIND == KIND_I8) { store_i8(g, gm, n0); return; }
     if (g.vec_store) { store_vec(g, gm - lane, n0, part, lane); return; }
     using SplitT = typename std::conditional<KIND == KIND_BF16X3, __nv_bfloat16, float>::type;
     if (gm >= g.M) return;
@@ -584,7 +624,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (KT::FMT << 7) | (KT::FMT << 10) | ((uint32_t)g.a_mn << 15) |
+      const uint32_t idesc = (KT::CFMT << 4) | (KT::FMT << 7) | (KT::FMT << 10) | ((uint32_t)g.a_mn << 15) |
                              ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_kstep = g.a_mn ? KT::MN_KSTEP : 32u;  // K-major: UMMA_K elements = 32 bytes
       const uint32_t b_kstep = g.b_mn ? KT::MN_KSTEP : 32u;
@@ -741,6 +781,15 @@ __device__ __forceinline__ void st_shared_cta(const void* local_addr, uint32_t c
       ::"r"(smem_u32(local_addr)), "r"(cta), "r"(v)
       : "memory");
 }
+__device__ __forceinline__ void tc_mma_i8_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                  uint32_t accumulate) {
   asm volatile(
@@ -751,23 +800,27 @@ __device__ __forceinline__ void tc_mma_bf16_pair(uint32_t d_tmem, uint64_t adesc
       : "memory");
 }
 
-struct Cfg2 {
+template <int KIND>
+struct Cfg2T {
   static constexpr int BN = 256;                                  // pair tile: 256 x 256
   static constexpr uint32_t A_BYTES = 128 * 128;                  // this CTA's 128 rows of A
   static constexpr uint32_t B_BYTES = 128 * 128;                  // this CTA's 128 columns of B
-  static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * 2;  // hi + lo
-  static constexpr int STAGES = 3;
+  static constexpr uint32_t NS = KindT<KIND>::NSPLIT;             // hi + lo (BF16x3) or one copy (I8)
+  static constexpr uint32_t STAGE_BYTES = (A_BYTES + B_BYTES) * NS;
+  static constexpr int STAGES = (int)(196608u / STAGE_BYTES);     // 3 (BF16x3) / 6 (I8)
   static constexpr uint32_t DBG_BYTES = 16384;  // scratch for the traffic-sensitivity experiment (NB_GEMM_DBG_EXTRA_LOAD)
   static constexpr uint32_t SMEM = STAGES * STAGE_BYTES + 1024 + 1024 + DBG_BYTES;
   static constexpr uint32_t TMEM_COLS = 512;
 };
+using Cfg2 = Cfg2T<KIND_BF16X3>;
 
+template <int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(NTHREADS, 1)
 k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUtensorMap mA1,
                const __grid_constant__ CUtensorMap mB0, const __grid_constant__ CUtensorMap mB1, const GemmArgs g) {
-  constexpr int KIND = KIND_BF16X3;
   using KT = KindT<KIND>;
-  using C_ = Cfg2;
+  using C_ = Cfg2T<KIND>;
+  constexpr int NS = (int)C_::NS;
   constexpr int STAGES = C_::STAGES, BN = C_::BN;
   constexpr int BK = KT::BK, MNC = KT::MN_CHUNK;
   constexpr uint32_t CHUNK_BYTES = KT::CHUNK_BYTES;
@@ -864,9 +917,9 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
           uint8_t* st = smem + s * C_::STAGE_BYTES;
           const int k0 = (int)g.k_begin + (flip ? nkb - 1 - kb : kb) * BK;
 #pragma unroll
-          for (int h = 0; h < 2; ++h) {
+          for (int h = 0; h < NS; ++h) {
             uint8_t* a_dst = st + h * C_::A_BYTES;
-            uint8_t* b_dst = st + 2 * C_::A_BYTES + h * C_::B_BYTES;
+            uint8_t* b_dst = st + NS * C_::A_BYTES + h * C_::B_BYTES;
             const CUtensorMap* ma = h ? &mA1 : &mA0;
             const CUtensorMap* mb = h ? &mB1 : &mB0;
             if (g.a_mn) {
@@ -892,7 +945,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = (1u << 4) | (KT::FMT << 7) | (KT::FMT << 10) | ((uint32_t)g.a_mn << 15) |
+      const uint32_t idesc = (KT::CFMT << 4) | (KT::FMT << 7) | (KT::FMT << 10) | ((uint32_t)g.a_mn << 15) |
                              ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t a_kstep = g.a_mn ? KT::MN_KSTEP : 32u;
       const uint32_t b_kstep = g.b_mn ? KT::MN_KSTEP : 32u;
@@ -914,16 +967,20 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
             tc_fence_after();
             const uint32_t st = smem_u32(smem + s * C_::STAGE_BYTES);
             const uint32_t a_hi = st, a_lo = st + C_::A_BYTES;
-            const uint32_t b_hi = st + 2 * C_::A_BYTES, b_lo = b_hi + C_::B_BYTES;
+            const uint32_t b_hi = st + NS * C_::A_BYTES, b_lo = b_hi + C_::B_BYTES;
 #pragma unroll
-            for (int p = 0; p < 3; ++p) {
-              const uint32_t ab = p == 0 ? a_lo : a_hi;
-              const uint32_t bb = p == 1 ? b_lo : b_hi;
+            for (int p = 0; p < KT::NPASS; ++p) {
+              const uint32_t ab = KT::NPASS == 1 ? a_hi : (p == 0 ? a_lo : a_hi);
+              const uint32_t bb = KT::NPASS == 1 ? b_hi : (p == 1 ? b_lo : b_hi);
 #pragma unroll
               for (int kk = 0; kk < BK / KT::UMMA_K; ++kk) {
-                tc_mma_bf16_pair(d_tmem, make_desc<KIND>(ab + kk * a_kstep, g.a_mn),
-                                 make_desc<KIND>(bb + kk * b_kstep, g.b_mn), idesc,
-                                 (uint32_t)(((kb - kb0) | p | kk) != 0));
+                const uint32_t accf = (uint32_t)(((kb - kb0) | p | kk) != 0);
+                if constexpr (KIND == KIND_I8)
+                  tc_mma_i8_pair(d_tmem, make_desc<KIND>(ab + kk * a_kstep, g.a_mn),
+                                 make_desc<KIND>(bb + kk * b_kstep, g.b_mn), idesc, accf);
+                else
+                  tc_mma_bf16_pair(d_tmem, make_desc<KIND>(ab + kk * a_kstep, g.a_mn),
+                                   make_desc<KIND>(bb + kk * b_kstep, g.b_mn), idesc, accf);
               }
             }
             tc_commit_pair(&empty[s]);  // frees the stage in BOTH CTAs
@@ -1086,10 +1143,12 @@ int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   return NB_OK;
 }
 
+template <int KIND>
 int32_t launch_pair(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
+  using C2 = Cfg2T<KIND>;
   static bool attr_done = false;
   if (!attr_done) {
-    NB_CUDA_OK(ctx, cudaFuncSetAttribute(k_gemm_tc_pair, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg2::SMEM));
+    NB_CUDA_OK(ctx, cudaFuncSetAttribute(k_gemm_tc_pair<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::SMEM));
     attr_done = true;
   }
   const int ntiles = g.tiles_m * g.tiles_n;
@@ -1097,7 +1156,7 @@ int32_t launch_pair(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   if (const char* e = getenv("NB_GEMM_PAIRS")) max_pairs = atoi(e) > 0 && atoi(e) < max_pairs ? atoi(e) : max_pairs;
   const int pairs = ntiles < max_pairs ? ntiles : max_pairs;
   NB_CUDA_OK(ctx, cudaMemsetAsync(g.tile_counter, 0, sizeof(int32_t), ctx->stream));
-  k_gemm_tc_pair<<<2 * pairs, NTHREADS, Cfg2::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
+  k_gemm_tc_pair<KIND><<<2 * pairs, NTHREADS, C2::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
 }
@@ -1353,7 +1412,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
       int64_t gm = panel_budget / (panel > 0 ? panel : 1);
       g.group_m = (int32_t)(gm < 1 ? 1 : gm > 32 ? 32 : gm);
       if (const char* e = getenv("NB_GEMM_GROUP_M")) g.group_m = atoi(e) > 0 ? atoi(e) : g.group_m;
-      if (use_pair) rc = launch_pair(ctx, maps, g);
+      if (use_pair) rc = launch_pair<KIND_BF16X3>(ctx, maps, g);
       else if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
       else if (kind == KIND_3XTF32) rc = BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
       else rc = BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);
@@ -1375,4 +1434,47 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
   for (int i = 0; i < 4; ++i)
     if (tmp[i]) nb_pool_release(ctx, tmp[i]);
   return rc;
+}
+
+// One level of the Float64 Ozaki split (ozaki.cu):  C64 = beta*C64 + scale * diag(row_scale) * (A8' * B8) * diag(col_scale)
+// with A8 (kp x m) and B8 (kp x n) signed 8-bit, K-major (column-major with K contiguous, leading dimensions lda8 /
+// ldb8 in elements = bytes, multiples of 16), kp a multiple of 128.  The int32 accumulation is exact as long as
+// kp * 2^12 < 2^31 (|slice| <= 64): checked by the caller.
+int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* A8, int64_t lda8, const int8_t* B8,
+                   int64_t ldb8, double scale, const double* row_scale, const double* col_scale, double beta,
+                   double* C, int64_t ldc) {
+  GemmState* st = state_of(ctx);
+  if (!st->encode) return NB_ERR_UNSUPPORTED;
+  if (kp % 128 || (lda8 & 15) || (ldb8 & 15) || (((uintptr_t)A8 | (uintptr_t)B8) & 15)) return NB_ERR_UNSUPPORTED;
+  int BN = 256;
+  if (((m + BM - 1) / BM) * ((n + 255) / 256) < ctx->num_sms && n > 128) BN = 128;
+  if (n <= 128) BN = 128;
+  bool use_pair = ((m + 255) / 256) * ((n + 255) / 256) >= ctx->num_sms / 2;
+  if (const char* e = getenv("NB_GEMM_2CTA")) use_pair = atoi(e) != 0;
+  if (use_pair) BN = 256;
+  CUtensorMap maps[4];
+  bool ok = make_map(st, &maps[0], A8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kp, m, lda8, 128, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            make_map(st, &maps[2], B8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, kp, n, ldb8, 128, use_pair ? 128u : (uint32_t)BN,
+                     CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!ok) return NB_ERR_UNSUPPORTED;
+  maps[1] = maps[0];
+  maps[3] = maps[2];
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = m; g.N = n; g.K = kp;
+  g.a_mn = 0; g.b_mn = 0;
+  g.alpha = 1.f; g.beta = 0.f;
+  g.C = nullptr; g.ldc = ldc;
+  g.tiles_m = (int32_t)((m + (use_pair ? 256 : BM) - 1) / (use_pair ? 256 : BM));
+  g.tiles_n = (int32_t)((n + BN - 1) / BN);
+  g.tile_counter = st->tile_counter;
+  g.k_begin = 0; g.k_end = kp;
+  g.kchunk_kb = (int32_t)(kp / 128);  // one exact accumulation, no folds
+  g.serpentine = 1;
+  const int64_t panel = (int64_t)BM * kp;
+  int64_t gm = (70ll << 20) / (panel > 0 ? panel : 1);
+  g.group_m = (int32_t)(gm < 1 ? 1 : gm > 32 ? 32 : gm);
+  g.C64 = C; g.row_scale = row_scale; g.col_scale = col_scale; g.scale64 = scale; g.beta64 = beta;
+  if (use_pair) return launch_pair<KIND_I8>(ctx, maps, g);
+  return BN == 256 ? launch<256, KIND_I8>(ctx, maps, g) : launch<128, KIND_I8>(ctx, maps, g);
 }

@@ -1,0 +1,169 @@
+// Float64 products on the 5th-generation tensor cores by an Ozaki split.
+//
+// Every reference example is Float64 (rtol 1e-10), tcgen05 has no f64 kind, and the DMMA path (gemm_f64.cu) tops
+// out at ~28 TFLOP/s.  Large products C = alpha*op(A)*op(B) + beta*C are therefore computed from EXACT integer
+// products (replaces OpenBLAS dgemm behind ChainRules' rrule(*), chainrules.jl:179-191, and BLAS.gemm adjoints,
+// blas.jl:224-228):
+//   1. every row i of op(A) and column j of op(B) is scaled by a power of two 2^-e so that |x| < 1/2
+//      (k_absmax_* -> row_scale / col_scale = 2^e);
+//   2. the scaled values are cut into S = 6 signed 7-bit slices  x = sum_p q_p 2^(-7(p+1)),  |q_p| <= 64
+//      (k_slice: q = rint(128 x), x <- 128 x - q, exact in Float64); the slices of one operand are stored K-major
+//      and concatenated along K — A in order 0..S-1, B in REVERSE order — each padded to a multiple of 128;
+//   3. level l = p + q of  sum_{p+q<S} A_p B_q 2^(-7(p+q+2))  is then ONE kind::i8 GEMM over K' = (l+1)*Kp
+//      (A slices 0..l against B slices l..0, which are contiguous in that layout), accumulated exactly in int32 TMEM
+//      (K' * 2^12 < 2^31), and its epilogue adds  alpha * 2^(-7(l+2)) * row_scale * col_scale * acc  into the Float64 C.
+// Dropped: the levels p + q >= S (relative 2^-43 of the row/column maxima) and the slice residual (2^-43): norm-wise
+// error ~1e-13, elementwise error relative to max|row| * max|col|, like any scaled fixed-point scheme.
+// 21 int8 passes at twice the bf16 rate = 10.5 bf16 passes per product.
+#include "common.cuh"
+
+int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* A8, int64_t lda8, const int8_t* B8,
+                   int64_t ldb8, double scale, const double* row_scale, const double* col_scale, double beta,
+                   double* C, int64_t ldc);
+
+namespace {
+
+constexpr int S = 6;  // slices per operand
+
+// scale[i] = 2^e with |x| * 2^-e < 1/2 for every element of line i of op(X) (MN index i, reduced over K)
+//   contiguous-K form  (element (i, kk) at X[kk + i*ld]): one warp per line
+__global__ void __launch_bounds__(256) k_absmax_kcontig(const double* __restrict__ X, int64_t ld, int64_t mn, int64_t k,
+                                                        double* __restrict__ scale) {
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (i >= mn) return;
+  double mx = 0.0;
+  for (int64_t kk = lane; kk < k; kk += 32) mx = fmax(mx, fabs(X[kk + i * ld]));
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
+  if (lane == 0) scale[i] = (mx > 0.0 && isfinite(mx)) ? ldexp(1.0, ilogb(mx) + 2) : 1.0;
+}
+//   contiguous-MN form (element (i, kk) at X[i + kk*ld]): CTAs of 32 lines x 8 k-lanes over a k range; the partial
+//   maxima meet in scale[] through atomicMax on the bit pattern (non-negative doubles order like integers), then
+//   k_absmax_finish turns the maximum into the power of two
+__global__ void __launch_bounds__(256) k_absmax_mncontig(const double* __restrict__ X, int64_t ld, int64_t mn, int64_t k,
+                                                         int64_t k_per_cta, double* __restrict__ scale) {
+  __shared__ double red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t i = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t kb = (int64_t)blockIdx.y * k_per_cta, ke = min(k, kb + k_per_cta);
+  double mx = 0.0;
+  if (i < mn)
+    for (int64_t kk = kb + ty; kk < ke; kk += 8) mx = fmax(mx, fabs(X[i + kk * ld]));
+  red[ty][tx] = mx;
+  __syncthreads();
+  if (ty == 0 && i < mn) {
+#pragma unroll
+    for (int y = 1; y < 8; ++y) mx = fmax(mx, red[y][tx]);
+    if (!(mx == mx)) mx = INFINITY;  // NaN -> poison
+    atomicMax(reinterpret_cast<unsigned long long*>(scale + i), (unsigned long long)__double_as_longlong(mx));
+  }
+}
+__global__ void __launch_bounds__(256) k_absmax_finish(int64_t mn, double* __restrict__ scale) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= mn) return;
+  const double mx = scale[i];
+  scale[i] = (mx > 0.0 && isfinite(mx)) ? ldexp(1.0, ilogb(mx) + 2) : 1.0;
+}
+
+// out[(off_p + kk) + i*ldo] = slice p of X(i, kk) / scale[i], p = 0..S-1, off_p = (reverse ? S-1-p : p) * kp;
+// kk in [k, kp) is zero padding.  A 32 x 32 shared-memory tile turns the MN-contiguous form around so that both the
+// Float64 reads and the int8 writes are coalesced.
+template <bool MN_CONTIG>
+__global__ void __launch_bounds__(256) k_slice(const double* __restrict__ X, int64_t ld, int64_t mn, int64_t k, int64_t kp,
+                                               const double* __restrict__ scale, int8_t* __restrict__ out, int64_t ldo,
+                                               int reverse) {
+  __shared__ double tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+  const int64_t k0 = (int64_t)blockIdx.x * 32, i0 = (int64_t)blockIdx.y * 32;
+  // load a 32 (k) x 32 (mn) tile: tile[kk][i]
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    if (MN_CONTIG) {  // X[i + kk*ld]: threads along i
+      const int64_t kk = k0 + r, i = i0 + tx;
+      tile[r][tx] = (kk < k && i < mn) ? X[i + kk * ld] : 0.0;
+    } else {          // X[kk + i*ld]: threads along kk
+      const int64_t kk = k0 + tx, i = i0 + r;
+      tile[tx][r] = (kk < k && i < mn) ? X[kk + i * ld] : 0.0;
+    }
+  }
+  __syncthreads();
+  // write: threads along kk (the contiguous direction of the output)
+#pragma unroll
+  for (int r = ty; r < 32; r += 8) {
+    const int64_t kk = k0 + tx, i = i0 + r;
+    if (kk >= kp || i >= mn) continue;
+    double x = tile[tx][r] / scale[i];  // power-of-two divide: exact
+    int8_t* o = out + kk + i * ldo;
+#pragma unroll
+    for (int p = 0; p < S; ++p) {
+      const double t = x * 128.0;
+      const double q = rint(t);
+      o[(int64_t)(reverse ? S - 1 - p : p) * kp] = (int8_t)(int)q;
+      x = t - q;
+    }
+  }
+}
+
+}  // namespace
+
+// Returns NB_ERR_UNSUPPORTED (nothing launched) when the product is not worth / not fit for the split path; the
+// caller (nb_gemm) then uses DMMA.
+int32_t nb_gemm_ozaki(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
+                      int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
+  if (m < 128 || n < 128 || k < 256) return NB_ERR_UNSUPPORTED;
+  if ((double)m * (double)n * (double)k < 6.0e10) return NB_ERR_UNSUPPORTED;  // small products: DMMA wins
+  const int64_t kp = (k + 127) / 128 * 128;
+  if ((double)S * (double)kp * 4096.0 >= 2147483648.0) return NB_ERR_UNSUPPORTED;  // int32 accumulator must stay exact
+  const int64_t ld8 = (int64_t)S * kp;
+  void *sa = nullptr, *sb = nullptr, *a8 = nullptr, *b8 = nullptr;
+  int32_t rc = nb_pool_alloc(ctx, (size_t)m * sizeof(double), &sa);
+  if (rc == NB_OK) rc = nb_pool_alloc(ctx, (size_t)n * sizeof(double), &sb);
+  if (rc == NB_OK) rc = nb_pool_alloc(ctx, (size_t)m * ld8, &a8);
+  if (rc == NB_OK) rc = nb_pool_alloc(ctx, (size_t)n * ld8, &b8);
+  auto cleanup = [&]() {
+    if (sa) nb_pool_release(ctx, sa);
+    if (sb) nb_pool_release(ctx, sb);
+    if (a8) nb_pool_release(ctx, a8);
+    if (b8) nb_pool_release(ctx, b8);
+  };
+  if (rc != NB_OK) { cleanup(); return rc; }
+  cudaStream_t st = ctx->stream;
+  // op(A) line i over kk: not transposed -> A[i + kk*lda] (MN-contiguous); transposed -> A[kk + i*lda]
+  // op(B) line j over kk: not transposed -> B[kk + j*ldb] (K-contiguous);  transposed -> B[j + kk*ldb]
+  const bool a_mnc = !tA, b_mnc = tB;
+  auto absmax = [&](bool mnc, const double* X, int64_t ld, int64_t mn, double* sc) {
+    if (mnc) {
+      cudaMemsetAsync(sc, 0, (size_t)mn * sizeof(double), st);
+      const int64_t lines = (mn + 31) / 32;
+      int64_t ksplit = ((int64_t)ctx->num_sms * 8 + lines - 1) / lines;
+      if (ksplit > (k + 255) / 256) ksplit = (k + 255) / 256;
+      if (ksplit < 1) ksplit = 1;
+      const int64_t kpc = (k + ksplit - 1) / ksplit;
+      k_absmax_mncontig<<<dim3((unsigned)lines, (unsigned)((k + kpc - 1) / kpc)), 256, 0, st>>>(X, ld, mn, k, kpc, sc);
+      k_absmax_finish<<<(unsigned)((mn + 255) / 256), 256, 0, st>>>(mn, sc);
+      ctx->stats.kernel_launches += 2;
+    } else {
+      k_absmax_kcontig<<<(unsigned)((mn * 32 + 255) / 256), 256, 0, st>>>(X, ld, mn, k, sc);
+      ctx->stats.kernel_launches++;
+    }
+  };
+  auto slice = [&](bool mnc, const double* X, int64_t ld, int64_t mn, const double* sc, int8_t* out, int rev) {
+    const dim3 grid((unsigned)(kp / 32), (unsigned)((mn + 31) / 32));
+    if (mnc) k_slice<true><<<grid, 256, 0, st>>>(X, ld, mn, k, kp, sc, out, ld8, rev);
+    else k_slice<false><<<grid, 256, 0, st>>>(X, ld, mn, k, kp, sc, out, ld8, rev);
+    ctx->stats.kernel_launches++;
+  };
+  absmax(a_mnc, A, lda, m, (double*)sa);
+  absmax(b_mnc, B, ldb, n, (double*)sb);
+  slice(a_mnc, A, lda, m, (const double*)sa, (int8_t*)a8, 0);
+  slice(b_mnc, B, ldb, n, (const double*)sb, (int8_t*)b8, 1);
+  if (cudaGetLastError() != cudaSuccess) { cleanup(); return nb_fail(ctx, NB_ERR_CUDA, "nb_gemm_ozaki: split kernels failed to launch"); }
+  for (int l = 0; l < S && rc == NB_OK; ++l) {
+    // A slices 0..l (columns [0, (l+1)kp) of the K axis) against B slices l..0 (rows [(S-1-l)kp, S*kp))
+    rc = nb_gemm_i8(ctx, m, n, (int64_t)(l + 1) * kp, (const int8_t*)a8, ld8, (const int8_t*)b8 + (int64_t)(S - 1 - l) * kp,
+                    ld8, alpha * ldexp(1.0, -7 * (l + 2)), (const double*)sa, (const double*)sb, l == 0 ? beta : 1.0, C, ldc);
+  }
+  cleanup();
+  return rc;
+}

@@ -1195,3 +1195,33 @@ def test_fused_dense_layers_inside_graph_capture(nb, orc, ctx):
     assert st == 4
     z = nb.matmul(nb.Leaf(nb.Tape(), np.ones((256, 256))), B64)
     assert z.val.pending is None
+
+
+def test_gemm_f64_ozaki_split(nb, ctx):
+    """Large Float64 products run as exact int8 slice products on the tensor cores (csrc/ozaki.cu): all four
+    transposes, ragged extents, alpha / beta, against NumPy Float64 at the Float64 bar (rtol 1e-10, norm-wise and
+    element-wise relative to the largest entry) and against the DMMA path (NB_MATH_FP32 = no tensor-core split)."""
+    from nabla_jl_b200 import kernels as K
+    rng = np.random.default_rng(123)
+    m, n, k = 4100, 4200, 4000   # m*n*k >= 6e10: the split path
+    old = ctx.math_mode
+    try:
+        for tA in "NT":
+            for tB in "NT":
+                A = rng.standard_normal((k, m) if tA == "T" else (m, k)) * np.exp(rng.uniform(-3, 3, (1, m) if tA == "T" else (m, 1)))
+                B = rng.standard_normal((n, k) if tB == "T" else (k, n))
+                C0 = rng.standard_normal((m, n))
+                ref = 0.7 * ((A.T if tA == "T" else A) @ (B.T if tB == "T" else B)) - 0.5 * C0
+                Ad, Bd = ctx.asarray(A), ctx.asarray(B)
+                out = {}
+                for mode in (nb.MATH_DEFAULT, nb.MATH_FP32):
+                    ctx.math_mode = mode
+                    n0 = ctx.stats()["kernel_launches"]
+                    Cd = ctx.asarray(C0)
+                    K.gemm(tA, tB, 0.7, Ad, Bd, -0.5, Cd, m, n, k)
+                    out[mode] = (Cd.numpy(), ctx.stats()["kernel_launches"] - n0)
+                close(out[nb.MATH_DEFAULT][0], ref)
+                close(out[nb.MATH_FP32][0], ref)
+                assert out[nb.MATH_DEFAULT][1] >= 10 and out[nb.MATH_FP32][1] <= 3   # split path: scales, slices, 6 levels
+    finally:
+        ctx.math_mode = old
