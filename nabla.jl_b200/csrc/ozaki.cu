@@ -112,7 +112,8 @@ __global__ void __launch_bounds__(256) k_slice(const double* __restrict__ X, int
 int32_t nb_gemm_ozaki(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                       int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc) {
   if (m < 128 || n < 128 || k < 256) return NB_ERR_UNSUPPORTED;
-  if ((double)m * (double)n * (double)k < 6.0e10) return NB_ERR_UNSUPPORTED;  // small products: DMMA wins
+  static const double min_work = getenv("NB_OZAKI_MIN_MNK") ? atof(getenv("NB_OZAKI_MIN_MNK")) : 3.0e9;  // crossover measured at ~3e9 (tools/ozaki_crossover.py)
+  if ((double)m * (double)n * (double)k < min_work) return NB_ERR_UNSUPPORTED;  // small products: DMMA wins
   const int64_t kp = (k + 127) / 128 * 128;
   if ((double)S * (double)kp * 4096.0 >= 2147483648.0) return NB_ERR_UNSUPPORTED;  // int32 accumulator must stay exact
   const int64_t ld8 = (int64_t)S * kp;
