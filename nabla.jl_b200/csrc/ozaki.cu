@@ -12,8 +12,9 @@
 //   3. level l = p + q of  sum_{p+q<S} A_p B_q 2^(-7(p+q+2))  is then ONE kind::i8 GEMM over K' = (l+1)*Kp
 //      (A slices 0..l against B slices l..0, which are contiguous in that layout), accumulated exactly in int32 TMEM
 //      (K' * 2^12 < 2^31), and its epilogue adds  alpha * 2^(-7(l+2)) * row_scale * col_scale * acc  into the Float64 C.
-// Dropped: the levels p + q >= S (relative 2^-43 of the row/column maxima) and the slice residual (2^-43): norm-wise
-// error ~1e-13, elementwise error relative to max|row| * max|col|, like any scaled fixed-point scheme.
+// Dropped: the levels p + q >= S (~2^-39 of max|row| * max|col| per product term) and the slice residual (2^-43):
+// measured norm-wise error 5e-12, elementwise error relative to max|row| * max|col|, like any scaled fixed-point
+// scheme.  A row / column holding a NaN or Inf makes its row / column of C NaN.
 // 21 int8 passes at twice the bf16 rate = 10.5 bf16 passes per product.
 #include "common.cuh"
 
@@ -33,10 +34,14 @@ __global__ void __launch_bounds__(256) k_absmax_kcontig(const double* __restrict
   const int lane = threadIdx.x & 31;
   if (i >= mn) return;
   double mx = 0.0;
-  for (int64_t kk = lane; kk < k; kk += 32) mx = fmax(mx, fabs(X[kk + i * ld]));
+  for (int64_t kk = lane; kk < k; kk += 32) {
+    const double v = fabs(X[kk + i * ld]);
+    mx = (v == v) ? fmax(mx, v) : INFINITY;  // fmax drops NaNs: poison instead
+  }
 #pragma unroll
   for (int s = 16; s > 0; s >>= 1) mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, s));
-  if (lane == 0) scale[i] = (mx > 0.0 && isfinite(mx)) ? ldexp(1.0, ilogb(mx) + 2) : 1.0;
+  // (a line with a NaN or Inf gets a NaN scale: its row / column of C becomes NaN instead of finite garbage)
+  if (lane == 0) scale[i] = mx == 0.0 ? 1.0 : isfinite(mx) ? ldexp(1.0, ilogb(mx) + 2) : nan("");
 }
 //   contiguous-MN form (element (i, kk) at X[i + kk*ld]): CTAs of 32 lines x 8 k-lanes over a k range; the partial
 //   maxima meet in scale[] through atomicMax on the bit pattern (non-negative doubles order like integers), then
@@ -49,7 +54,10 @@ __global__ void __launch_bounds__(256) k_absmax_mncontig(const double* __restric
   const int64_t kb = (int64_t)blockIdx.y * k_per_cta, ke = min(k, kb + k_per_cta);
   double mx = 0.0;
   if (i < mn)
-    for (int64_t kk = kb + ty; kk < ke; kk += 8) mx = fmax(mx, fabs(X[i + kk * ld]));
+    for (int64_t kk = kb + ty; kk < ke; kk += 8) {
+      const double v = fabs(X[i + kk * ld]);
+      mx = (v == v) ? fmax(mx, v) : INFINITY;
+    }
   red[ty][tx] = mx;
   __syncthreads();
   if (ty == 0 && i < mn) {
@@ -63,7 +71,7 @@ __global__ void __launch_bounds__(256) k_absmax_finish(int64_t mn, double* __res
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= mn) return;
   const double mx = scale[i];
-  scale[i] = (mx > 0.0 && isfinite(mx)) ? ldexp(1.0, ilogb(mx) + 2) : 1.0;
+  scale[i] = mx == 0.0 ? 1.0 : isfinite(mx) ? ldexp(1.0, ilogb(mx) + 2) : nan("");
 }
 
 // out[(off_p + kk) + i*ldo] = slice p of X(i, kk) / scale[i], p = 0..S-1, off_p = (reverse ? S-1-p : p) * kp;

@@ -1223,5 +1223,16 @@ def test_gemm_f64_ozaki_split(nb, ctx):
                 close(out[nb.MATH_DEFAULT][0], ref)
                 close(out[nb.MATH_FP32][0], ref)
                 assert out[nb.MATH_DEFAULT][1] >= 10 and out[nb.MATH_FP32][1] <= 3   # split path: scales, slices, 6 levels
+        # non-finite input: the affected row of C is NaN (never finite garbage), the rest is untouched
+        A = rng.standard_normal((m, k))
+        B = rng.standard_normal((k, n))
+        A[7, 11] = np.inf
+        A[300, 5] = np.nan
+        ctx.math_mode = nb.MATH_DEFAULT
+        Cd = ctx.zeros((m, n), np.float64)
+        K.gemm("N", "N", 1.0, ctx.asarray(A), ctx.asarray(B), 0.0, Cd, m, n, k)
+        got = Cd.numpy()
+        assert np.all(np.isnan(got[7])) and np.all(np.isnan(got[300]))
+        assert np.all(np.isfinite(np.delete(got, [7, 300], axis=0)))
     finally:
         ctx.math_mode = old
