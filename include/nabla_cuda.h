@@ -48,12 +48,14 @@ typedef enum nb_status {
 
 typedef enum nb_dtype { NB_F32 = 0, NB_F64 = 1 } nb_dtype;
 
-/* GEMM arithmetic for Float32 operands (Float64 always runs exact FP64 FMA on the DMMA path). */
+/* GEMM arithmetic.  Float32: see the modes.  Float64: exact FP64 FMA on the DMMA path for small products, exact
+ * int8 slice products on tcgen05 (Ozaki split, ~5e-12 relative error norm-wise) for m*n*k >= 3e9; NB_MATH_FP32 keeps
+ * every Float64 product on DMMA. */
 typedef enum nb_math_mode {
-  NB_MATH_DEFAULT = 0,  /* f32: NB_MATH_BF16X3; f64: DMMA */
+  NB_MATH_DEFAULT = 0,  /* f32: NB_MATH_BF16X3; f64: DMMA / Ozaki split by size */
   NB_MATH_TF32 = 1,     /* f32: single-pass kind::tf32 on tcgen05 (~8e-4 relative error) */
   NB_MATH_3XTF32 = 2,   /* f32: x = hi + lo in tf32, lo*hi + hi*lo + hi*hi on tcgen05 (~4e-7) */
-  NB_MATH_FP32 = 3,     /* f32: FP32 FMA on CUDA cores (no tensor cores) */
+  NB_MATH_FP32 = 3,     /* f32: FP32 FMA on CUDA cores (no tensor cores); f64: DMMA only */
   NB_MATH_BF16X3 = 4    /* f32: x = hi + lo in bfloat16, three kind::f16 passes on tcgen05 (~1e-5): meets
                            rtol 1e-4 at half the tensor work of 3xTF32 */
 } nb_math_mode;
