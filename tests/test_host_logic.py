@@ -125,3 +125,49 @@ def test_pullback_reads():
     assert fusion.pullback_reads(sin, [0]) == ({0}, False)
     comp = nb.compile_scalar(lambda a, b: nb.tanh(a) * b, 2)
     assert fusion.pullback_reads(comp, [0]) is None
+
+
+def test_ozaki_split_scheme_in_numpy():
+    """The Float64-on-int8 scheme of csrc/ozaki.cu restated in NumPy (no GPU): power-of-two row/column scales,
+    six signed 7-bit slices by q = rint(128 x), x <- 128 x - q, slices concatenated along K (A in order, B
+    reversed) so that level l is ONE integer product over K' = (l+1) K, exact in int32, combined with
+    2^(-7(l+2)).  Pins the slice ranges, the exactness bound and the accuracy the device path is tested against."""
+    import numpy as np
+    rng = np.random.default_rng(5)
+    S, m, n, k = 6, 37, 29, 200
+    A = rng.standard_normal((m, k)) * np.exp(rng.uniform(-4, 4, (m, 1)))
+    B = rng.standard_normal((k, n)) * np.exp(rng.uniform(-4, 4, (1, n)))
+
+    def scales(X, axis):
+        mx = np.max(np.abs(X), axis=axis, keepdims=True)
+        return np.ldexp(1.0, np.frexp(mx)[1] + 1)      # 2^(ilogb(mx) + 2): |x| / scale < 1/2
+
+    def slices(X):
+        out = []
+        for _ in range(S):
+            t = X * 128.0
+            q = np.rint(t)
+            out.append(q.astype(np.int64))
+            X = t - q                                    # exact
+        return out
+
+    ra, cb = scales(A, 1), scales(B, 0)
+    assert np.all(np.abs(A / ra) < 0.5) and np.all(np.abs(B / cb) < 0.5)
+    sa, sb = slices(A / ra), slices(B / cb)
+    assert all(np.abs(q).max() <= 64 for q in sa + sb)
+    # the slices reconstruct the scaled operand to 2^-43
+    rec = sum(q * 2.0 ** (-7 * (p + 1)) for p, q in enumerate(sa))
+    assert np.max(np.abs(rec - A / ra)) <= 2.0 ** -43
+    Acat = np.concatenate(sa, axis=1)                   # m x (S k): slices 0 .. S-1
+    Bcat = np.concatenate(sb[::-1], axis=0)             # (S k) x n: slices S-1 .. 0
+    C = np.zeros((m, n))
+    for l in range(S):
+        acc = Acat[:, :(l + 1) * k] @ Bcat[(S - 1 - l) * k:, :]        # = sum_{p+q=l} A_p B_q, one product
+        direct = sum(sa[p] @ sb[l - p] for p in range(l + 1))
+        assert np.array_equal(acc, direct)
+        assert np.abs(acc).max() < 2 ** 31 and (l + 1) * k * 4096 < 2 ** 31     # exact in int32
+        C += np.ldexp(acc.astype(np.float64), -7 * (l + 2))
+    C *= ra * cb
+    ref = A @ B
+    assert np.linalg.norm(C - ref) / np.linalg.norm(ref) < 2e-11
+    assert np.max(np.abs(C - ref) / (np.abs(A).max(1, keepdims=True) * np.abs(B).max(0, keepdims=True) * np.sqrt(k))) < 1e-10
