@@ -56,19 +56,22 @@ constexpr int REGS_WG0 = 80, REGS_EPI = 208;  // 128*80 + 256*208 <= 384*168
 // Operand kinds.  Every staged row is 128 bytes (one swizzle row), so tile byte sizes are kind-independent.
 // KIND_I8: signed 8-bit operands, exact int32 accumulation (kind::i8) — the slice products of the Float64 Ozaki
 // split (ozaki.cu); K-major operands only, one pass, no K chunking (the int32 accumulator is exact).
-enum { KIND_TF32 = 0, KIND_3XTF32 = 1, KIND_BF16X3 = 2, KIND_I8 = 3 };
+// KIND_I8ALL: every level of the Ozaki split in ONE launch (chunk table in GemmArgs, Float64 running sum in the
+// epilogue registers): mid-size Float64 products, where six launches and six read-modify-writes of C dominate.
+enum { KIND_TF32 = 0, KIND_3XTF32 = 1, KIND_BF16X3 = 2, KIND_I8 = 3, KIND_I8ALL = 4 };
+__host__ __device__ constexpr bool kind_is_i8(int k) { return k == KIND_I8 || k == KIND_I8ALL; }
 template <int KIND>
 struct KindT {
-  static constexpr int ESIZE = KIND == KIND_I8 ? 1 : KIND == KIND_BF16X3 ? 2 : 4;  // bytes per staged element
+  static constexpr int ESIZE = kind_is_i8(KIND) ? 1 : KIND == KIND_BF16X3 ? 2 : 4;  // bytes per staged element
   static constexpr int BK = 128 / ESIZE;                          // elements of K per stage (32 / 64)
   static constexpr int UMMA_K = 32 / ESIZE;                       // K of one tcgen05.mma (8 / 16)
   static constexpr int MN_CHUNK = 128 / ESIZE;                    // MN-elements per 128-byte row (32 / 64)
   static constexpr uint32_t CHUNK_BYTES = BK * 128;               // one MN-major chunk: MN_CHUNK x BK rows
-  static constexpr int NSPLIT = (KIND == KIND_TF32 || KIND == KIND_I8) ? 1 : 2;  // staged copies per operand (hi, lo)
-  static constexpr int NPASS = (KIND == KIND_TF32 || KIND == KIND_I8) ? 1 : 3;
+  static constexpr int NSPLIT = (KIND == KIND_TF32 || kind_is_i8(KIND)) ? 1 : 2;  // staged copies per operand (hi, lo)
+  static constexpr int NPASS = (KIND == KIND_TF32 || kind_is_i8(KIND)) ? 1 : 3;
   // instruction-descriptor a/b format: F32F16 family 1 = bf16, 2 = tf32; S8 family 1 = signed 8 bit
-  static constexpr uint32_t FMT = (KIND == KIND_BF16X3 || KIND == KIND_I8) ? 1u : 2u;
-  static constexpr uint32_t CFMT = KIND == KIND_I8 ? 2u : 1u;     // accumulator: 1 = f32, 2 = s32
+  static constexpr uint32_t FMT = (KIND == KIND_BF16X3 || kind_is_i8(KIND)) ? 1u : 2u;
+  static constexpr uint32_t CFMT = kind_is_i8(KIND) ? 2u : 1u;     // accumulator: 1 = f32, 2 = s32
   // MN-major smem layout (see make_desc)
   static constexpr uint64_t MN_TYPE = KIND == KIND_BF16X3 ? 2 : 1;
   static constexpr uint64_t MN_SBO = KIND == KIND_BF16X3 ? 1024 : 512;
@@ -118,6 +121,11 @@ struct GemmArgs {
   const double* row_scale;
   const double* col_scale;
   double scale64, beta64;
+  // KIND_I8ALL: chunk c = one level of the split: tab_nkb[c] K blocks, A from K element tab_ka[c], B from tab_kb[c],
+  // its int32 accumulator weighted by tab_scale[c] in the Float64 running sum
+  int32_t nchunk_tab;
+  int32_t tab_nkb[8], tab_ka[8], tab_kb[8];
+  double tab_scale[8];
 };
 
 constexpr int SCHED_SLOTS = 4;
@@ -205,7 +213,7 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 template <int KIND>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
-  if (KIND == KIND_I8) {
+  if (kind_is_i8(KIND)) {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
@@ -453,7 +461,7 @@ struct EpiAcc {
 
   // C[gm, n0 .. n0+NCOL) = epilogue(alpha * r + beta * C); `part` indexes this thread's row-sum partial
   __device__ __forceinline__ void store(const GemmArgs& g, int64_t gm, int64_t n0, int part, int lane) {
-    if constexpr (KIND == KIND_I8) { store_i8(g, gm, n0); return; }
+    if constexpr (kind_is_i8(KIND)) { store_i8(g, gm, n0); return; }
     if (g.vec_store) { store_vec(g, gm - lane, n0, part, lane); return; }
     using SplitT = typename std::conditional<KIND == KIND_BF16X3, __nv_bfloat16, float>::type;
     if (gm >= g.M) return;
@@ -507,6 +515,47 @@ struct EpiAcc {
       }
     }
     if (ek != EPI_NONE && g.epi.rowsum_partial) g.epi.rowsum_partial[(int64_t)part * g.M + gm] = rsum;
+  }
+};
+
+// KIND_I8ALL: Float64 running sum over the levels of the Ozaki split for this thread's row x NCOL columns
+template <int NCOL>
+struct EpiAcc64 {
+  double r[NCOL];
+  __device__ __forceinline__ void fold(uint32_t taddr, double w, bool first) {
+#pragma unroll
+    for (int c = 0; c < NCOL / 32; ++c) {
+      uint32_t v[32];
+      tmem_ld32(taddr + (uint32_t)(c * 32), v);
+      if (first) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[c * 32 + j] = w * (double)(int)v[j];
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) r[c * 32 + j] += w * (double)(int)v[j];
+      }
+    }
+  }
+  __device__ __forceinline__ void store(const GemmArgs& g, int64_t gm, int64_t n0) {
+    if (gm >= g.M) return;
+    const double rs = g.scale64 * g.row_scale[gm];
+    const double beta = g.beta64;
+#pragma unroll
+    for (int c = 0; c < NCOL / 8; ++c) {
+      const int64_t nb = n0 + c * 8;
+      if (nb >= g.N) break;
+      double* cp = g.C64 + gm + nb * g.ldc;
+      double old[8], cs[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const bool ok = nb + j < g.N;
+        cs[j] = ok ? g.col_scale[nb + j] : 0.0;
+        old[j] = (ok && beta != 0.0) ? cp[(int64_t)j * g.ldc] : 0.0;
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (nb + j < g.N) cp[(int64_t)j * g.ldc] = beta * old[j] + rs * cs[j] * r[c * 8 + j];
+    }
   }
 };
 
@@ -593,6 +642,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         int tm, tn;
         tile_coords(t_cur, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
         const int m0 = tm * BM, n0 = tn * BN;
+        if constexpr (KIND == KIND_I8ALL) {
+          for (int c = 0; c < g.nchunk_tab; ++c)
+            for (int kb = 0; kb < g.tab_nkb[c]; ++kb) {
+              mbar_wait(&empty[s], ph ^ 1);
+              mbar_expect_tx(&full[s], C_::STAGE_BYTES);
+              uint8_t* st = smem + s * C_::STAGE_BYTES;
+              tma_load_2d(st, &mA0, &full[s], g.tab_ka[c] + kb * BK, m0, 0);
+              tma_load_2d(st + C_::A_BYTES, &mB0, &full[s], g.tab_kb[c] + kb * BK, n0, 0);
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+          continue;
+        }
         for (int kb = 0; kb < nkb; ++kb) {  // chunk boundaries do not concern the producer
           mbar_wait(&empty[s], ph ^ 1);
           mbar_expect_tx(&full[s], C_::STAGE_BYTES);
@@ -636,6 +697,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         mbar_arrive(&sempty[q]);
         if (++q == SCHED_SLOTS) { q = 0; qph ^= 1; }
         if (t >= ntiles) break;
+        if constexpr (KIND == KIND_I8ALL) {
+          for (int c = 0; c < g.nchunk_tab; ++c) {
+            mbar_wait(&tempty[a], aph ^ 1);
+            tc_fence_after();
+            const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
+            for (int kb = 0; kb < g.tab_nkb[c]; ++kb) {
+              mbar_wait(&full[s], ph);
+              tc_fence_after();
+              const uint32_t st = smem_u32(smem + s * C_::STAGE_BYTES);
+#pragma unroll
+              for (int kk = 0; kk < BK / KT::UMMA_K; ++kk)
+                tc_mma<KIND>(d_tmem, make_desc<KIND>(st + kk * 32u, false),
+                             make_desc<KIND>(st + C_::A_BYTES + kk * 32u, false), idesc, (uint32_t)((kb | kk) != 0));
+              tc_commit(&empty[s]);
+              if (++s == STAGES) { s = 0; ph ^= 1; }
+            }
+            tc_commit(&tfull[a]);
+            if (++a == 2) { a = 0; aph ^= 1; }
+          }
+          continue;
+        }
         for (int kb0 = 0; kb0 < nkb; kb0 += g.kchunk_kb) {
           const int kb1 = min(nkb, kb0 + g.kchunk_kb);
           mbar_wait(&tempty[a], aph ^ 1);
@@ -684,6 +766,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
       if (t >= ntiles) break;
       int tm, tn;
       tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
+      if constexpr (KIND == KIND_I8ALL) {
+        EpiAcc64<BN / 2> a64;
+        for (int c = 0; c < g.nchunk_tab; ++c) {
+          mbar_wait(&tfull[a], aph);
+          tc_fence_after();
+          a64.fold(tmem_base + (uint32_t)(a * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16), g.tab_scale[c], c == 0);
+          tc_fence_before();
+          mbar_arrive(&tempty[a]);
+          if (++a == 2) { a = 0; aph ^= 1; }
+        }
+        a64.store(g, (int64_t)tm * BM + q * 32 + lane, (int64_t)tn * BN + half * (BN / 2));
+        continue;
+      }
       for (int kb0 = 0; kb0 < nkb; kb0 += g.kchunk_kb) {
         mbar_wait(&tfull[a], aph);
         tc_fence_after();
@@ -1477,4 +1572,52 @@ int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* 
   g.C64 = C; g.row_scale = row_scale; g.col_scale = col_scale; g.scale64 = scale; g.beta64 = beta;
   if (use_pair) return launch_pair<KIND_I8>(ctx, maps, g);
   return BN == 256 ? launch<256, KIND_I8>(ctx, maps, g) : launch<128, KIND_I8>(ctx, maps, g);
+}
+
+// Every level of the Ozaki split in ONE launch (KIND_I8ALL): A8 (S*kp x m) and B8 (S*kp x n) as in nb_gemm_i8, levels
+// 0 .. S-1 (A slices 0..l against B slices l..0) plus, with extra_level, level S (A slices 1..S-1 against B slices
+// S-1..1: five more passes, error 2^-7 smaller).  C64 = beta*C64 + alpha * diag(row_scale) * (sum of levels) * diag(col_scale).
+int32_t nb_gemm_i8all(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, int32_t S, int32_t extra_level, const int8_t* A8,
+                      int64_t ld8, const int8_t* B8, double alpha, const double* row_scale, const double* col_scale,
+                      double beta, double* C, int64_t ldc) {
+  GemmState* st = state_of(ctx);
+  if (!st->encode) return NB_ERR_UNSUPPORTED;
+  if (kp % 128 || (ld8 & 15) || (((uintptr_t)A8 | (uintptr_t)B8) & 15) || S < 1 || S + (extra_level ? 1 : 0) > 8)
+    return NB_ERR_UNSUPPORTED;
+  constexpr int BNL = 128;  // Float64 running sums: 64 columns per epilogue thread
+  CUtensorMap maps[4];
+  bool ok = make_map(st, &maps[0], A8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)S * kp, m, ld8, 128, BM, CU_TENSOR_MAP_SWIZZLE_128B) &&
+            make_map(st, &maps[2], B8, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, (int64_t)S * kp, n, ld8, 128, BNL, CU_TENSOR_MAP_SWIZZLE_128B);
+  if (!ok) return NB_ERR_UNSUPPORTED;
+  maps[1] = maps[0];
+  maps[3] = maps[2];
+  GemmArgs g;
+  memset(&g, 0, sizeof(g));
+  g.M = m; g.N = n; g.K = kp;
+  g.alpha = 1.f;
+  g.ldc = ldc;
+  g.tiles_m = (int32_t)((m + BM - 1) / BM);
+  g.tiles_n = (int32_t)((n + BNL - 1) / BNL);
+  g.tile_counter = st->tile_counter;
+  g.k_begin = 0; g.k_end = kp;
+  g.kchunk_kb = 1;
+  g.group_m = 8;
+  g.C64 = C; g.row_scale = row_scale; g.col_scale = col_scale; g.scale64 = alpha; g.beta64 = beta;
+  const int32_t nkb0 = (int32_t)(kp / 128);
+  int c = 0;
+  for (int l = 0; l < S; ++l, ++c) {
+    g.tab_nkb[c] = (l + 1) * nkb0;
+    g.tab_ka[c] = 0;
+    g.tab_kb[c] = (int32_t)((S - 1 - l) * kp);
+    g.tab_scale[c] = ldexp(1.0, -7 * (l + 2));
+  }
+  if (extra_level && S > 1) {
+    g.tab_nkb[c] = (S - 1) * nkb0;
+    g.tab_ka[c] = (int32_t)kp;
+    g.tab_kb[c] = 0;
+    g.tab_scale[c] = ldexp(1.0, -7 * (S + 2));
+    ++c;
+  }
+  g.nchunk_tab = c;
+  return launch<BNL, KIND_I8ALL>(ctx, maps, g);
 }

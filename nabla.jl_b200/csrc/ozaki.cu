@@ -22,6 +22,10 @@ int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* 
                    int64_t ldb8, double scale, const double* row_scale, const double* col_scale, double beta,
                    double* C, int64_t ldc);
 
+int32_t nb_gemm_i8all(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, int32_t S, int32_t extra_level, const int8_t* A8,
+                      int64_t ld8, const int8_t* B8, double alpha, const double* row_scale, const double* col_scale,
+                      double beta, double* C, int64_t ldc);
+
 namespace {
 
 constexpr int S = 6;  // slices per operand
@@ -168,6 +172,16 @@ int32_t nb_gemm_ozaki(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64
   slice(a_mnc, A, lda, m, (const double*)sa, (int8_t*)a8, 0);
   slice(b_mnc, B, ldb, n, (const double*)sb, (int8_t*)b8, 1);
   if (cudaGetLastError() != cudaSuccess) { cleanup(); return nb_fail(ctx, NB_ERR_CUDA, "nb_gemm_ozaki: split kernels failed to launch"); }
+  // mid-size products: all levels (plus a seventh for 4e-14) in ONE launch with a Float64 running sum in the epilogue
+  // registers; large ones: one CTA-pair launch per level (higher int8 pipe utilisation, six passes over C)
+  static const double one_launch_below = getenv("NB_OZAKI_ONE_LAUNCH_MNK") ? atof(getenv("NB_OZAKI_ONE_LAUNCH_MNK")) : 2.0e10;
+  // (small K: the six read-modify-writes of C outweigh the pair kernel's better pipe utilisation at any m x n)
+  if (((double)m * (double)n * (double)k < one_launch_below || k <= 2048) && (double)S * (double)kp < 2147483648.0 / 4096.0) {
+    rc = nb_gemm_i8all(ctx, m, n, kp, S, 1, (const int8_t*)a8, ld8, (const int8_t*)b8, alpha, (const double*)sa,
+                       (const double*)sb, beta, C, ldc);
+    if (rc != NB_ERR_UNSUPPORTED) { cleanup(); return rc; }
+    rc = NB_OK;
+  }
   for (int l = 0; l < S && rc == NB_OK; ++l) {
     // A slices 0..l (columns [0, (l+1)kp) of the K axis) against B slices l..0 (rows [(S-1-l)kp, S*kp))
     rc = nb_gemm_i8(ctx, m, n, (int64_t)(l + 1) * kp, (const int8_t*)a8, ld8, (const int8_t*)b8 + (int64_t)(S - 1 - l) * kp,

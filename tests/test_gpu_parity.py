@@ -1223,6 +1223,20 @@ def test_gemm_f64_ozaki_split(nb, ctx):
                 close(out[nb.MATH_DEFAULT][0], ref)
                 close(out[nb.MATH_FP32][0], ref)
                 assert out[nb.MATH_DEFAULT][1] >= 10 and out[nb.MATH_FP32][1] <= 3   # split path: scales, slices, 6 levels
+        # mid-size products: every level in ONE launch (Float64 running sum in the epilogue), seven levels
+        for (mm, nn, kk) in ((1100, 1300, 2100), (700, 4096, 1100)):
+            for tA in "NT":
+                for tB in "NT":
+                    A = rng.standard_normal((kk, mm) if tA == "T" else (mm, kk))
+                    B = rng.standard_normal((nn, kk) if tB == "T" else (kk, nn))
+                    C0 = rng.standard_normal((mm, nn))
+                    ref = -1.3 * ((A.T if tA == "T" else A) @ (B.T if tB == "T" else B)) + C0
+                    ctx.math_mode = nb.MATH_DEFAULT
+                    Cd = ctx.asarray(C0)
+                    n0 = ctx.stats()["kernel_launches"]
+                    K.gemm(tA, tB, -1.3, ctx.asarray(A), ctx.asarray(B), 1.0, Cd, mm, nn, kk)
+                    assert 5 <= ctx.stats()["kernel_launches"] - n0 <= 7
+                    close(Cd.numpy(), ref, scale=0.1)   # 1e-11
         # non-finite input: the affected row of C is NaN (never finite garbage), the rest is untouched
         A = rng.standard_normal((m, k))
         B = rng.standard_normal((k, n))
