@@ -1250,3 +1250,12 @@ def test_gemm_f64_ozaki_split(nb, ctx):
         assert np.all(np.isfinite(np.delete(got, [7, 300], axis=0)))
     finally:
         ctx.math_mode = old
+
+
+def test_mlp_gradient_f64_on_the_split_path(nb, orc):
+    """A Float64 MLP whose hidden-layer products (2048^3 = 8.6e9) run on the Ozaki split: the whole gradient
+    against the oracle at the Float64 bar."""
+    y, g, yr, gr = _mlp_both(nb, orc, (2048, 2048, 2048, 10), 2048, np.float64, seed=7)
+    np.testing.assert_allclose(y, yr, rtol=1e-10)
+    for a, b in zip(g, gr):
+        close(a, b)
