@@ -453,12 +453,15 @@ def run_gpu(args):
         peak = peaks["bf16_sustained"] * ratio
         f64_peak_note = None
         if args.dtype == "f64":
-            # Large Float64 products run as 21 exact int8 slice products on the tensor cores (csrc/ozaki.cu): the
-            # bound is the kind::i8 pipe at twice the bf16 rate, i.e. 2 x bf16 / 21 in algorithmic Float64 FLOPs
-            # (MEASURED_PEAKS.json has no int8 or FP64 figure; DMMA, used for the small products, is ~36 TFLOP/s)
-            peak, ratio = 2.0 * peaks["bf16_sustained"] / 21.0, None
-            f64_peak_note = (f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s x 2 (kind::i8) / 21 "
-                             "int8 passes per Float64 product (Ozaki split, 6 slices); small products on DMMA")
+            # Large Float64 products run as S(S+1)/2 = 28 exact int8 slice products on the tensor cores
+            # (csrc/ozaki.cu, S = 7 slices): the bound is the kind::i8 pipe at twice the bf16 rate, i.e.
+            # 2 x bf16 / 28 in algorithmic Float64 FLOPs (MEASURED_PEAKS.json has no int8 or FP64 figure; DMMA, used
+            # for the small products, is ~36 TFLOP/s)
+            slices = min(7, max(2, int(os.environ.get("NB_OZAKI_SLICES", "7"))))
+            passes = slices * (slices + 1) // 2
+            peak, ratio = 2.0 * peaks["bf16_sustained"] / passes, None
+            f64_peak_note = (f"{peaks['source']} bf16 sustained {peaks['bf16_sustained']} TFLOP/s x 2 (kind::i8) / {passes} "
+                             f"int8 passes per Float64 product (Ozaki split, {slices} slices); small products on DMMA")
         traffic = None
         tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
         if args.math == "bf16x3" and args.dtype == "f32" and n == 1 and B == 32768 and os.path.exists(tpath):

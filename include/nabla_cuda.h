@@ -49,7 +49,7 @@ typedef enum nb_status {
 typedef enum nb_dtype { NB_F32 = 0, NB_F64 = 1 } nb_dtype;
 
 /* GEMM arithmetic.  Float32: see the modes.  Float64: exact FP64 FMA on the DMMA path for small products, exact
- * int8 slice products on tcgen05 (Ozaki split, ~5e-12 relative error norm-wise) for m*n*k >= 3e9; NB_MATH_FP32 keeps
+ * int8 slice products on tcgen05 (Ozaki split, ~4e-14 relative error norm-wise) for m*n*k >= 3e9; NB_MATH_FP32 keeps
  * every Float64 product on DMMA. */
 typedef enum nb_math_mode {
   NB_MATH_DEFAULT = 0,  /* f32: NB_MATH_BF16X3; f64: DMMA / Ozaki split by size */

@@ -6,16 +6,20 @@
 // blas.jl:224-228):
 //   1. every row i of op(A) and column j of op(B) is scaled by a power of two 2^-e so that |x| < 1/2
 //      (k_absmax_* -> row_scale / col_scale = 2^e);
-//   2. the scaled values are cut into S = 6 signed 7-bit slices  x = sum_p q_p 2^(-7(p+1)),  |q_p| <= 64
+//   2. the scaled values are cut into S = 7 signed 7-bit slices  x = sum_p q_p 2^(-7(p+1)),  |q_p| <= 64
 //      (k_slice: q = rint(128 x), x <- 128 x - q, exact in Float64); the slices of one operand are stored K-major
 //      and concatenated along K — A in order 0..S-1, B in REVERSE order — each padded to a multiple of 128;
 //   3. level l = p + q of  sum_{p+q<S} A_p B_q 2^(-7(p+q+2))  is then ONE kind::i8 GEMM over K' = (l+1)*Kp
 //      (A slices 0..l against B slices l..0, which are contiguous in that layout), accumulated exactly in int32 TMEM
 //      (K' * 2^12 < 2^31), and its epilogue adds  alpha * 2^(-7(l+2)) * row_scale * col_scale * acc  into the Float64 C.
-// Dropped: the levels p + q >= S (~2^-39 of max|row| * max|col| per product term) and the slice residual (2^-43):
-// measured norm-wise error 5e-12, elementwise error relative to max|row| * max|col|, like any scaled fixed-point
-// scheme.  A row / column holding a NaN or Inf makes its row / column of C NaN.
-// 21 int8 passes at twice the bf16 rate = 10.5 bf16 passes per product.
+// Dropped: the levels p + q >= S (~2^-51 of max|row| * max|col| per product term) and the slice residual (2^-50):
+// measured norm-wise error 4e-14 per product (DMMA: 2e-15), and a five-layer MLP gradient built from a dozen chained
+// 4096^3 split products agrees with the CPU oracle to 9e-13 (DMMA: 8e-14) — a hundred times inside rtol 1e-10; the
+// elementwise error is relative to max|row| * max|col|, like any scaled fixed-point scheme.  A row / column holding
+// a NaN or Inf makes its row / column of C NaN.
+// 28 int8 passes at twice the bf16 rate = 14 bf16 passes per product.  NB_OZAKI_SLICES=6 is the looser, faster
+// setting (21 passes, 26 in the one-launch form; 20-25 % less time): 5e-12 per product, which the same chain grows
+// to 8e-11 — too close to the 1e-10 bar to be the default (tools/check_f64_split_depth.py).
 #include "common.cuh"
 
 int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* A8, int64_t lda8, const int8_t* B8,
@@ -28,7 +32,7 @@ int32_t nb_gemm_i8all(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, int32_t S, 
 
 namespace {
 
-constexpr int S = 6;  // slices per operand
+constexpr int MAX_S = 7;  // slices per operand (<= 8 levels fit nb_gemm_i8all's table)
 
 // scale[i] = 2^e with |x| * 2^-e < 1/2 for every element of line i of op(X) (MN index i, reduced over K)
 //   contiguous-K form  (element (i, kk) at X[kk + i*ld]): one warp per line
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(256) k_absmax_finish(int64_t mn, double* __res
 template <bool MN_CONTIG>
 __global__ void __launch_bounds__(256) k_slice(const double* __restrict__ X, int64_t ld, int64_t mn, int64_t k, int64_t kp,
                                                const double* __restrict__ scale, int8_t* __restrict__ out, int64_t ldo,
-                                               int reverse) {
+                                               int reverse, int S) {
   __shared__ double tile[32][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
   const int64_t k0 = (int64_t)blockIdx.x * 32, i0 = (int64_t)blockIdx.y * 32;
@@ -108,7 +112,8 @@ __global__ void __launch_bounds__(256) k_slice(const double* __restrict__ X, int
     double x = tile[tx][r] / scale[i];  // power-of-two divide: exact
     int8_t* o = out + kk + i * ldo;
 #pragma unroll
-    for (int p = 0; p < S; ++p) {
+    for (int p = 0; p < MAX_S; ++p) {
+      if (p >= S) break;
       const double t = x * 128.0;
       const double q = rint(t);
       o[(int64_t)(reverse ? S - 1 - p : p) * kp] = (int8_t)(int)q;
@@ -126,6 +131,11 @@ int32_t nb_gemm_ozaki(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64
   if (m < 128 || n < 128 || k < 256) return NB_ERR_UNSUPPORTED;
   static const double min_work = getenv("NB_OZAKI_MIN_MNK") ? atof(getenv("NB_OZAKI_MIN_MNK")) : 3.0e9;  // crossover measured at ~3e9 (tools/ozaki_crossover.py)
   if ((double)m * (double)n * (double)k < min_work) return NB_ERR_UNSUPPORTED;  // small products: DMMA wins
+  static const int S = [] {
+    const char* e = getenv("NB_OZAKI_SLICES");
+    const int v = e ? atoi(e) : MAX_S;
+    return v < 2 ? 2 : v > MAX_S ? MAX_S : v;
+  }();
   const int64_t kp = (k + 127) / 128 * 128;
   if ((double)S * (double)kp * 4096.0 >= 2147483648.0) return NB_ERR_UNSUPPORTED;  // int32 accumulator must stay exact
   const int64_t ld8 = (int64_t)S * kp;
@@ -163,8 +173,8 @@ int32_t nb_gemm_ozaki(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64
   };
   auto slice = [&](bool mnc, const double* X, int64_t ld, int64_t mn, const double* sc, int8_t* out, int rev) {
     const dim3 grid((unsigned)(kp / 32), (unsigned)((mn + 31) / 32));
-    if (mnc) k_slice<true><<<grid, 256, 0, st>>>(X, ld, mn, k, kp, sc, out, ld8, rev);
-    else k_slice<false><<<grid, 256, 0, st>>>(X, ld, mn, k, kp, sc, out, ld8, rev);
+    if (mnc) k_slice<true><<<grid, 256, 0, st>>>(X, ld, mn, k, kp, sc, out, ld8, rev, S);
+    else k_slice<false><<<grid, 256, 0, st>>>(X, ld, mn, k, kp, sc, out, ld8, rev, S);
     ctx->stats.kernel_launches++;
   };
   absmax(a_mnc, A, lda, m, (double*)sa);
@@ -172,12 +182,13 @@ int32_t nb_gemm_ozaki(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64
   slice(a_mnc, A, lda, m, (const double*)sa, (int8_t*)a8, 0);
   slice(b_mnc, B, ldb, n, (const double*)sb, (int8_t*)b8, 1);
   if (cudaGetLastError() != cudaSuccess) { cleanup(); return nb_fail(ctx, NB_ERR_CUDA, "nb_gemm_ozaki: split kernels failed to launch"); }
-  // mid-size products: all levels (plus a seventh for 4e-14) in ONE launch with a Float64 running sum in the epilogue
-  // registers; large ones: one CTA-pair launch per level (higher int8 pipe utilisation, six passes over C)
+  // mid-size products: all levels in ONE launch with a Float64 running sum in the epilogue registers (with fewer
+  // than seven slices, the first dropped level rides along); large ones: one CTA-pair launch per level (higher int8
+  // pipe utilisation, S passes over C)
   static const double one_launch_below = getenv("NB_OZAKI_ONE_LAUNCH_MNK") ? atof(getenv("NB_OZAKI_ONE_LAUNCH_MNK")) : 2.0e10;
-  // (small K: the six read-modify-writes of C outweigh the pair kernel's better pipe utilisation at any m x n)
+  // (small K: the S read-modify-writes of C outweigh the pair kernel's better pipe utilisation at any m x n)
   if (((double)m * (double)n * (double)k < one_launch_below || k <= 2048) && (double)S * (double)kp < 2147483648.0 / 4096.0) {
-    rc = nb_gemm_i8all(ctx, m, n, kp, S, 1, (const int8_t*)a8, ld8, (const int8_t*)b8, alpha, (const double*)sa,
+    rc = nb_gemm_i8all(ctx, m, n, kp, S, S < MAX_S ? 1 : 0, (const int8_t*)a8, ld8, (const int8_t*)b8, alpha, (const double*)sa,
                        (const double*)sb, beta, C, ldc);
     if (rc != NB_ERR_UNSUPPORTED) { cleanup(); return rc; }
     rc = NB_OK;

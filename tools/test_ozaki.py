@@ -10,9 +10,13 @@ from nabla_jl_b200 import kernels as K  # noqa: E402
 
 ctx = nb.get_context()
 rng = np.random.default_rng(0)
-for (m, n, k) in ((4096, 4096, 4096), (4100, 4200, 4000), (8192, 2048, 8192)):
-    for tA in "NT":
-        for tB in "NT":
+SHAPES = ((4096, 4096, 4096), (4100, 4200, 4000), (8192, 2048, 8192))
+if os.environ.get("OZ_SHAPES"):   # e.g. OZ_SHAPES=4100x4200x4000,4096x4096x4096
+    SHAPES = tuple(tuple(int(v) for v in s.split("x")) for s in os.environ["OZ_SHAPES"].split(","))
+ITERS = int(os.environ.get("OZ_ITERS", "3"))
+for (m, n, k) in SHAPES:
+    for tA in os.environ.get("OZ_TA", "NT"):
+        for tB in os.environ.get("OZ_TB", "NT"):
             A = rng.standard_normal((k, m) if tA == "T" else (m, k))
             B = rng.standard_normal((n, k) if tB == "T" else (k, n))
             C0 = rng.standard_normal((m, n))
@@ -28,11 +32,11 @@ for (m, n, k) in ((4096, 4096, 4096), (4100, 4200, 4000), (8192, 2048, 8192)):
                 emax = np.max(np.abs(got - ref)) / np.max(np.abs(ref))
                 e0, e1 = ctx.event(), ctx.event()
                 ctx.record(e0)
-                for _ in range(3):
+                for _ in range(ITERS):
                     K.gemm(tA, tB, 0.7, Ad, Bd, 0.0, Cd, m, n, k)
                 ctx.record(e1)
                 ctx.sync()
-                ms = ctx.elapsed_ms(e0, e1) / 3
+                ms = ctx.elapsed_ms(e0, e1) / ITERS
                 res[name] = (err, emax, ms)
             ctx.math_mode = nb.MATH_DEFAULT
             print(f"{tA}{tB} {m}x{n}x{k}: " + "  ".join(
