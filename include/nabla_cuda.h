@@ -97,7 +97,9 @@ typedef enum nb_op {
   NB_OP_SF_BEGIN = 96,
   NB_OP_GAMMA = 96, NB_OP_DIGAMMA = 97, NB_OP_TRIGAMMA = 98, NB_OP_BESSELJ0 = 99, NB_OP_BESSELJ1 = 100,
   NB_OP_BESSELY0 = 101, NB_OP_BESSELY1 = 102, NB_OP_ERFINV = 103, NB_OP_ERFCINV = 104, NB_OP_ERFCX = 105,
-  NB_OP_SF_END = 106
+  NB_OP_AIRYAI = 106, NB_OP_AIRYAIPRIME = 107, NB_OP_AIRYBI = 108, NB_OP_AIRYBIPRIME = 109,
+  NB_OP_DAWSON = 110, NB_OP_ERFI = 111, NB_OP_INVDIGAMMA = 112,   /* csrc/special.cuh */
+  NB_OP_SF_END = 113
 } nb_op;
 
 typedef struct nb_stats {

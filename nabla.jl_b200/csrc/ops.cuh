@@ -7,6 +7,7 @@
 // reverse accumulation over the program DAG (same derivative, one pass for all operands).
 #pragma once
 #include "common.cuh"
+#include "special.cuh"
 
 struct nb_prog {
   int32_t nargs;
@@ -69,8 +70,8 @@ __host__ __device__ constexpr int nb_partial_needs(int op, int wrt /*0=a,1=b*/) 
     case NB_OP_HYPOT: return wrt == 0 ? (A | Y) : (B | Y);
     case NB_OP_MAX: case NB_OP_MIN: case NB_OP_ATAN2: return A | B;
     case NB_OP_BETA: return A | B | Y;
-    case NB_OP_ERFINV: case NB_OP_ERFCINV: return Y;
-    case NB_OP_GAMMA: case NB_OP_ERFCX: return A | Y;
+    case NB_OP_ERFINV: case NB_OP_ERFCINV: case NB_OP_INVDIGAMMA: return Y;
+    case NB_OP_GAMMA: case NB_OP_ERFCX: case NB_OP_DAWSON: return A | Y;
     default: return A;  // unary ops whose partial is a function of x
   }
 }
@@ -241,6 +242,13 @@ __device__ __forceinline__ T nb_eval_full(int op, T a, T b) {
     case NB_OP_ERFINV: return nb_erfinv<T>(a);
     case NB_OP_ERFCINV: return nb_erfcinv<T>(a);
     case NB_OP_ERFCX: return nb_erfcx<T>(a);
+    case NB_OP_AIRYAI: return T(nb_airy((double)a, 0));
+    case NB_OP_AIRYAIPRIME: return T(nb_airy((double)a, 1));
+    case NB_OP_AIRYBI: return T(nb_airy((double)a, 2));
+    case NB_OP_AIRYBIPRIME: return T(nb_airy((double)a, 3));
+    case NB_OP_DAWSON: return T(nb_dawson((double)a));
+    case NB_OP_ERFI: return T(nb_erfi((double)a));
+    case NB_OP_INVDIGAMMA: return T(nb_invdigamma((double)a));
     default: return a;
   }
 }
@@ -323,6 +331,13 @@ __device__ __forceinline__ T nb_dunary_full(int op, T a, T y) {
     case NB_OP_ERFINV: return T(1.0 / NB_2_SQRTPI) * exp(y * y);
     case NB_OP_ERFCINV: return -T(1.0 / NB_2_SQRTPI) * exp(y * y);
     case NB_OP_ERFCX: return T(2) * a * y - T(NB_2_SQRTPI);
+    case NB_OP_AIRYAI: return T(nb_airy((double)a, 1));          // Ai'
+    case NB_OP_AIRYAIPRIME: return a * T(nb_airy((double)a, 0)); // Ai'' = x Ai
+    case NB_OP_AIRYBI: return T(nb_airy((double)a, 3));
+    case NB_OP_AIRYBIPRIME: return a * T(nb_airy((double)a, 2));
+    case NB_OP_DAWSON: return T(1) - T(2) * a * y;
+    case NB_OP_ERFI: return T(NB_2_SQRTPI * nb_exp_sq((double)a));
+    case NB_OP_INVDIGAMMA: return T(1.0 / nb_sf_trigamma_pos((double)y));
     default: return T(0);
   }
 }

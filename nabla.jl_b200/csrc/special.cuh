@@ -1,0 +1,172 @@
+// SpecialFunctions.jl functions the CUDA math library does not have (test/runtests.jl:34-36 of the reference):
+// airyai, airyaiprime, airybi, airybiprime, dawson, erfi, invdigamma.  Evaluated in double for both element types.
+//
+// The file compiles as plain C++ too (NB_SF_FN / NB_SF_TAB): tests/test_host_logic.py builds it with g++ and checks
+// every function against mpmath / scipy over the whole real line without a GPU; the device build is the same source.
+//
+//   Airy:    y'' = x y.  |x| <= 16: Taylor recurrence (n+2)(n+1) a_{n+2} = x0 a_n + a_{n-1} from the nearest anchor
+//            x0 (spacing 1/2, |h| <= 1/4, 26 terms; anchor values correctly rounded from mpmath,
+//            tools/gen_airy_table.py) — each of Ai, Bi is continued from its OWN exact anchor over at most 1/4, so the
+//            recessive solution is not polluted by the dominant one.  |x| > 16: the expansions DLMF 9.7.5-9.7.12
+//            (16 terms, last term < 2e-19 at zeta = 42.7).
+//   dawson:  |x| < 1/2 Maclaurin series; up to 25 Rybicki's sampling formula (samples 0.4 apart, error e^{-(pi/0.4)^2} ~ 1e-27);
+//            beyond, the asymptotic series.  d/dx = 1 - 2 x F(x).
+//   erfi:    2/sqrt(pi) exp(x^2) dawson(x), Maclaurin below 1/2; x^2 is split by an fma so that exp sees its exact
+//            argument.  d/dx = 2/sqrt(pi) exp(x^2).
+//   invdigamma: Newton on digamma(x) = y from Minka's closed-form start (the scheme SpecialFunctions.jl uses),
+//            run to the last bit.  d/dy = 1 / trigamma(invdigamma(y)).
+#pragma once
+#if defined(__CUDACC__)
+#define NB_SF_FN static __device__ __noinline__
+#define NB_SF_TAB static __device__ const double
+#else
+#include <math.h>
+#define NB_SF_FN static inline
+#define NB_SF_TAB static const double
+#endif
+
+#include "special_airy_table.inc"
+
+#define NB_SF_SQRTPI 1.77245385090551602730
+#define NB_SF_PI_4 0.78539816339744830962
+
+// which: 0 Ai, 1 Ai', 2 Bi, 3 Bi'
+NB_SF_FN double nb_airy(double x, int which) {
+  if (x != x) return x;
+  const bool bi = which >= 2, prime = which & 1;
+  if (fabs(x) <= NB_AIRY_XA) {
+    int j = (int)floor((x + NB_AIRY_XA) * NB_AIRY_INV_H + 0.5);
+    j = j < 0 ? 0 : j > NB_AIRY_N - 1 ? NB_AIRY_N - 1 : j;
+    const double x0 = -NB_AIRY_XA + (double)j / NB_AIRY_INV_H, h = x - x0;
+    double am1 = 0.0, a0 = NB_AIRY_ANCHORS[4 * j + (bi ? 2 : 0)], a1 = NB_AIRY_ANCHORS[4 * j + (bi ? 3 : 1)];
+    double y = a0 + a1 * h, yp = a1, hn = h;  // hn = h^(n+1)
+    for (int n = 0; n < 26; ++n) {
+      const double a2 = (x0 * a0 + am1) / (double)((n + 1) * (n + 2));
+      yp += (double)(n + 2) * a2 * hn;
+      hn *= h;
+      y += a2 * hn;
+      am1 = a0; a0 = a1; a1 = a2;
+    }
+    return prime ? yp : y;
+  }
+  const double ax = fabs(x), r = sqrt(ax), zeta = (2.0 / 3.0) * ax * r, q = sqrt(r);  // q = |x|^(1/4)
+  const double iz = 1.0 / zeta;
+  const double* c = prime ? NB_AIRY_V : NB_AIRY_U;
+  if (x > 0.0) {
+    // Ai ~ e^-z / (2 sqrt(pi) q) sum (-1)^k u_k z^-k;  Ai' ~ -q e^-z / (2 sqrt(pi)) sum (-1)^k v_k z^-k
+    // Bi ~ e^z  / (sqrt(pi) q)   sum u_k z^-k;         Bi' ~  q e^z  / sqrt(pi)     sum v_k z^-k
+    double s = 0.0, p = 1.0;
+    for (int k = 0; k < NB_AIRY_NASY; ++k) {
+      s += ((!bi && (k & 1)) ? -c[k] : c[k]) * p;
+      p *= iz;
+    }
+    const double amp = prime ? q : 1.0 / q;
+    if (bi) return exp(zeta) * amp * s / NB_SF_SQRTPI;
+    return (prime ? -0.5 : 0.5) * exp(-zeta) * amp * s / NB_SF_SQRTPI;
+  }
+  // x < 0: even / odd parts P = sum (-1)^k c_2k z^-2k, Q = sum (-1)^k c_2k+1 z^-(2k+1)
+  double P = 0.0, Q = 0.0, p = 1.0;
+  for (int k = 0; k < NB_AIRY_NASY; k += 2) {
+    const double sg = (k & 2) ? -1.0 : 1.0;
+    P += sg * c[k] * p;
+    p *= iz;
+    Q += sg * c[k + 1] * p;
+    p *= iz;
+  }
+  const double th = zeta - NB_SF_PI_4, sn = sin(th), cs = cos(th);
+  switch (which) {
+    case 0: return (cs * P + sn * Q) / (NB_SF_SQRTPI * q);
+    case 1: return q * (sn * P - cs * Q) / NB_SF_SQRTPI;
+    case 2: return (-sn * P + cs * Q) / (NB_SF_SQRTPI * q);
+    default: return q * (cs * P + sn * Q) / NB_SF_SQRTPI;
+  }
+}
+
+NB_SF_FN double nb_dawson(double x) {
+  const double ax = fabs(x);
+  if (x != x) return x;
+  if (ax < 0.5) {  // F = x sum (-2 x^2)^k / (2k+1)!!
+    const double t = -2.0 * x * x;
+    double term = 1.0, s = 1.0;
+    for (int k = 1; k < 15; ++k) {
+      term *= t / (double)(2 * k + 1);
+      s += term;
+    }
+    return x * s;
+  }
+  if (ax > 25.0) {  // F ~ 1/(2x) sum (2k-1)!! / (2 x^2)^k
+    const double t = 0.5 / (ax * ax);
+    double term = 1.0, s = 1.0;
+    for (int k = 1; k < 8; ++k) {
+      term *= (double)(2 * k - 1) * t;
+      s += term;
+    }
+    return (x < 0.0 ? -0.5 : 0.5) * s / ax;
+  }
+  // Rybicki: F(x) = 1/sqrt(pi) sum_{n odd} e^{-(x - n h)^2} / n, centred on the even multiple of h nearest to x
+  const double H = 0.2;  // samples 2H apart: error e^{-(pi / 2H)^2} = 2e-27
+  const int n0 = 2 * (int)(0.5 * ax / H + 0.5);
+  const double xp = ax - (double)n0 * H;
+  double e1 = exp(2.0 * xp * H);
+  const double e2 = e1 * e1;
+  double d1 = (double)n0 + 1.0, d2 = d1 - 2.0, s = 0.0;
+  for (int i = 0; i < 17; ++i) {
+    const double w = (double)(2 * i + 1) * H;
+    s += exp(-w * w) * (e1 / d1 + 1.0 / (d2 * e1));
+    d1 += 2.0;
+    d2 -= 2.0;
+    e1 *= e2;
+  }
+  const double f = exp(-xp * xp) * s / NB_SF_SQRTPI;
+  return x < 0.0 ? -f : f;
+}
+
+// exp(x^2) with the rounding error of x*x folded back in
+NB_SF_FN double nb_exp_sq(double x) {
+  const double s = x * x, e = fma(x, x, -s);
+  return exp(s) * (1.0 + e);
+}
+
+NB_SF_FN double nb_erfi(double x) {
+  if (fabs(x) < 0.5) {  // 2/sqrt(pi) sum x^(2k+1) / (k! (2k+1))
+    const double t = x * x;
+    double pw = 1.0, s = 1.0;
+    for (int k = 1; k < 16; ++k) {
+      pw *= t / (double)k;
+      s += pw / (double)(2 * k + 1);
+    }
+    return (2.0 / NB_SF_SQRTPI) * x * s;
+  }
+  return (2.0 / NB_SF_SQRTPI) * nb_exp_sq(x) * nb_dawson(x);
+}
+
+// digamma / trigamma for x > 0: recurrence to x >= 10, then the asymptotic series
+NB_SF_FN double nb_sf_digamma_pos(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+  const double f = 1.0 / (x * x);
+  return r + log(x) - 0.5 / x -
+         f * (1.0 / 12 - f * (1.0 / 120 - f * (1.0 / 252 - f * (1.0 / 240 - f * (1.0 / 132 - f * (691.0 / 32760 - f / 12))))));
+}
+NB_SF_FN double nb_sf_trigamma_pos(double x) {
+  double r = 0.0;
+  while (x < 10.0) { r += 1.0 / (x * x); x += 1.0; }
+  const double f = 1.0 / (x * x);
+  return r + 1.0 / x + 0.5 * f +
+         (f / x) * (1.0 / 6 - f * (1.0 / 30 - f * (1.0 / 42 - f * (1.0 / 30 - f * (5.0 / 66 - f * (691.0 / 2730 - f * 7.0 / 6))))));
+}
+
+NB_SF_FN double nb_invdigamma(double y) {
+  if (y != y) return y;
+  double x = y >= -2.22 ? exp(y) + 0.5 : -1.0 / (y + 0.57721566490153286061);
+  if (!(x < 1.0e300)) return x;  // exp overflow: digamma(x) ~ log x
+  for (int it = 0; it < 40; ++it) {
+    const double d = (nb_sf_digamma_pos(x) - y) / nb_sf_trigamma_pos(x);
+    double xn = x - d;
+    if (!(xn > 0.0)) xn = 0.5 * x;  // stay in the domain
+    const bool done = fabs(xn - x) <= 4.0e-16 * xn;
+    x = xn;
+    if (done) break;
+  }
+  return x;
+}

@@ -31,8 +31,8 @@ _A, _B, _Y = 1, 2, 4
 _NEEDS_NONE = {"identity", "neg", "deg2rad", "rad2deg"}
 _NEEDS_Y = {"tanh", "exp", "logistic", "sqrt", "inv", "tan", "exp2", "exp10", "cbrt", "cot", "coth", "tand",
             "cotd", "expm1"}
-_NEEDS_Y |= {"erfinv", "erfcinv"}
-_NEEDS_AY = {"sec", "csc", "sech", "csch", "secd", "cscd", "gamma", "erfcx"}
+_NEEDS_Y |= {"erfinv", "erfcinv", "invdigamma"}
+_NEEDS_AY = {"sec", "csc", "sech", "csch", "secd", "cscd", "gamma", "erfcx", "dawson"}
 
 
 def _is_binary(op):

@@ -260,6 +260,23 @@ def _polygamma_any(n, x):
     return out if out.ndim else float(out)
 
 
+def _invdigamma(y):
+    """Inverse of digamma on x > 0: Newton from Minka's closed-form start ("Estimating a Dirichlet distribution",
+    2000), the scheme SpecialFunctions.jl's invdigamma uses (its loop stops at |dx| <= 1e-12; here it runs on to
+    the last bit, the results agree to that tolerance)."""
+    y = np.asarray(y, dtype=np.float64)
+    with np.errstate(all="ignore"):
+        x = np.where(y >= -2.22, np.exp(y) + 0.5, -1.0 / (y - _sp.digamma(1.0)))
+        for _ in range(40):
+            xn = x - (_sp.digamma(x) - y) / _sp.polygamma(1, x)
+            xn = np.where(xn > 0.0, xn, 0.5 * x)
+            if np.all(np.abs(xn - x) <= 4e-16 * xn):
+                x = xn
+                break
+            x = xn
+    return x if x.ndim else float(x)
+
+
 _UNARY = {
     # name: (f, f')  -- SURVEY.md §8(c) catalogue
     "identity": (lambda x: x, lambda x: 1.0 + 0.0 * x),
@@ -332,6 +349,13 @@ _UNARY = {
     "besselj1": (lambda x: _sp.j1(x), lambda x: (_sp.j0(x) - _sp.jv(2, x)) / 2.0),
     "bessely0": (lambda x: _sp.y0(x), lambda x: -_sp.y1(x)),
     "bessely1": (lambda x: _sp.y1(x), lambda x: (_sp.y0(x) - _sp.yv(2, x)) / 2.0),
+    "airyai": (lambda x: _sp.airy(x)[0], lambda x: _sp.airy(x)[1]),
+    "airyaiprime": (lambda x: _sp.airy(x)[1], lambda x: x * _sp.airy(x)[0]),          # Ai'' = x Ai
+    "airybi": (lambda x: _sp.airy(x)[2], lambda x: _sp.airy(x)[3]),
+    "airybiprime": (lambda x: _sp.airy(x)[3], lambda x: x * _sp.airy(x)[2]),
+    "dawson": (lambda x: _sp.dawsn(x), lambda x: 1.0 - 2.0 * x * _sp.dawsn(x)),
+    "erfi": (lambda x: _sp.erfi(x), lambda x: _2_SQRTPI * np.exp(x * x)),
+    "invdigamma": (_invdigamma, lambda x: 1.0 / _sp.polygamma(1, _invdigamma(x))),
 }
 
 _BINARY = {

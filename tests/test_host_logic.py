@@ -38,8 +38,51 @@ def test_opcodes_match_header():
     assert ops["identity"] == 0 and ops["tanh"] == 23 and ops["logistic"] == 55
     assert ops["add"] == 64 and ops["atan2"] == 73
     assert ops["beta"] == 74 and ops["gamma"] == 96 and ops["erfcx"] == 105
-    assert len(scalar.UNARY) == 58 + 10 and len(scalar.BINARY) == 11   # + the SpecialFunctions subset
+    assert ops["airyai"] == 106 and ops["invdigamma"] == 112 and ops["sf_end"] == 113
+    assert len(scalar.UNARY) == 58 + 17 and len(scalar.BINARY) == 11   # + every unary of SpecialFunctions the reference lists
     assert "sf_begin" not in scalar.UNARY and "binary_end" not in scalar.BINARY
+
+
+def test_special_functions_source_on_the_host(tmp_path):
+    """csrc/special.cuh (airy*, dawson, erfi, invdigamma: the SpecialFunctions.jl entries of test/runtests.jl:34-36
+    the CUDA math library lacks) is plain C++ as well as device code: build it with g++ and check every function
+    against 40-digit mpmath values over the whole real line.  The device kernels compile the same source."""
+    import ctypes as C
+    import subprocess
+    import mpmath as mp
+    import numpy as np
+    lib = str(tmp_path / "libsf.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", lib,
+                           os.path.join(ROOT, "tests", "special_host_shim.cpp")])
+    L = C.CDLL(lib)
+    L.sf_airy.restype, L.sf_airy.argtypes = C.c_double, [C.c_double, C.c_int]
+    for n in ("sf_dawson", "sf_erfi", "sf_invdigamma"):
+        getattr(L, n).restype, getattr(L, n).argtypes = C.c_double, [C.c_double]
+    mp.mp.dps = 40
+    rng = np.random.default_rng(0)
+    airy = [lambda x: mp.airyai(x), lambda x: mp.airyai(x, derivative=1),
+            lambda x: mp.airybi(x), lambda x: mp.airybi(x, derivative=1)]
+    xs = np.concatenate([rng.uniform(-16, 16, 400), rng.uniform(-40, -16, 60), rng.uniform(16, 40, 60),
+                         np.linspace(-16, 16, 65), np.linspace(-16, 16, 65)[:-1] + 0.25, [0.0, 1e-300, 16.0001, -16.0001]])
+    for w in range(4):
+        for x in xs:
+            X = mp.mpf(float(x))
+            ref = airy[w](X)
+            # oscillatory side: error relative to the local amplitude (values cross zero); else to the value
+            amp = mp.sqrt(airy[w & 1](X) ** 2 + airy[2 + (w & 1)](X) ** 2) if x < 0 else abs(ref)
+            assert abs(L.sf_airy(float(x), w) - ref) <= 1e-13 * amp, (w, x)
+    assert L.sf_airy(200.0, 0) == 0.0 and L.sf_airy(200.0, 2) == float("inf") and np.isnan(L.sf_airy(float("nan"), 1))
+    xs = np.concatenate([rng.uniform(-30, 30, 500), rng.uniform(-1, 1, 100), [0.5, -0.5, 25.0, 25.0001, 1e-8, 1e5, -1e8]])
+    for x in xs:
+        X = mp.mpf(float(x))
+        ref = mp.sqrt(mp.pi) / 2 * mp.exp(-X * X) * mp.erfi(X)
+        assert abs(L.sf_dawson(float(x)) - ref) <= 4e-15 * abs(ref), x
+        if abs(x) < 26:
+            assert abs(L.sf_erfi(float(x)) - mp.erfi(X)) <= 4e-15 * abs(mp.erfi(X)), x
+    assert L.sf_dawson(0.0) == 0.0 and L.sf_erfi(0.0) == 0.0 and L.sf_erfi(27.0) == float("inf")
+    for y in np.concatenate([rng.uniform(-50, 10, 300), rng.uniform(-3.1, 3.1, 100), [-2.22, -2.2200001, 0.0, 100.0, -1e6]]):
+        G = mp.mpf(L.sf_invdigamma(float(y)))
+        assert abs(mp.digamma(G) - mp.mpf(float(y))) <= 1e-14 * mp.polygamma(1, G) * G, y   # relative error of x
 
 
 def test_tracer_single_primitive_and_constants():
