@@ -92,7 +92,10 @@ typedef enum nb_op {
   NB_OP_POW = 69, NB_OP_HYPOT = 70, NB_OP_MAX = 71, NB_OP_MIN = 72,
   NB_OP_ATAN2 = 73,     /* atan(y_, x_) with operand a = y_, b = x_ */
   NB_OP_BETA = 74,      /* SpecialFunctions.beta(a, b) */
-  NB_OP_BINARY_END = 75,
+  /* differentiable in the SECOND operand only (test/runtests.jl:43-47): operand a is the integer order, its partial is
+   * NaN as in DiffRules; a non-integer order gives NaN (csrc/special.cuh) */
+  NB_OP_BESSELJ = 75, NB_OP_BESSELY = 76, NB_OP_BESSELI = 77, NB_OP_BESSELK = 78, NB_OP_POLYGAMMA = 79,
+  NB_OP_BINARY_END = 80,
   /* SpecialFunctions.jl unary functions of test/runtests.jl:34-36 (second unary range) */
   NB_OP_SF_BEGIN = 96,
   NB_OP_GAMMA = 96, NB_OP_DIGAMMA = 97, NB_OP_TRIGAMMA = 98, NB_OP_BESSELJ0 = 99, NB_OP_BESSELJ1 = 100,

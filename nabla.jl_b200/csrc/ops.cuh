@@ -70,6 +70,8 @@ __host__ __device__ constexpr int nb_partial_needs(int op, int wrt /*0=a,1=b*/) 
     case NB_OP_HYPOT: return wrt == 0 ? (A | Y) : (B | Y);
     case NB_OP_MAX: case NB_OP_MIN: case NB_OP_ATAN2: return A | B;
     case NB_OP_BETA: return A | B | Y;
+    case NB_OP_BESSELJ: case NB_OP_BESSELY: case NB_OP_BESSELI: case NB_OP_BESSELK: case NB_OP_POLYGAMMA:
+      return wrt == 0 ? 0 : (A | B);   // d/d(order) is the constant NaN
     case NB_OP_ERFINV: case NB_OP_ERFCINV: case NB_OP_INVDIGAMMA: return Y;
     case NB_OP_GAMMA: case NB_OP_ERFCX: case NB_OP_DAWSON: return A | Y;
     default: return A;  // unary ops whose partial is a function of x
@@ -232,6 +234,11 @@ __device__ __forceinline__ T nb_eval_full(int op, T a, T b) {
     case NB_OP_MIN: return fmin(a, b);
     case NB_OP_ATAN2: return atan2(a, b);
     case NB_OP_BETA: return exp(lgamma(a) + lgamma(b) - lgamma(a + b));
+    case NB_OP_BESSELJ: return T(nb_bessel(0, (double)a, (double)b));
+    case NB_OP_BESSELY: return T(nb_bessel(1, (double)a, (double)b));
+    case NB_OP_BESSELI: return T(nb_bessel(2, (double)a, (double)b));
+    case NB_OP_BESSELK: return T(nb_bessel(3, (double)a, (double)b));
+    case NB_OP_POLYGAMMA: return T(nb_polygamma_n((double)a, (double)b));
     case NB_OP_GAMMA: return tgamma(a);
     case NB_OP_DIGAMMA: return T(nb_polygamma<0>((double)a));
     case NB_OP_TRIGAMMA: return T(nb_polygamma<1>((double)a));
@@ -404,6 +411,9 @@ __device__ __forceinline__ T nb_dbinary(int op, int wrt, T a, T b, T y) {
       const double pab = nb_polygamma<0>((double)a + (double)b);
       return y * T(nb_polygamma<0>((double)(wrt == 0 ? a : b)) - pab);
     }
+    case NB_OP_BESSELJ: case NB_OP_BESSELY: case NB_OP_BESSELI: case NB_OP_BESSELK:
+      return wrt == 0 ? T(nan("")) : T(nb_bessel_dx(op - NB_OP_BESSELJ, (double)a, (double)b));
+    case NB_OP_POLYGAMMA: return wrt == 0 ? T(nan("")) : T(nb_polygamma_n((double)a + 1.0, (double)b));
     default: return T(0);
   }
 }

@@ -170,3 +170,162 @@ NB_SF_FN double nb_invdigamma(double y) {
   }
   return x;
 }
+
+// ---- integer-order Bessel functions and polygamma(n, x): the second-argument-only binary functions of
+// test/runtests.jl:43-47 (the reference tests them with integer first arguments 0..5; a non-integer order gives NaN).
+//   J_n: power series below |x| = max(3, 2 sqrt(n+1)); periodic trapezoid rule on (1/2pi) int cos(n t - x sin t) dt with 128 points
+//        (aliasing error J_{128-n}(x), < 1e-30 for |x| <= 50); Hankel's expansion beyond.
+//   I_n: the same three regimes on (1/2pi) int e^{x cos t} cos(n t) dt.
+//   K_n: trapezoid rule on int_0^inf e^{-x cosh t} cosh(n t) dt, step min(1/8, 1/(2 sqrt x)) (doubly exponential decay,
+//        error e^{-2 pi d / h} with d ~ 1.4 the half-width of the strip where the integrand decays).
+//   Y_n: y0 / y1 of the math library and the upward recurrence (stable for Y).
+//   polygamma(n, x) = (-1)^(n+1) n! zeta(n+1, x): shift to x >= 20 by the defining sum, then Euler-Maclaurin.
+#define NB_SF_2PI 6.28318530717958647692
+
+// sum_k (-1)^k? a_k / (8x)^k pieces of Hankel's expansions: P (even k, alternating), Q (odd k, alternating), and the
+// plain sums with (+) or (-1)^k signs for K_n / I_n.  mu = 4 n^2.
+NB_SF_FN void nb_hankel_terms(int n, double ax, double* P, double* Q, double* Sp, double* Sm) {
+  const double mu = 4.0 * (double)n * (double)n, i8x = 0.125 / ax;
+  double a = 1.0, p = 1.0, q = 0.0, sp = 1.0, sm = 1.0;
+  for (int k = 1; k <= 30; ++k) {
+    const double od = (double)(2 * k - 1);
+    const double an = a * (mu - od * od) / (double)k * i8x;
+    if (fabs(an) > fabs(a) && k > n) break;  // the expansion has started to diverge
+    a = an;
+    sp += a;
+    sm += (k & 1) ? -a : a;
+    if (k & 1) q += (k & 2) ? -a : a;   // k = 1: +, 3: -, 5: + ...
+    else p += (k & 2) ? -a : a;         // k = 2: -, 4: +, ...
+    if (fabs(a) < 1e-18) break;
+  }
+  *P = p; *Q = q; *Sp = sp; *Sm = sm;
+}
+
+// kind 0: J_n(x), kind 1: I_n(x); any real x, any integer n
+NB_SF_FN double nb_bessel_ji(int n, double x, int kind) {
+  if (x != x) return x;
+  double sign = 1.0;
+  if (n < 0) { n = -n; if (kind == 0 && (n & 1)) sign = -sign; }
+  if (x < 0.0) { x = -x; if (n & 1) sign = -sign; }
+  if (x < 3.0 || x * x < 4.0 * (double)(n + 1)) {  // (x/2)^n / n! sum (-+ x^2/4)^k / (k! (n+1)_k): terms decrease, no cancellation
+    const double t = (kind == 0 ? -0.25 : 0.25) * x * x;
+    double term = 1.0, s = 1.0;
+    for (int k = 1; k < 40; ++k) {
+      term *= t / ((double)k * (double)(k + n));
+      s += term;
+      if (fabs(term) < 1e-18 * fabs(s)) break;
+    }
+    double lead = 1.0;
+    for (int k = 1; k <= n; ++k) lead *= 0.5 * x / (double)k;
+    return sign * lead * s;
+  }
+  if (x > 50.0) {
+    double P, Q, Sp, Sm;
+    nb_hankel_terms(n, x, &P, &Q, &Sp, &Sm);
+    if (kind == 1) return sign * exp(x) * Sm / sqrt(NB_SF_2PI * x);
+    const double chi = x - (0.5 * (double)n + 0.25) * (0.5 * NB_SF_2PI);
+    return sign * sqrt(4.0 / (NB_SF_2PI * x)) * (P * cos(chi) - Q * sin(chi));
+  }
+  // periodic trapezoid rule, N = 128; the integrand is even about pi: f(0) + f(pi) + 2 sum_{k=1}^{63} f(t_k)
+  const int N = 128;
+  const double dt = NB_SF_2PI / (double)N;
+  double s;
+  if (kind == 0) s = 1.0 + ((n & 1) ? -1.0 : 1.0);
+  else s = 1.0 + ((n & 1) ? -1.0 : 1.0) * exp(-2.0 * x);   // terms scaled by e^-x
+  for (int k = 1; k < N / 2; ++k) {
+    const double t = dt * (double)k;
+    if (kind == 0) s += 2.0 * cos((double)n * t - x * sin(t));
+    else s += 2.0 * exp(x * (cos(t) - 1.0)) * cos((double)n * t);
+  }
+  s /= (double)N;
+  return sign * (kind == 0 ? s : s * exp(x));
+}
+
+// K_n(x), x > 0
+NB_SF_FN double nb_bessel_k(int n, double x) {
+  if (x != x) return x;
+  if (!(x > 0.0)) return x == 0.0 ? INFINITY : nan("");
+  if (n < 0) n = -n;
+  const double nn = (double)n;
+  double h = 0.5 / sqrt(x);
+  if (h > 0.125) h = 0.125;
+  double s = 0.5;  // t = 0: cosh(0) = 1, half weight
+  for (int k = 1; k < 4000; ++k) {
+    const double t = h * (double)k, em = exp(-t);
+    const double ch1 = 0.5 * (1.0 - em) * (1.0 - em) / em;  // cosh t - 1 without cancellation
+    const double e = -x * ch1;
+    const double term = 0.5 * (exp(e + nn * t) + exp(e - nn * t));
+    s += term;
+    if (term < 1e-18 * s && x * ch1 > nn * t) break;
+  }
+  return h * s * exp(-x);
+}
+
+// Y_n(x), x > 0
+NB_SF_FN double nb_bessel_y(int n, double x) {
+  if (x != x) return x;
+  if (!(x > 0.0)) return x == 0.0 ? -INFINITY : nan("");
+  double sign = 1.0;
+  if (n < 0) { n = -n; if (n & 1) sign = -1.0; }
+  double ym = y0(x);
+  if (n == 0) return ym;
+  double yc = y1(x);
+  for (int k = 1; k < n; ++k) {
+    const double yn_ = (2.0 * (double)k / x) * yc - ym;
+    ym = yc;
+    yc = yn_;
+  }
+  return sign * yc;
+}
+
+// first-argument dispatch: nu must be an integer.  which: 0 J, 1 Y, 2 I, 3 K
+NB_SF_FN double nb_bessel(int which, double nu, double x) {
+  if (nu != floor(nu) || fabs(nu) > 1.0e6) return nan("");
+  const int n = (int)nu;
+  switch (which) {
+    case 0: return nb_bessel_ji(n, x, 0);
+    case 1: return nb_bessel_y(n, x);
+    case 2: return nb_bessel_ji(n, x, 1);
+    default: return nb_bessel_k(n, x);
+  }
+}
+// d/dx: (J_{n-1} - J_{n+1})/2, same for Y; (I_{n-1} + I_{n+1})/2; -(K_{n-1} + K_{n+1})/2
+NB_SF_FN double nb_bessel_dx(int which, double nu, double x) {
+  const double lo = nb_bessel(which, nu - 1.0, x), hi = nb_bessel(which, nu + 1.0, x);
+  if (which <= 1) return 0.5 * (lo - hi);
+  return which == 2 ? 0.5 * (lo + hi) : -0.5 * (lo + hi);
+}
+
+// polygamma(n, x), integer n >= 0, any real x that is not a pole
+NB_SF_FN double nb_polygamma_n(double nu, double x) {
+  if (x != x || nu != floor(nu) || nu < 0.0 || nu > 100.0) return nan("");
+  if (x <= 0.0 && x == floor(x)) return nan("");
+  if (x < -1.0e5) return nan("");  // (the shift below would not terminate in reasonable time)
+  const int n = (int)nu;
+  if (n == 0) {
+    double r = 0.0;
+    while (x < 10.0) { r -= 1.0 / x; x += 1.0; }
+    return r + nb_sf_digamma_pos(x);
+  }
+  // zeta(s, x) = sum_k (x + k)^-s, s = n + 1
+  const double s = (double)(n + 1);
+  double z = 0.0;
+  const double X0 = 20.0 + (double)n;
+  while (x < X0) { z += pow(x, -s); x += 1.0; }
+  // Euler-Maclaurin tail: x^(1-s)/(s-1) + x^-s/2 + sum_j B_2j/(2j)! (s)_(2j-1) x^(-s-2j+1)
+  const double B2J_OVER_FACT[10] = {1.0 / 12, -1.0 / 720, 1.0 / 30240, -1.0 / 1209600, 1.0 / 47900160,
+                                    -691.0 / 1307674368000.0, 1.0 / 74724249600.0, -3617.0 / 10670622842880000.0,
+                                    43867.0 / 5109094217170944000.0, -174611.0 / 802857662698291200000.0};
+  const double xs = pow(x, -s), ix2 = 1.0 / (x * x);
+  double tail = x * xs / (s - 1.0) + 0.5 * xs;
+  double poch = s, pw = xs / x;  // (s)_(2j-1) and x^(-s-2j+1) for j = 1
+  for (int j = 1; j <= 10; ++j) {
+    tail += B2J_OVER_FACT[j - 1] * poch * pw;
+    poch *= (s + (double)(2 * j - 1)) * (s + (double)(2 * j));
+    pw *= ix2;
+  }
+  z += tail;
+  double fact = 1.0;
+  for (int k = 2; k <= n; ++k) fact *= (double)k;
+  return ((n & 1) ? 1.0 : -1.0) * fact * z;
+}

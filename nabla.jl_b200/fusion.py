@@ -64,6 +64,8 @@ def partial_needs(op, wrt=0):
         return _A | _B
     if name == "beta":
         return _A | _B | _Y
+    if name in ("besselj", "bessely", "besseli", "besselk", "polygamma"):
+        return 0 if wrt == 0 else (_A | _B)   # the partial in the order is the constant NaN
     return _A
 
 

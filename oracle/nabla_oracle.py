@@ -375,6 +375,34 @@ _BINARY = {
              lambda x, y: _sp.beta(x, y) * (_sp.digamma(y) - _sp.digamma(x + y))),
 }
 
+_NAN = lambda x, y: np.nan + 0.0 * (x + y)  # noqa: E731
+
+
+def _polygamma_int(n, x):
+    """polygamma(n, x) for integer n >= 0 and any real x that is not a pole: the defining sum
+    (-1)^(n+1) n! sum_k (x+k)^-(n+1) shifts x to the positive axis, where scipy's polygamma applies."""
+    n, x = np.broadcast_arrays(np.asarray(n, dtype=np.float64), np.asarray(x, dtype=np.float64))
+    out = np.empty(x.shape)
+    for idx in np.ndindex(x.shape):
+        ni, xi, acc = int(n[idx]), float(x[idx]), 0.0
+        while xi <= 0.0:
+            acc += (1.0 / xi if ni == 0 else xi ** -(ni + 1.0))
+            xi += 1.0
+        fact = math.factorial(ni)
+        out[idx] = (_sp.digamma(xi) - acc) if ni == 0 else (_sp.polygamma(ni, xi) + (-1.0) ** (ni + 1) * fact * acc)
+    return out if out.ndim else float(out)
+
+
+# Differentiable in the second argument only (test/runtests.jl:43-47; DiffRules gives NaN for the order):
+# name: (f, d/d(order) = NaN, d/dx)
+_SECOND_ARG_ONLY = {
+    "besselj": (lambda n, x: _sp.jv(n, x), _NAN, lambda n, x: (_sp.jv(n - 1, x) - _sp.jv(n + 1, x)) / 2.0),
+    "bessely": (lambda n, x: _sp.yv(n, x), _NAN, lambda n, x: (_sp.yv(n - 1, x) - _sp.yv(n + 1, x)) / 2.0),
+    "besseli": (lambda n, x: _sp.iv(n, x), _NAN, lambda n, x: (_sp.iv(n - 1, x) + _sp.iv(n + 1, x)) / 2.0),
+    "besselk": (lambda n, x: _sp.kv(n, x), _NAN, lambda n, x: -(_sp.kv(n - 1, x) + _sp.kv(n + 1, x)) / 2.0),
+    "polygamma": (_polygamma_int, _NAN, lambda n, x: _polygamma_int(np.asarray(n) + 1, x)),
+}
+
 
 class ScalarFn:
     """A named scalar function that accepts floats, ndarrays, Duals and scalar Nodes."""
@@ -386,7 +414,7 @@ class ScalarFn:
         if arity == 1:
             self.f, self.df = _UNARY[name]
         else:
-            self.f, self.dfx, self.dfy = _BINARY[name]
+            self.f, self.dfx, self.dfy = (_BINARY.get(name) or _SECOND_ARG_ONLY[name])
 
     def __repr__(self):
         return f"<oracle scalar fn {self.name}>"
@@ -418,12 +446,15 @@ for _n in _UNARY:
 for _n in _BINARY:
     globals()["max_" if _n == "max" else "min_" if _n == "min" else "pow_" if _n == "pow" else _n] = \
         ScalarFn(_n, 2)
+for _n in _SECOND_ARG_ONLY:
+    globals()[_n] = ScalarFn(_n, 2)
 UNARY_NAMES = tuple(_UNARY)
 BINARY_NAMES = tuple(_BINARY)
+SECOND_ARG_ONLY_NAMES = tuple(_SECOND_ARG_ONLY)
 
 
 def scalar_fn(name):
-    return ScalarFn(name, 1 if name in _UNARY else 2)
+    return ScalarFn(name, 1 if name in _UNARY else 2)  # (binary: _BINARY or _SECOND_ARG_ONLY)
 
 
 # --------------------------------------------------------------------------------------------

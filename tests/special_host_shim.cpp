@@ -8,3 +8,8 @@ double sf_invdigamma(double y) { return nb_invdigamma(y); }
 double sf_digamma_pos(double x) { return nb_sf_digamma_pos(x); }
 double sf_trigamma_pos(double x) { return nb_sf_trigamma_pos(x); }
 }
+extern "C" {
+double sf_bessel(int which, double nu, double x) { return nb_bessel(which, nu, x); }
+double sf_bessel_dx(int which, double nu, double x) { return nb_bessel_dx(which, nu, x); }
+double sf_polygamma(double n, double x) { return nb_polygamma_n(n, x); }
+}

@@ -203,6 +203,31 @@ def test_binary_catalogue_and_scalar_mixes(nb, orc, dtype):
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_second_arg_only_catalogue(nb, orc, dtype):
+    # test/sensitivities/scalar.jl:38-49 — besselj/y/i/k(n, x), polygamma(n, x): integer first argument 0..5 (a
+    # constant: not differentiable), sensitivity in x; generic kernels (ragged size) and the lean ones (64 x 36).
+    for name in orc.SECOND_ARG_ONLY_NAMES:
+        for n in range(6):
+            rng = np.random.default_rng(zlib.crc32(name.encode()) + n)
+            for shape in ((203,), (64, 36)):
+                x = rng.uniform(0.15, 3.0, shape)
+                if name in ("besselj", "besseli") and len(shape) == 1:
+                    x = x * rng.choice([-1.0, 1.0], shape)
+                ybar = rng.standard_normal(shape)
+                try:
+                    check_case(nb, orc, lambda ns, a: ns.broadcast(_fn(ns, name), n, a), [x], ybar, dtype)
+                except AssertionError as e:
+                    raise AssertionError(f"{name}({n}, x) {shape} ({np.dtype(dtype).name}): {e}") from e
+    # a Node in the order position gets DiffRules' NaN; x keeps its sensitivity
+    ctx = nb.get_context()
+    nu, x = np.full(50, 2.0), np.linspace(0.5, 2.5, 50)
+    got = nb.nabla(lambda a, b: nb.sum(nb.broadcast(nb.besselk, a, b)))(nu.astype(dtype), x.astype(dtype))
+    assert np.all(np.isnan(_np(got[0])))
+    ref = orc.nabla(lambda a, b: orc.sum(orc.broadcast(orc.besselk, a, b)))(nu, x)
+    close(_np(got[1]), ref[1], dtype)
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
 def test_catalogue_on_lean_kernels(nb, orc, dtype):
     # The same scalar catalogue at vector-friendly sizes (multiples of the 128-bit vector, 16-byte aligned
     # buffers), where every single primitive runs on the compile-time-specialised lean kernels

@@ -39,7 +39,8 @@ def test_opcodes_match_header():
     assert ops["add"] == 64 and ops["atan2"] == 73
     assert ops["beta"] == 74 and ops["gamma"] == 96 and ops["erfcx"] == 105
     assert ops["airyai"] == 106 and ops["invdigamma"] == 112 and ops["sf_end"] == 113
-    assert len(scalar.UNARY) == 58 + 17 and len(scalar.BINARY) == 11   # + every unary of SpecialFunctions the reference lists
+    assert ops["besselj"] == 75 and ops["polygamma"] == 79 and ops["binary_end"] == 80
+    assert len(scalar.UNARY) == 58 + 17 and len(scalar.BINARY) == 16   # + every SpecialFunctions entry the reference lists
     assert "sf_begin" not in scalar.UNARY and "binary_end" not in scalar.BINARY
 
 
@@ -83,6 +84,33 @@ def test_special_functions_source_on_the_host(tmp_path):
     for y in np.concatenate([rng.uniform(-50, 10, 300), rng.uniform(-3.1, 3.1, 100), [-2.22, -2.2200001, 0.0, 100.0, -1e6]]):
         G = mp.mpf(L.sf_invdigamma(float(y)))
         assert abs(mp.digamma(G) - mp.mpf(float(y))) <= 1e-14 * mp.polygamma(1, G) * G, y   # relative error of x
+    # integer-order Bessel functions (all regimes: series, trapezoid rules, large-argument expansions) and polygamma
+    L.sf_bessel.restype, L.sf_bessel.argtypes = C.c_double, [C.c_int, C.c_double, C.c_double]
+    L.sf_bessel_dx.restype, L.sf_bessel_dx.argtypes = C.c_double, [C.c_int, C.c_double, C.c_double]
+    L.sf_polygamma.restype, L.sf_polygamma.argtypes = C.c_double, [C.c_double, C.c_double]
+    mp.mp.dps = 30
+    ref = [mp.besselj, mp.bessely, mp.besseli, mp.besselk]
+    xs = np.concatenate([rng.uniform(1e-3, 3, 12), rng.uniform(3, 50, 20), rng.uniform(50, 300, 8)])
+    for w in range(4):
+        for n in (-1, 0, 1, 2, 5, 7):
+            for x in xs:
+                for X in ((float(x), -float(x)) if w in (0, 2) else (float(x),)):
+                    r = ref[w](n, mp.mpf(X))
+                    amp = abs(r)
+                    if w <= 1 and abs(X) > abs(n):   # oscillatory: relative to the modulus
+                        amp = mp.sqrt(mp.besselj(n, abs(X)) ** 2 + mp.bessely(n, abs(X)) ** 2)
+                    assert abs(L.sf_bessel(w, float(n), X) - r) <= 2e-13 * amp, (w, n, X)
+        for n in range(6):
+            for x in rng.uniform(0.1, 3.1, 5):
+                r = mp.diff(lambda t: ref[w](n, t), mp.mpf(float(x)))
+                assert abs(L.sf_bessel_dx(w, float(n), float(x)) - r) <= 1e-13 * max(abs(r), 1e-3), (w, n, x)
+    assert np.isnan(L.sf_bessel(0, 0.5, 1.0)) and L.sf_bessel(3, 2.0, 0.0) == float("inf") and np.isnan(L.sf_bessel(1, 0.0, -1.0))
+    for n in range(9):
+        for x in np.concatenate([rng.uniform(0.05, 30, 25), rng.uniform(-6, 0, 15), [1e-3, 100.0, 1e4]]):
+            r = mp.polygamma(n, mp.mpf(float(x)))
+            cond = min(1.0, 10 * abs(x - round(x))) if x < 0 else 1.0    # conditioning next to the poles
+            assert abs(L.sf_polygamma(float(n), float(x)) - r) * cond <= 1e-13 * abs(r), (n, x)
+    assert np.isnan(L.sf_polygamma(2.0, -3.0)) and np.isnan(L.sf_polygamma(1.5, 1.0))
 
 
 def test_tracer_single_primitive_and_constants():

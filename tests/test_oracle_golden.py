@@ -195,6 +195,26 @@ def test_binary_catalogue_check_errs(name):
     np.testing.assert_allclose(r1[b_], r2[b2], rtol=1e-12)
 
 
+@pytest.mark.parametrize("name", o.SECOND_ARG_ONLY_NAMES)
+def test_second_arg_only_catalogue_matches_fd(name):
+    # test/sensitivities/scalar.jl:38-49 — besseli/j/k/y and polygamma: the first argument is an integer 0..5 and is
+    # not differentiable; the rule in the second argument against central differences.
+    f = getattr(o, name)
+    rng = np.random.default_rng(11)
+    for n in range(6):
+        x = rng.uniform(0.2, 3.0, 30)
+        x_ = o.Leaf(o.Tape(), x)
+        g = o.nabla(bc(f, n, x_), np.ones_like(x))[x_]
+        h = 1e-6
+        fd = (f.f(n, x + h) - f.f(n, x - h)) / (2 * h)
+        np.testing.assert_allclose(g, fd, rtol=2e-5, atol=1e-7)
+    # a Node in the order position gets DiffRules' NaN
+    t = o.Tape()
+    n_, x_ = o.Leaf(t, np.full(4, 2.0)), o.Leaf(t, np.linspace(0.5, 2.0, 4))
+    r = o.nabla(bc(f, n_, x_), np.ones(4))
+    assert np.all(np.isnan(r[n_])) and np.all(np.isfinite(r[x_]))
+
+
 def test_ternary_broadcast_and_fmad():
     # test/sensitivities/functional/functional.jl:68-78
     rng = np.random.default_rng(0)
