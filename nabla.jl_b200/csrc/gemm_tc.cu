@@ -7,16 +7,21 @@
 // forward W*X, Abar = Ybar*B' ('N','T'), Bbar = A'*Ybar ('T','N'); beta = 1 is the in-place accumulate.
 //
 // Design (sm_100a):
-//   * persistent kernel, one CTA per SM, tile 128 x BN (BN = 256 or 128), K step = one 128-byte
-//     swizzle row; 6 warps: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread)
-//     + TMEM owner, warps 2..5 = epilogue (TMEM -> registers -> coalesced column-major stores).
+//   * two persistent kernels.  k_gemm_tc: one CTA per SM, tile 128 x BN (BN = 256 or 128).  k_gemm_tc_pair
+//     (large products, the default there): one CTA PAIR (2-CTA cluster, tcgen05 cta_group::2) per two SMs, tile
+//     256 x 256, each CTA stages half of B and its own half of A, the leader's MMA thread issues for both and
+//     releases the stages of both CTAs with multicast commits.  K step = one 128-byte swizzle row.
+//     12 warps: warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (one elected thread) + TMEM owner, warps 2-3
+//     idle (they give their registers away, setmaxnreg), warps 4..11 = epilogue (TMEM -> registers -> stores).
 //   * operands are staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzles) straight from the
 //     column-major arrays: a non-transposed A is "MN-major", a transposed A is "K-major" (the UMMA
 //     descriptors carry the major-ness, so no transposed copy of any operand is ever made).
 //   * tiles are handed out DYNAMICALLY: the producer thread takes the next tile index from a global
-//     atomic counter and publishes it to the MMA and epilogue roles through a 4-slot shared-memory ring
-//     (mbarrier full/empty), so a CTA that starts late or shares its SM with an NCCL kernel (the
-//     overlapped allreduce) simply processes fewer tiles instead of delaying the whole GEMM.
+//     atomic counter and publishes it to the MMA and epilogue roles (of both CTAs of a pair) through a
+//     shared-memory ring (mbarrier full/empty), so a CTA that starts late or shares its SM with an NCCL kernel
+//     (the overlapped allreduce) simply processes fewer tiles instead of delaying the whole GEMM.  Tiles are
+//     rasterised in groups of group_m tile rows sized to the L2, and consecutive tiles walk K in alternating
+//     directions (serpentine) so the panel tail of one tile is the head of the next.
 //   * accumulators live in TMEM (2 x BN columns, double-buffered so the epilogue of chunk i overlaps
 //     the main loop of chunk i+1); smem ring of STAGES stages guarded by full/empty mbarriers;
 //     tcgen05.commit releases smem stages and publishes finished accumulators.
@@ -28,13 +33,21 @@
 //                       ~1e-5 error, 3 kind::f16 passes at twice the tf32 rate.  The tensor pipe is
 //                       power-limited on this part (1 kW cap), so tensor work per useful FLOP is the
 //                       cost that matters: half of 3xTF32's time and energy.  The split copies are this
-//                       kernel's own temporaries, so their leading dimension is padded to a multiple of
+//                       kernel's own temporaries (cached per operand buffer, or emitted by the epilogue of the
+//                       product that wrote the operand), so their leading dimension is padded to a multiple of
 //                       8 elements: ANY lda/ldb/alignment works (e.g. the 10-row output layer).
 //   * the tensor core adds each product group into the FP32 accumulator with truncation, so the error
 //     of one long accumulation grows linearly in K (measured 2.9e-5 at K = 4096 for tf32).  K is
 //     therefore processed in chunks of KCHUNK: every chunk gets a fresh TMEM accumulator and the
-//     epilogue folds it into C with a correctly rounded FP32 add (C tile re-read from L2), which keeps
-//     the error at the single-chunk level for any K (the Abar GEMMs have K = batch = 32768).
+//     epilogue warps fold it into a running sum held in REGISTERS with a correctly rounded FP32 add (C is
+//     written once, after the last chunk), which keeps the error at the single-chunk level for any K
+//     (the Abar GEMMs have K = batch = 32768).
+//   * fused epilogues (nb_gemm_fused): + bias and activation on the way out (the forward Branches `.+ b`,
+//     `tanh.`), `.* f'(y)` of a saved activation (their pullbacks), per-row sums (the bias sensitivity) and the
+//     bf16 hi/lo split of the result for the next product — 16-byte stores after a 4 x 4 transpose inside each
+//     quad of lanes.
+//   * kind::i8 instances of the same kernels compute the exact int8 slice products of the Float64 Ozaki split
+//     (ozaki.cu): int32 TMEM accumulators, Float64 epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -57,7 +70,7 @@ constexpr int REGS_WG0 = 80, REGS_EPI = 208;  // 128*80 + 256*208 <= 384*168
 // KIND_I8: signed 8-bit operands, exact int32 accumulation (kind::i8) — the slice products of the Float64 Ozaki
 // split (ozaki.cu); K-major operands only, one pass, no K chunking (the int32 accumulator is exact).
 // KIND_I8ALL: every level of the Ozaki split in ONE launch (chunk table in GemmArgs, Float64 running sum in the
-// epilogue registers): mid-size Float64 products, where six launches and six read-modify-writes of C dominate.
+// epilogue registers): mid-size Float64 products, where one launch and one read-modify-write of C per level dominate.
 enum { KIND_TF32 = 0, KIND_3XTF32 = 1, KIND_BF16X3 = 2, KIND_I8 = 3, KIND_I8ALL = 4 };
 __host__ __device__ constexpr bool kind_is_i8(int k) { return k == KIND_I8 || k == KIND_I8ALL; }
 template <int KIND>
