@@ -14,6 +14,7 @@ Tolerances (BASELINE.json north_star): rtol 1e-10 for Float64, 1e-4 for Float32.
 results are compared with the oracle evaluated in Float64 on the same (Float32-representable)
 inputs, so the 1e-4 bounds the device's own error rather than the difference of two roundings."""
 import math
+import os
 import zlib
 
 import numpy as np
@@ -200,6 +201,33 @@ def test_binary_catalogue_and_scalar_mixes(nb, orc, dtype):
             check_case(nb, orc, lambda ns, b: ns.broadcast(_fn(ns, name), 0.6, b), [y], ybar, dtype)
         except AssertionError as e:
             raise AssertionError(f"{name} ({np.dtype(dtype).name}): {e}") from e
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_scalar_catalogue_against_mpmath_golden(nb, dtype):
+    # tests/golden/scalar_catalogue_mpmath.json: 50-digit mpmath values of every catalogue function and its
+    # derivative at the reference's test points (src/finite_differencing.jl:175-179) — no oracle, no SciPy involved.
+    import json
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scalar_catalogue_mpmath.json")))
+
+    def one(fn, consts, t, tag):
+        x = np.asarray(t["x"], dtype=dtype)
+        if x.size == 0:
+            return
+        # (Float32: the table is evaluated at the Float64 points; compare at the Float32 bar)
+        leaf = nb.Leaf(nb.Tape(), x)
+        y = nb.broadcast(fn, *consts, leaf)
+        try:
+            close(_np(nb.unbox(y)), t["f"], dtype)
+            close(_np(nb.nabla(y, nb.oneslike(y))[leaf]), t["df"], dtype)
+        except AssertionError as e:
+            raise AssertionError(f"{tag} ({np.dtype(dtype).name}): {e}") from e
+
+    for name, t in G["unary"].items():
+        one(_fn(nb, name), (), t, name)
+    for name, rows in G["second_arg_only"].items():
+        for row in rows:
+            one(_fn(nb, name), (row["n"],), row, f"{name}({row['n']}, x)")
 
 
 @pytest.mark.parametrize("dtype", [np.float64, np.float32])

@@ -195,6 +195,31 @@ def test_binary_catalogue_check_errs(name):
     np.testing.assert_allclose(r1[b_], r2[b2], rtol=1e-12)
 
 
+def test_scalar_catalogue_against_mpmath_golden():
+    """tests/golden/scalar_catalogue_mpmath.json (50-digit mpmath, generated by tests/golden/make_scalar_catalogue.py):
+    every function of test/runtests.jl:28-52 and its derivative at the reference's own test points.  The oracle's
+    values AND its rules (through the tape: broadcast forward, sensitivity for a seed of ones) must agree to 1e-13."""
+    import json
+    import os
+    G = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "scalar_catalogue_mpmath.json")))
+    assert set(o.UNARY_NAMES) <= set(G["unary"]) and set(o.SECOND_ARG_ONLY_NAMES) == set(G["second_arg_only"])
+    for name in o.UNARY_NAMES:
+        t = G["unary"][name]
+        x = np.array(t["x"])
+        x_ = o.Leaf(o.Tape(), x)
+        s = bc(getattr(o, "abs_" if name == "abs" else name), x_)
+        np.testing.assert_allclose(o.unbox(s), t["f"], rtol=1e-13, atol=0, err_msg=name)
+        np.testing.assert_allclose(o.nabla(s, np.ones_like(x))[x_], t["df"], rtol=1e-13, atol=0, err_msg=name)
+    for name in o.SECOND_ARG_ONLY_NAMES:
+        for row in G["second_arg_only"][name]:
+            x = np.array(row["x"])
+            x_ = o.Leaf(o.Tape(), x)
+            s = bc(getattr(o, name), row["n"], x_)
+            np.testing.assert_allclose(o.unbox(s), row["f"], rtol=1e-13, atol=0, err_msg=f"{name}({row['n']}, x)")
+            np.testing.assert_allclose(o.nabla(s, np.ones_like(x))[x_], row["df"], rtol=1e-13, atol=0,
+                                       err_msg=f"d/dx {name}({row['n']}, x)")
+
+
 @pytest.mark.parametrize("name", o.SECOND_ARG_ONLY_NAMES)
 def test_second_arg_only_catalogue_matches_fd(name):
     # test/sensitivities/scalar.jl:38-49 — besseli/j/k/y and polygamma: the first argument is an integer 0..5 and is
