@@ -202,6 +202,114 @@ function allreduce_sum!(bufs::Vector{<:DevArray{T}}) where {T}
                 ctx.h, length(bufs), ptrs, counts, nbdtype(T)), ctx)
 end
 
-function program end   # scalar-function lowering (nb_prog_create); see INTEGRATION.md
+# ---- scalar-function lowering: `program(f, nargs)` -> nb_prog* (nb_prog_create) ---------------------
+#      The tested twin is nabla.jl_b200/scalar.py (compile_scalar).  A catalogue function maps to its opcode; any
+#      other scalar function is called ONCE on symbolic scalars that record a register program (with structural
+#      common-subexpression elimination); functions that branch on values or call primitives outside the
+#      catalogue throw MethodError, as an un-ruled function does in Nabla (test/core.jl:159).
+import SpecialFunctions
+const SF = SpecialFunctions
+const NB_MAX_ARGS, NB_MAX_INSTR, NB_MAX_CONSTS = 6, 32, 16
+
+# function => nb_op (include/nabla_cuda.h; the values are ABI).  The list is test/runtests.jl:28-52.
+const UNARY_OPS = Dict{Any,Int32}(
+    identity => 0, abs => 2, abs2 => 3, sqrt => 4, cbrt => 5, inv => 6, exp => 7, exp2 => 8, exp10 => 9,
+    expm1 => 10, log => 11, log2 => 12, log10 => 13, log1p => 14, sin => 15, cos => 16, tan => 17, sec => 18,
+    csc => 19, cot => 20, sinh => 21, cosh => 22, tanh => 23, sech => 24, csch => 25, coth => 26, asin => 27,
+    acos => 28, atan => 29, asec => 30, acsc => 31, acot => 32, asinh => 33, acosh => 34, atanh => 35,
+    asech => 36, acsch => 37, acoth => 38, sind => 39, cosd => 40, tand => 41, secd => 42, cscd => 43,
+    cotd => 44, asind => 45, acosd => 46, atand => 47, asecd => 48, acscd => 49, acotd => 50, sinpi => 51,
+    cospi => 52, deg2rad => 53, rad2deg => 54,
+    SF.erf => 56, SF.erfc => 57, SF.gamma => 96, SF.digamma => 97, SF.trigamma => 98, SF.besselj0 => 99,
+    SF.besselj1 => 100, SF.bessely0 => 101, SF.bessely1 => 102, SF.erfinv => 103, SF.erfcinv => 104,
+    SF.erfcx => 105, SF.airyai => 106, SF.airyaiprime => 107, SF.airybi => 108, SF.airybiprime => 109,
+    SF.dawson => 110, SF.erfi => 111, SF.invdigamma => 112)
+const BINARY_OPS = Dict{Any,Int32}(
+    (+) => 64, (-) => 65, (*) => 66, (/) => 67, (\) => 68, (^) => 69, hypot => 70, max => 71, min => 72,
+    SF.beta => 74,
+    # differentiable in the second argument only; the first is the integer order (test/runtests.jl:43-47)
+    SF.besselj => 75, SF.bessely => 76, SF.besseli => 77, SF.besselk => 78, SF.polygamma => 79)
+const OP_NEG, OP_LOGISTIC, OP_ATAN2 = Int32(1), Int32(55), Int32(73)
+
+struct Sym <: Real
+    kind::Symbol                 # :arg, :const, :op
+    op::Int32
+    a::Union{Sym,Nothing}
+    b::Union{Sym,Nothing}
+    value::Float64
+    index::Int32
+end
+symarg(i) = Sym(:arg, 0, nothing, nothing, 0.0, i)
+symconst(v::Real) = Sym(:const, 0, nothing, nothing, Float64(v), 0)
+symop(op, a, b=nothing) = Sym(:op, op, a, b, 0.0, 0)
+Base.promote_rule(::Type{Sym}, ::Type{<:Real}) = Sym
+Base.convert(::Type{Sym}, v::Real) = symconst(v)
+Base.convert(::Type{Sym}, s::Sym) = s
+for (f, op) in UNARY_OPS
+    f === identity && continue
+    m = parentmodule(f); n = nameof(f)
+    @eval $m.$n(x::Sym) = symop($op, x)
+end
+Base.:-(x::Sym) = symop(OP_NEG, x)
+for (f, op) in BINARY_OPS
+    m = parentmodule(f); n = nameof(f)
+    @eval $m.$n(x::Sym, y::Sym) = symop($op, x, y)
+    @eval $m.$n(x::Sym, y::Real) = symop($op, x, symconst(y))
+    @eval $m.$n(x::Real, y::Sym) = symop($op, symconst(x), y)
+end
+Base.atan(y::Sym, x::Sym) = symop(OP_ATAN2, y, x)
+Base.literal_pow(::typeof(^), x::Sym, ::Val{p}) where {p} = symop(BINARY_OPS[^], x, symconst(p))
+# comparisons would make the trace depend on values: refuse
+Base.isless(::Sym, ::Sym) = throw(MethodError(isless, (Sym, Sym)))
+Base.:<(::Sym, ::Real) = throw(MethodError(<, (Sym, Real)))
+
+const PROGRAMS = Dict{Tuple{UInt,Int},Ptr{Cvoid}}()
+
+function program(f, nargs::Int)
+    get!(PROGRAMS, (objectid(f), nargs)) do
+        nargs <= NB_MAX_ARGS || throw(MethodError(f, ntuple(_ -> Sym, nargs)))
+        args = [symarg(Int32(i - 1)) for i in 1:nargs]
+        root = if nargs == 1 && haskey(UNARY_OPS, f)
+            f === identity ? args[1] : symop(UNARY_OPS[f], args[1])
+        elseif nargs == 2 && haskey(BINARY_OPS, f)
+            symop(BINARY_OPS[f], args[1], args[2])
+        else
+            convert(Sym, f(args...))          # trace
+        end
+        ops, ia, ib, consts = Int32[], Int32[], Int32[], Float64[]
+        memo = Dict{Tuple{Int32,Int32,Int32},Int32}()
+        function emit(s::Sym)::Int32
+            s.kind === :arg && return s.index
+            if s.kind === :const
+                k = findfirst(c -> c === s.value, consts)
+                k === nothing && (push!(consts, s.value); k = length(consts))
+                length(consts) <= NB_MAX_CONSTS || throw(MethodError(f, ntuple(_ -> Sym, nargs)))
+                return Int32(-k)                # consts[c] is named -(c+1), c zero-based
+            end
+            a = emit(s.a)
+            b = s.b === nothing ? Int32(0) : emit(s.b)
+            get!(memo, (s.op, a, b)) do
+                push!(ops, s.op); push!(ia, a); push!(ib, b)
+                length(ops) <= NB_MAX_INSTR || throw(MethodError(f, ntuple(_ -> Sym, nargs)))
+                Int32(nargs + length(ops) - 1)
+            end
+        end
+        r = emit(root)
+        if root.kind === :const                 # constant function: c + 0 keeps operand 0 for the shape
+            push!(ops, BINARY_OPS[+]); push!(ia, r); push!(ib, emit(symconst(0.0)))
+        elseif root.kind === :arg && r != 0     # f(x, y) = y
+            push!(ops, Int32(0)); push!(ia, r); push!(ib, Int32(0))
+        end
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        st = ccall((:nb_prog_create, LIB), Int32,
+                   (Int32, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Int32}, Int32, Ptr{Float64}, Ref{Ptr{Cvoid}}),
+                   nargs, length(ops), ops, ia, ib, length(consts), consts, out)
+        st == 0 || throw(MethodError(f, ntuple(_ -> Sym, nargs)))   # NB_ERR_UNSUPPORTED: outside the catalogue
+        out[]
+    end
+end
+# logistic(x) = 1 / (1 + exp(-x)) (examples/mlp.jl:42) traces to four instructions; the Python twin's peephole
+# (scalar.py:_simplify) rewrites that pattern to the single NB_OP_LOGISTIC the fused epilogues know — do the same
+# here by registering the user's function:  NablaCUDA.UNARY_OPS[logistic] = NablaCUDA.OP_LOGISTIC.
 
 end # module
