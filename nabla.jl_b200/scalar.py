@@ -10,6 +10,7 @@ raises MethodError) — there is no CPU fallback."""
 import ctypes as C
 import math
 import numbers
+import types
 
 from . import _lib
 from ._lib import NB_MAX_ARGS, NB_MAX_CONSTS, NB_MAX_INSTR, OPCODES, UnsupportedOp, check
@@ -149,26 +150,77 @@ class Program:
 _TRACE_CACHE = {}
 
 
+_CODE_NAMES = {}
+_KEY_DEPTH = 4
+
+
+def _code_names(code):
+    """Global / attribute names a code object (and the code objects nested in it) refers to."""
+    names = _CODE_NAMES.get(code)
+    if names is None:
+        acc = list(code.co_names)
+        for c in code.co_consts:
+            if isinstance(c, types.CodeType):
+                acc.extend(_code_names(c))
+        names = _CODE_NAMES[code] = tuple(dict.fromkeys(acc))
+    return names
+
+
+def _value_key(v, depth):
+    """Key component of a value a traced function captures (closure cell or global), or None when the value cannot
+    be keyed SAFELY.  Numbers go in by value, catalogue primitives by name, modules / builtins / classes as the
+    objects themselves (the key then keeps them alive, so no identity is ever reused), plain functions structurally
+    (recursively).  Anything mutable or opaque — dicts, lists, arrays, instances — makes the function uncacheable:
+    an identity key would go stale when the object is mutated or when its id is reused after it is freed."""
+    if isinstance(v, bool):
+        return ("b", v)
+    if isinstance(v, numbers.Real):
+        return ("n", float(v))
+    if isinstance(v, ScalarFn):
+        return ("prim", v.name)
+    if isinstance(v, (types.ModuleType, types.BuiltinFunctionType, type)):
+        return ("o", v)
+    if isinstance(v, types.FunctionType) and depth < _KEY_DEPTH:
+        k = _function_key(v, depth + 1)
+        return None if k is None else ("f", k)
+    return None
+
+
+def _function_key(f, depth=0):
+    code = getattr(f, "__code__", None)
+    if code is None or getattr(f, "__defaults__", None) or getattr(f, "__kwdefaults__", None):
+        return None
+    parts = [code]
+    for c in (getattr(f, "__closure__", None) or ()):
+        try:
+            k = _value_key(c.cell_contents, depth)
+        except ValueError:   # empty cell
+            return None
+        if k is None:
+            return None
+        parts.append(k)
+    g = getattr(f, "__globals__", None) or {}
+    for name in _code_names(code):
+        if name in g:      # (other names are attributes or builtins)
+            k = _value_key(g[name], depth)
+            if k is None:
+                return None
+            parts.append((name, k))
+    return tuple(parts)
+
+
 def _trace_key(f, nargs, const_args):
     """Cache key of a traced function: catalogue primitives by name; Python functions by code object plus the
-    values (numbers) / identities (anything else) of their closure cells and defaults — a lambda re-created by the
-    same source line with the same captured values traces to the same program."""
+    VALUES of everything the code can see — closure cells and referenced globals (`_value_key`) — so that a lambda
+    re-created by the same source line with the same captured values hits the cache, while a rebound cell, a changed
+    global or any captured mutable object never yields a stale program (such functions are simply re-traced)."""
     consts = tuple(sorted((i, float(v)) for i, v in const_args.items()))
     if isinstance(f, ScalarFn):
         return ("prim", f.name, nargs, consts)
-    code = getattr(f, "__code__", None)
-    if code is None:
+    k = _function_key(f)
+    if k is None:
         return None
-    cells = []
-    for c in (getattr(f, "__closure__", None) or ()):
-        try:
-            v = c.cell_contents
-        except ValueError:
-            return None
-        cells.append(("n", float(v)) if isinstance(v, numbers.Real) and not isinstance(v, bool) else ("o", id(v)))
-    if getattr(f, "__defaults__", None) or getattr(f, "__kwdefaults__", None):
-        return None
-    return ("fn", code, tuple(cells), nargs, consts)
+    return ("fn", k, nargs, consts)
 
 
 def compile_scalar(f, nargs, const_args=None):
@@ -185,7 +237,7 @@ def compile_scalar(f, nargs, const_args=None):
     if key is not None:
         if len(_TRACE_CACHE) > 4096:
             _TRACE_CACHE.clear()
-        _TRACE_CACHE[key] = (prog, f)   # (keeps f alive: ids of closure contents stay unique while cached)
+        _TRACE_CACHE[key] = (prog,)
     return prog
 
 

@@ -2,6 +2,7 @@
 declares, the opcode table matches, the scalar tracer lowers functions correctly, and the product
 path fails loudly (no CPU fallback) when no GPU is present."""
 import ctypes
+import math
 import os
 import subprocess
 
@@ -138,6 +139,156 @@ def test_tracer_composite_program_with_cse():
         s = nb.sin(x)
         return s * s
     assert len(nb.compile_scalar(h, 1).ops) == 2    # shared sub-expression emitted once
+
+
+def _run_program(orc, P, xs):
+    """Python restatement of nb_prog_eval / nb_prog_grad (csrc/ops.cuh): value of the program and d(value)/d(operand k),
+    with the catalogue's f / partials taken from the oracle's tables."""
+    import numpy as np
+    names = {v: k for k, v in _lib.OPCODES.items()}
+    slot = lambda vals, i: vals[i] if i >= 0 else np.float64(P.consts[-i - 1])
+    vals = [np.asarray(x, dtype=np.float64) for x in xs]
+    for op, a, b in zip(P.ops, P.a, P.b):
+        n = names[op]
+        if n == "logistic":
+            vals.append(1.0 / (1.0 + np.exp(-slot(vals, a))))
+        elif n in orc._UNARY:
+            vals.append(orc._UNARY[n][0](slot(vals, a)))
+        else:
+            vals.append(orc._BINARY[n][0](slot(vals, a), slot(vals, b)))
+    y = vals[-1] if P.ops else vals[0]
+    adj = [np.zeros_like(y) for _ in vals]
+    adj[-1 if P.ops else 0] = np.ones_like(y)
+    for i in range(len(P.ops) - 1, -1, -1):
+        n, a, b, g = names[P.ops[i]], P.a[i], P.b[i], adj[P.nargs + i]
+        if n == "logistic":
+            yy = vals[P.nargs + i]
+            adj[a] = adj[a] + g * yy * (1 - yy) if a >= 0 else adj[a]
+        elif n in orc._UNARY:
+            if a >= 0:
+                adj[a] = adj[a] + g * orc._UNARY[n][1](slot(vals, a))
+        else:
+            _, dx, dy = orc._BINARY[n]
+            if a >= 0:
+                adj[a] = adj[a] + g * dx(slot(vals, a), slot(vals, b))
+            if b >= 0:
+                adj[b] = adj[b] + g * dy(slot(vals, a), slot(vals, b))
+    return y, adj[:P.nargs]
+
+
+def test_tracer_random_expressions_evaluate_and_differentiate_correctly(orc):
+    """Property test of the tracer (operator overloads, operand swaps, constant pool, structural CSE, peephole
+    rewrites): 150 random scalar expressions are traced to programs, the programs are run by a Python restatement
+    of the device interpreter, and value / gradient are compared with the expression evaluated directly in NumPy
+    and differentiated by central differences."""
+    import numpy as np
+    rng = np.random.default_rng(2024)
+    un = ["tanh", "sin", "cos", "exp", "abs2", "atan", "logistic", "neg", "sinh"]
+
+    def gen(depth, nargs):
+        """-> (callable over a namespace ns and operands) ; bounded values so that nothing overflows"""
+        r = rng.random()
+        if depth == 0 or r < 0.15:
+            k = int(rng.integers(nargs))
+            return lambda ns, xs: xs[k]
+        if r < 0.25:
+            c = float(np.round(rng.uniform(-2, 2), 2))
+            return lambda ns, xs: c
+        if r < 0.55:
+            name = un[int(rng.integers(len(un)))]
+            sub = gen(depth - 1, nargs)
+
+            def u(ns, xs):
+                v = sub(ns, xs)
+                if name == "neg":
+                    return -v
+                if isinstance(v, float):          # a constant subtree: tie it to an operand so both namespaces
+                    v = v + 0 * xs[0]             # see a non-float from here on
+                if name == "logistic":
+                    return 1.0 / (1.0 + ns.exp(-v))
+                if name in ("exp", "sinh"):
+                    v = ns.tanh(v)                # keep the argument bounded
+                return getattr(ns, name)(v)
+            return u
+        l, rr = gen(depth - 1, nargs), gen(depth - 1, nargs)
+        kind = int(rng.integers(5))
+
+        def b(ns, xs):
+            p, q = l(ns, xs), rr(ns, xs)
+            if kind == 0:
+                return p + q
+            if kind == 1:
+                return p - q
+            if kind == 2:
+                return p * q
+            if kind == 3:
+                return p / (1.5 + q * q)
+            return (p * p + 0.5) ** 1.5 if not isinstance(p, float) else p + q
+        return b
+
+    class NP:   # the same expression evaluated directly
+        tanh, sin, cos, exp, atan, sinh = np.tanh, np.sin, np.cos, np.exp, np.arctan, np.sinh
+        abs2 = staticmethod(lambda v: v * v)
+
+    done = 0
+    for trial in range(400):
+        nargs = int(rng.integers(1, 4))
+        expr = gen(4, nargs)
+        f = lambda *xs: expr(nb, list(xs))
+        try:
+            P = nb.compile_scalar(f, nargs)
+        except nb.UnsupportedOp:      # more than 32 instructions / 16 constants: legitimately refused
+            continue
+        except TypeError:
+            continue                  # the expression collapsed to a constant without operands
+        xs = [rng.uniform(-1.5, 1.5, 7) for _ in range(nargs)]
+        y, grads = _run_program(orc, P, xs)
+        ref = expr(NP, xs) + 0 * xs[0]
+        np.testing.assert_allclose(y + 0 * xs[0], ref, rtol=1e-12, atol=1e-12, err_msg=f"trial {trial}")
+        h = 1e-6
+        for k in range(nargs):
+            xp = [x.copy() for x in xs]; xm = [x.copy() for x in xs]
+            xp[k] += h; xm[k] -= h
+            fd = (expr(NP, xp) - expr(NP, xm)) / (2 * h) + 0 * xs[0]
+            np.testing.assert_allclose(grads[k] + 0 * xs[0], fd, rtol=2e-5, atol=2e-7, err_msg=f"trial {trial} arg {k}")
+        done += 1
+        if done == 150:
+            break
+    assert done == 150
+
+
+_SCALE = 2.0   # a module global read by a traced lambda below
+
+
+def test_trace_cache_never_serves_a_stale_program():
+    """The trace cache keys a Python function by its code object and the VALUES of everything the code can see.
+    Regression for identity-based keys: a rebound closure cell (the freed object's id gets reused), a changed global
+    and a mutated captured container must all re-trace; re-creating the same lambda with the same captured values
+    must hit."""
+    global _SCALE
+    consts = lambda p: set(p.consts)
+
+    def make(c):
+        return lambda x: c * nb.tanh(x)
+    p1, p2, p3 = nb.compile_scalar(make(0.5), 1), nb.compile_scalar(make(0.5), 1), nb.compile_scalar(make(0.75), 1)
+    assert p1 is p2 and p3 is not p1 and consts(p3) == {0.75}                 # value-keyed: hit / miss
+    for c in (0.1, 0.2, 0.3, 0.4):                                            # one cell, rebound every iteration
+        inner = make(c)
+        assert consts(nb.compile_scalar(lambda x: inner(x) + 1.0, 1)) == {c, 1.0}
+    f = lambda x: _SCALE * x
+    assert consts(nb.compile_scalar(f, 1)) == {2.0}
+    _SCALE = 3.0
+    try:
+        assert consts(nb.compile_scalar(f, 1)) == {3.0}                       # the global changed: re-traced
+    finally:
+        _SCALE = 2.0
+    box = {"a": 1.5}
+    g = lambda x: box["a"] * x
+    assert consts(nb.compile_scalar(g, 1)) == {1.5}
+    box["a"] = 2.5
+    assert consts(nb.compile_scalar(g, 1)) == {2.5}                           # captured container: never cached
+    assert scalar._trace_key(g, 1, {}) is None and scalar._trace_key(f, 1, {}) is not None
+    assert nb.compile_scalar(nb.tanh, 1) is nb.compile_scalar(nb.tanh, 1)
 
 
 def test_tracer_rejects_unsupported():
