@@ -14,7 +14,7 @@ import numpy as np
 from . import kernels as K
 from ._lib import DimensionMismatch, check
 from .core import Leaf, Node, Primitive, Tape, as_device, nabla, unbox, unthunk, zeroslike
-from .device import DevArray, get_context
+from .device import DevArray
 
 
 class R:

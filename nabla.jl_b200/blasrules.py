@@ -5,8 +5,6 @@ The structured operand is materialised once by ``nb_tri`` (symmetric matrix from
 triangle with a unit / zeroed diagonal) and the products run on the dense GEMM / GEMV kernels; the
 pullbacks follow the reference formulas line by line (``tmp + tmp' - Diagonal(tmp)`` then
 ``tril!/triu!``; transposed products; triangular solves with ``alpha = -1``).  Solves are ``nb_trsm``."""
-import numpy as np
-
 from . import kernels as K
 from ._lib import DimensionMismatch, check
 from .core import Primitive, as_device

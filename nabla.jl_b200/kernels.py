@@ -4,7 +4,7 @@ import ctypes as C
 
 from . import _lib
 from ._lib import NB_MAX_ARGS, check, nb_tensor
-from .device import BroadcastView, DevArray
+from .device import BroadcastView
 
 _T = nb_tensor * NB_MAX_ARGS
 

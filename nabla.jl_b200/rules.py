@@ -10,9 +10,9 @@ import numpy as np
 from . import fusion
 from . import kernels as K
 from ._lib import OPCODES, DimensionMismatch
-from .core import (UNDEF, Branch, Node, Primitive, accumulate, as_device, own, unbox)
+from .core import UNDEF, Node, Primitive, accumulate, as_device, own, unbox
 from .device import BroadcastView, DevArray, get_context
-from .scalar import CATALOGUE, Program, ScalarFn, compile_scalar
+from .scalar import CATALOGUE, ScalarFn, compile_scalar
 
 _ADD, _SUB, _ID, _MUL = OPCODES["add"], OPCODES["sub"], OPCODES["identity"], OPCODES["mul"]
 _LAZY_SUM = __import__("os").environ.get("NB_LAZY_SUM", "1") != "0"

@@ -12,7 +12,6 @@ import math
 import numbers
 import types
 
-from . import _lib
 from ._lib import NB_MAX_ARGS, NB_MAX_CONSTS, NB_MAX_INSTR, OPCODES, UnsupportedOp, check
 
 UNARY = [n for n, v in OPCODES.items() if not n.endswith(("_end", "_begin")) and

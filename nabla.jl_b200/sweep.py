@@ -12,10 +12,9 @@ import ctypes as C
 
 import numpy as np
 
-from . import _lib
 from ._lib import check
 from .core import Leaf, Node, Tape, nabla, unbox, unthunk, zeroslike
-from .device import DevArray, get_context
+from .device import get_context
 from .scalar import CATALOGUE, compile_scalar
 
 _ADD_PROG = compile_scalar(CATALOGUE["add"], 2)

@@ -2,7 +2,6 @@
 declares, the opcode table matches, the scalar tracer lowers functions correctly, and the product
 path fails loudly (no CPU fallback) when no GPU is present."""
 import ctypes
-import math
 import os
 import subprocess
 
