@@ -247,6 +247,13 @@ NB_SF_FN double nb_bessel_k(int n, double x) {
   if (!(x > 0.0)) return x == 0.0 ? INFINITY : nan("");
   if (n < 0) n = -n;
   const double nn = (double)n;
+  if (x < 1.0e-8) {  // leading terms (relative error O(x^2 log x)): the integrand would need t up to log(1/x)
+    if (n == 0) return -log(0.5 * x) - 0.57721566490153286061;
+    double r = 0.5;
+    for (int k = 1; k < n; ++k) r *= (double)k;
+    for (int k = 0; k < n; ++k) r *= 2.0 / x;   // (n-1)!/2 (2/x)^n, overflowing to +inf when it must
+    return r;
+  }
   double h = 0.5 / sqrt(x);
   if (h > 0.125) h = 0.125;
   double s = 0.5;  // t = 0: cosh(0) = 1, half weight

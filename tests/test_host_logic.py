@@ -105,6 +105,11 @@ def test_special_functions_source_on_the_host(tmp_path):
                 r = mp.diff(lambda t: ref[w](n, t), mp.mpf(float(x)))
                 assert abs(L.sf_bessel_dx(w, float(n), float(x)) - r) <= 1e-13 * max(abs(r), 1e-3), (w, n, x)
     assert np.isnan(L.sf_bessel(0, 0.5, 1.0)) and L.sf_bessel(3, 2.0, 0.0) == float("inf") and np.isnan(L.sf_bessel(1, 0.0, -1.0))
+    for n in (0, 1, 3):          # K_n next to the origin (leading-term branch below 1e-8 and just above it)
+        for x in (1e-300, 1e-100, 9.9e-9, 1.01e-8, 1e-5):
+            r = mp.besselk(n, mp.mpf(x))
+            got = L.sf_bessel(3, float(n), x)
+            assert (got == float("inf") and r > mp.mpf(1.7e308)) or abs(got - r) <= 1e-13 * r, (n, x)
     for n in range(9):
         for x in np.concatenate([rng.uniform(0.05, 30, 25), rng.uniform(-6, 0, 15), [1e-3, 100.0, 1e4]]):
             r = mp.polygamma(n, mp.mpf(float(x)))
