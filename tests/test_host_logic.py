@@ -23,6 +23,18 @@ def test_library_exports_every_declared_symbol():
     assert L.nb_abi_version() == 1
 
 
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md's appendix (tools/gen_ccall_stubs.py) holds a Julia ccall stub for every function the header
+    declares — the binding a Nabla maintainer would load."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "nabla_cuda.h")).read()
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    names = set(re.findall(r"\b(nb_[a-z0-9_]+)\s*\(", re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)))
+    assert len(names) >= 50
+    for n in names:
+        assert f"ccall((:{n}, LIB)" in doc, f"{n} has no ccall stub in INTEGRATION.md (run tools/gen_ccall_stubs.py)"
+
+
 def test_library_is_sm100a_and_has_no_oracle_dependency():
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
