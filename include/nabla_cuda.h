@@ -114,7 +114,10 @@ typedef struct nb_stats {
   uint64_t h2d_bytes, d2h_bytes;
 } nb_stats;
 
-/* ---- library / context --------------------------------------------------------------------- */
+/* ---- library / context ---------------------------------------------------------------------
+ * No function of the reference corresponds to these: in Nabla the Julia runtime owns array storage, threads and
+ * error propagation (exceptions: MethodError for a missing rule test/core.jl:159, ErrorException
+ * src/checkpointing.jl:11,15).  Here a status code + message replaces the exception, a ctx replaces the runtime. */
 int32_t nb_abi_version(void);
 /* Message of the last failing call on this ctx (ctx may be NULL for create failures). */
 const char* nb_last_error(nb_ctx* ctx);
@@ -259,13 +262,17 @@ int32_t nb_allreduce_sum_async(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, c
 int32_t nb_comm_join(nb_ctx* ctx);
 int32_t nb_comm_destroy(nb_ctx* ctx);
 
-/* ---- CUDA-graph capture of a whole forward + reverse sweep --------------------------------- */
+/* ---- CUDA-graph capture of a whole forward + reverse sweep ---------------------------------
+ * The reference re-runs the host loop of propagate (src/core.jl:160-166) for every gradient evaluation; a tape with
+ * a fixed signature (same Branches, same shapes: examples/mlp.jl, examples/vae.jl inside an optimiser loop) is
+ * captured once between begin/end and replayed with one launch. */
 int32_t nb_graph_begin(nb_ctx* ctx);
 int32_t nb_graph_end(nb_ctx* ctx, nb_graph** out);
 int32_t nb_graph_launch(nb_ctx* ctx, nb_graph* g);
 int32_t nb_graph_destroy(nb_graph* g);
 
-/* ---- device timing on the ctx stream -------------------------------------------------------- */
+/* ---- device timing on the ctx stream --------------------------------------------------------
+ * (measurement only: the reference times with @elapsed / BenchmarkTools on the host; no rule depends on these) */
 int32_t nb_event_create(void** out);
 int32_t nb_event_record(nb_ctx* ctx, void* ev);
 int32_t nb_event_elapsed_ms(void* ev_start, void* ev_stop, float* ms_out); /* syncs ev_stop */
