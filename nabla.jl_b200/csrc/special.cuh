@@ -34,6 +34,10 @@
 NB_SF_FN double nb_airy(double x, int which) {
   if (x != x) return x;
   const bool bi = which >= 2, prime = which & 1;
+  if (isinf(x)) {  // Ai, Ai' -> 0 and Bi, Bi' -> +inf on the right; Ai, Bi -> 0 on the left, the derivatives oscillate unboundedly
+    if (x > 0.0) return bi ? INFINITY : 0.0;
+    return prime ? nan("") : 0.0;
+  }
   if (fabs(x) <= NB_AIRY_XA) {
     int j = (int)floor((x + NB_AIRY_XA) * NB_AIRY_INV_H + 0.5);
     j = j < 0 ? 0 : j > NB_AIRY_N - 1 ? NB_AIRY_N - 1 : j;
@@ -123,11 +127,13 @@ NB_SF_FN double nb_dawson(double x) {
 
 // exp(x^2) with the rounding error of x*x folded back in
 NB_SF_FN double nb_exp_sq(double x) {
+  if (isinf(x)) return INFINITY;
   const double s = x * x, e = fma(x, x, -s);
   return exp(s) * (1.0 + e);
 }
 
 NB_SF_FN double nb_erfi(double x) {
+  if (isinf(x)) return x;
   if (fabs(x) < 0.5) {  // 2/sqrt(pi) sum x^(2k+1) / (k! (2k+1))
     const double t = x * x;
     double pw = 1.0, s = 1.0;
@@ -219,6 +225,7 @@ NB_SF_FN double nb_bessel_ji(int n, double x, int kind) {
     for (int k = 1; k <= n; ++k) lead *= 0.5 * x / (double)k;
     return sign * lead * s;
   }
+  if (isinf(x)) return kind == 0 ? 0.0 : sign * INFINITY;
   if (x > 50.0) {
     double P, Q, Sp, Sm;
     nb_hankel_terms(n, x, &P, &Q, &Sp, &Sm);
@@ -245,6 +252,7 @@ NB_SF_FN double nb_bessel_ji(int n, double x, int kind) {
 NB_SF_FN double nb_bessel_k(int n, double x) {
   if (x != x) return x;
   if (!(x > 0.0)) return x == 0.0 ? INFINITY : nan("");
+  if (isinf(x)) return 0.0;
   if (n < 0) n = -n;
   const double nn = (double)n;
   if (x < 1.0e-8) {  // leading terms (relative error O(x^2 log x)): the integrand would need t up to log(1/x)
@@ -309,6 +317,7 @@ NB_SF_FN double nb_polygamma_n(double nu, double x) {
   if (x <= 0.0 && x == floor(x)) return nan("");
   if (x < -1.0e5) return nan("");  // (the shift below would not terminate in reasonable time)
   const int n = (int)nu;
+  if (isinf(x)) return n == 0 ? x : 0.0;
   if (n == 0) {
     double r = 0.0;
     while (x < 10.0) { r -= 1.0 / x; x += 1.0; }

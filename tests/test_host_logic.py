@@ -130,6 +130,12 @@ def test_special_functions_source_on_the_host(tmp_path):
             cond = min(1.0, 10 * abs(x - round(x))) if x < 0 else 1.0    # conditioning next to the poles
             assert abs(L.sf_polygamma(float(n), float(x)) - r) * cond <= 1e-13 * abs(r), (n, x)
     assert np.isnan(L.sf_polygamma(2.0, -3.0)) and np.isnan(L.sf_polygamma(1.5, 1.0))
+    # infinite arguments give the limits, never NaN from inf * 0
+    inf = float("inf")
+    assert [L.sf_airy(inf, w) for w in range(4)] == [0.0, 0.0, inf, inf] and L.sf_airy(-inf, 0) == 0.0 == L.sf_airy(-inf, 2)
+    assert L.sf_dawson(inf) == 0.0 and L.sf_erfi(inf) == inf and L.sf_erfi(-inf) == -inf and L.sf_invdigamma(inf) == inf
+    assert [L.sf_bessel(w, 2.0, inf) for w in range(4)] == [0.0, 0.0, inf, 0.0] and L.sf_bessel(2, 3.0, -inf) == -inf
+    assert L.sf_polygamma(0.0, inf) == inf and L.sf_polygamma(2.0, inf) == 0.0 and np.isnan(L.sf_polygamma(2.0, -inf))
 
 
 def test_tracer_single_primitive_and_constants():
