@@ -35,6 +35,31 @@ def test_integration_doc_lists_every_entry_point():
         assert f"ccall((:{n}, LIB)" in doc, f"{n} has no ccall stub in INTEGRATION.md (run tools/gen_ccall_stubs.py)"
 
 
+def test_julia_glue_opcode_table_matches_the_header():
+    """julia/NablaCUDA.jl cannot be executed here (no Julia in the image); its function => nb_op tables are at least
+    kept equal to the header's enum, and cover the whole catalogue."""
+    import re
+    src = open(os.path.join(ROOT, "julia", "NablaCUDA.jl")).read()
+    ops = _lib.OPCODES
+    alias = {"+": "add", "-": "sub", "*": "mul", "/": "div", "\\": "ldiv", "^": "pow"}
+    seen = {}
+    for table in ("UNARY_OPS", "BINARY_OPS"):
+        body = src[src.index(f"const {table} = Dict"):]
+        body = body[:body.index(")\nconst ") if ")\nconst " in body else len(body)]
+        for name, val in re.findall(r"(?:SF\.)?\(?([A-Za-z0-9_]+|[-+*/^\\])\)?\s*=>\s*(\d+)", body):
+            key = alias.get(name, name)
+            assert key in ops, f"{table}: {name} is not a catalogue op"
+            assert ops[key] == int(val), f"{table}: {name} => {val}, header says {ops[key]}"
+            seen[key] = int(val)
+    m = re.search(r"OP_NEG, OP_LOGISTIC, OP_ATAN2 = Int32\((\d+)\), Int32\((\d+)\), Int32\((\d+)\)", src)
+    consts = dict(zip(("neg", "logistic", "atan2"), map(int, m.groups())))
+    for k, v in consts.items():
+        assert ops[k] == v
+        seen[k] = v
+    missing = [n for n in scalar.UNARY + scalar.BINARY if n not in seen]
+    assert not missing, f"catalogue ops without a Julia mapping: {missing}"
+
+
 def test_library_is_sm100a_and_has_no_oracle_dependency():
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
