@@ -60,6 +60,46 @@ def test_julia_glue_opcode_table_matches_the_header():
     assert not missing, f"catalogue ops without a Julia mapping: {missing}"
 
 
+def test_julia_glue_ccall_signatures_match_the_header():
+    """Every hand-written `ccall` in julia/NablaCUDA.jl passes the argument list the header declares (same count,
+    same scalar widths, pointers where the header has pointers)."""
+    import re
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_ccall_stubs
+    want = {n: (r, [t for t, _ in al]) for n, r, al in gen_ccall_stubs.prototypes()}
+    src = open(os.path.join(ROOT, "julia", "NablaCUDA.jl")).read()
+
+    def cls(t):
+        t = t.strip()
+        return "ptr" if t.startswith(("Ptr", "Ref")) or t == "Cstring" else t
+
+    def split_top(text):
+        out, depth, cur = [], 0, ""
+        for ch in text:
+            depth += ch in "{(" 
+            depth -= ch in "})"
+            if ch == "," and depth == 0:
+                out.append(cur)
+                cur = ""
+            else:
+                cur += ch
+        return [x.strip() for x in out + [cur] if x.strip()]
+
+    checked = 0
+    for m in re.finditer(r"ccall\(\(:(nb_[a-z0-9_]+), LIB\),\s*([A-Za-z0-9{}]+),\s*\(", src):
+        name, ret = m.group(1), m.group(2)
+        assert name in want, f"{name} is not declared in include/nabla_cuda.h"
+        j, depth = m.end(), 1
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[j], 0)
+            j += 1
+        got = [cls(t) for t in split_top(src[m.end():j - 1])]
+        assert cls(ret) == cls(want[name][0]) and got == [cls(t) for t in want[name][1]], f"ccall of {name}: {got}"
+        checked += 1
+    assert checked >= 15
+
+
 def test_library_is_sm100a_and_has_no_oracle_dependency():
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
