@@ -100,6 +100,26 @@ def test_julia_glue_ccall_signatures_match_the_header():
     assert checked >= 15
 
 
+def test_ctypes_signatures_match_the_header():
+    """nabla.jl_b200/_lib.py declares argtypes for every entry point of the header with the same argument count,
+    scalar widths and pointer positions."""
+    import ctypes as C
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import gen_ccall_stubs
+    want = {n: [t for t, _ in al] for n, _, al in gen_ccall_stubs.prototypes()}
+    assert set(want) == set(_lib._SIGS)
+    scalars = {C.c_int32: "Int32", C.c_int64: "Int64", C.c_uint32: "UInt32", C.c_uint64: "UInt64", C.c_double: "Float64",
+               C.c_float: "Float32", C.c_char: "Cchar"}
+
+    def cls(t):
+        return scalars.get(t, "ptr")    # c_void_p, c_char_p, POINTER(...) and arrays are all pointers at the ABI
+
+    for name, (argtypes, _) in _lib._SIGS.items():
+        exp = ["ptr" if t.startswith(("Ptr", "Ref")) or t == "Cstring" else t.replace("Csize_t", "UInt64") for t in want[name]]
+        assert [cls(t) for t in argtypes] == exp, name
+
+
 def test_library_is_sm100a_and_has_no_oracle_dependency():
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
