@@ -120,6 +120,34 @@ def test_ctypes_signatures_match_the_header():
         assert [cls(t) for t in argtypes] == exp, name
 
 
+def test_header_is_plain_c_and_struct_layouts_match_ctypes(tmp_path):
+    """include/nabla_cuda.h compiles as strict C99 (the boundary is a C ABI: no C++ in the signatures), and the
+    struct layouts the C compiler sees are the ones the ctypes mirror uses."""
+    import ctypes as C
+    from nabla_jl_b200 import fusion
+    csrc = tmp_path / "abi.c"
+    csrc.write_text("""
+#include <stdio.h>
+#include <stddef.h>
+#include "nabla_cuda.h"
+int main(void) {
+  printf("%zu %zu %zu\\n", sizeof(nb_tensor), offsetof(nb_tensor, ndim), offsetof(nb_tensor, shape));
+  printf("%zu\\n", sizeof(nb_stats));
+  printf("%zu %zu %zu %zu\\n", sizeof(nb_gemm_epilogue), offsetof(nb_gemm_epilogue, bias), offsetof(nb_gemm_epilogue, ldy),
+         offsetof(nb_gemm_epilogue, rowsum));
+  return 0;
+}
+""")
+    exe = str(tmp_path / "abi")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"),
+                           "-o", exe, str(csrc)])
+    out = subprocess.run([exe], capture_output=True, text=True, check=True).stdout.split("\n")
+    T, S, E = _lib.nb_tensor, _lib.nb_stats, fusion.nb_gemm_epilogue
+    assert [int(v) for v in out[0].split()] == [C.sizeof(T), T.ndim.offset, T.shape.offset]
+    assert int(out[1]) == C.sizeof(S)
+    assert [int(v) for v in out[2].split()] == [C.sizeof(E), E.bias.offset, E.ldy.offset, E.rowsum.offset]
+
+
 def test_library_is_sm100a_and_has_no_oracle_dependency():
     out = subprocess.run(["cuobjdump", "--list-elf", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
