@@ -2,6 +2,7 @@
 hot path, and against the reference's own test method (5-point central finite differences, both the
 fresh-slot and the pre-filled-slot variants: src/finite_differencing.jl:106-120).  CPU only."""
 import math
+import zlib
 
 import numpy as np
 import pytest
@@ -163,15 +164,22 @@ def _domain(name):
 def test_unary_catalogue_matches_fd(name):
     # test/sensitivities/functional/functional.jl:15-26 (broadcast gradient == scalar derivative)
     lo, hi = _domain(name)
-    rng = np.random.default_rng(hash(name) % 2**32)
+    rng = np.random.default_rng(zlib.crc32(name.encode()))      # (hash() is salted per process: not reproducible)
     x = rng.uniform(lo, hi, 50)
     f = getattr(o, "abs_" if name == "abs" else name)
     x_ = o.Leaf(o.Tape(), x)
     s = bc(f, x_)
     g = o.nabla(s, np.ones_like(x))[x_]
     h = 1e-6
-    fd = (f(x + h) - f(x - h)) / (2 * h)
-    ok = np.abs(x - np.round(x)) > 1e-3 if name == "abs" else np.ones_like(x, bool)
+    with np.errstate(all="ignore"):
+        fd = (f(x + h) - f(x - h)) / (2 * h)
+        fd2 = (f(x + 2 * h) - f(x - 2 * h)) / (4 * h)
+    # the interval may contain poles (tan, gamma, digamma, ...): keep the points where the difference quotient itself
+    # has converged (two step sizes agree), i.e. where it is a valid reference
+    ok = np.isfinite(fd) & np.isfinite(fd2) & (np.abs(fd - fd2) <= 1e-6 * np.maximum(np.abs(fd), 1e-3))
+    if name == "abs":
+        ok &= np.abs(x) > 1e-3
+    assert ok.sum() >= 30
     np.testing.assert_allclose(g[ok], fd[ok], rtol=2e-5, atol=1e-7)
 
 
