@@ -190,8 +190,10 @@ def workload_config(args, n):
 def timed_region(ctx, fn, steps):
     e0, e1 = ctx.event(), ctx.event()
     ctx.record(e0)
+    t0 = time.perf_counter()
     for _ in range(steps):
         fn()
+    timed_region.host_ms = (time.perf_counter() - t0) * 1e3   # host time to ENQUEUE the steps (no sync inside)
     ctx.record(e1)
     ctx.sync()
     ms = ctx.elapsed_ms(e0, e1)
@@ -421,6 +423,7 @@ def run_gpu(args):
     ctx.profile_begin()
     barrier()
     ms = timed_region(ctx, step, args.steps)
+    host_ms = timed_region.host_ms
     barrier()
     recs = ctx.profile_end()
     launches = ctx.stats()["kernel_launches"] - launches0
@@ -490,7 +493,7 @@ def run_gpu(args):
         "scaling": "strong", "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",
         "config": workload_config(args, n),
         "TFLOP/s_algorithmic": mlp_flops(dims, B) / (ms_step * 1e-3) / 1e12,
-        "clocks": clocks, "gpu_launches": int(launches),
+        "clocks": clocks, "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms / args.steps,
         "pool": {"cuda_mallocs_in_timed_regions": ctx.stats()["cuda_mallocs"] - stats0["cuda_mallocs"],
                  "high_water_GB": ctx.stats()["pool_high_water"] / 1e9},
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "evals/s",
