@@ -48,16 +48,27 @@ typedef enum nb_status {
 
 typedef enum nb_dtype { NB_F32 = 0, NB_F64 = 1 } nb_dtype;
 
-/* GEMM arithmetic.  Float32: see the modes.  Float64: exact FP64 FMA on the DMMA path for small products, exact
- * int8 slice products on tcgen05 (Ozaki split, ~4e-14 relative error norm-wise) for m*n*k >= 3e9; NB_MATH_FP32 keeps
- * every Float64 product on DMMA. */
+/* GEMM arithmetic.
+ * Float32 on the tensor cores: operands are split x = hi + lo into 16-bit (or tf32) halves and the product is
+ * issued as lo*hi + hi*lo + hi*hi into one FP32 accumulator.  The split copies are the library's own temporaries,
+ * cached per source array until that array is written through an nb_* entry point or released (a caller that writes
+ * an array with its own kernels on nb_ctx_stream must call nb_buffer_written).
+ * Float64: exact FP64 FMA on the DMMA path for small products, exact int8 slice products on tcgen05 (Ozaki split)
+ * for m*n*k >= 3e9 — its error is ~2^-49 relative to max|row of A| * max|col of B| (4e-14 norm-wise measured), NOT
+ * relative to |A||B| element-wise like dgemm: rows or columns with a very large dynamic range lose low-order bits of
+ * their small entries.  NB_MATH_FP32 (or NB_F64_OZAKI=0) keeps every Float64 product on DMMA. */
 typedef enum nb_math_mode {
-  NB_MATH_DEFAULT = 0,  /* f32: NB_MATH_BF16X3; f64: DMMA / Ozaki split by size */
+  NB_MATH_DEFAULT = 0,  /* f32: NB_MATH_FP16X3; f64: DMMA / Ozaki split by size */
   NB_MATH_TF32 = 1,     /* f32: single-pass kind::tf32 on tcgen05 (~8e-4 relative error) */
-  NB_MATH_3XTF32 = 2,   /* f32: x = hi + lo in tf32, lo*hi + hi*lo + hi*hi on tcgen05 (~4e-7) */
+  NB_MATH_3XTF32 = 2,   /* f32: x = hi + lo in tf32 (21 bits), three kind::tf32 passes (~4e-7) */
   NB_MATH_FP32 = 3,     /* f32: FP32 FMA on CUDA cores (no tensor cores); f64: DMMA only */
-  NB_MATH_BF16X3 = 4    /* f32: x = hi + lo in bfloat16, three kind::f16 passes on tcgen05 (~1e-5): meets
-                           rtol 1e-4 at half the tensor work of 3xTF32 */
+  NB_MATH_BF16X3 = 4,   /* f32: x = hi + lo in bfloat16 (16 bits, any dynamic range), three kind::f16 passes (~5e-6 per
+                           product).  Enough for the adjoint products, whose error enters the gradient linearly; NOT
+                           for forward products that feed saturating activations (width 8192: 7e-4 on the gradient).
+                           A cached binary16 split of an operand (a forward value) is re-used when there is one. */
+  NB_MATH_FP16X3 = 5    /* f32: x * 2^s = hi + lo in binary16 with one power-of-two scale per array (22 bits for
+                           every element within 2^18 of the array's largest magnitude, absolute floor 2^-40 of it
+                           below), three kind::f16 passes at the BF16X3 cost (~3e-7 per product): FP32-class */
 } nb_math_mode;
 
 typedef struct nb_tensor {
@@ -144,6 +155,11 @@ int32_t nb_d2h(nb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t nbytes
 int32_t nb_d2h_async(nb_ctx* ctx, void* dst_host, const void* src_dev, uint64_t nbytes);
 int32_t nb_d2d(nb_ctx* ctx, void* dst_dev, const void* src_dev, uint64_t nbytes);
 int32_t nb_fill(nb_ctx* ctx, void* dst_dev, int32_t dtype, uint64_t count, double value);
+/* The caller wrote [ptr, ptr + nbytes) with its own kernels or copies enqueued on nb_ctx_stream (every nb_* entry
+ * point does this bookkeeping itself).  The library caches tensor-core operand splits of Float32 arrays it has
+ * multiplied (see nb_math_mode); this drops the cached splits of every array overlapping the range.  No reference
+ * counterpart: Julia arrays have no derived copies. */
+int32_t nb_buffer_written(nb_ctx* ctx, const void* ptr, uint64_t nbytes);
 int32_t nb_host_alloc(uint64_t nbytes, void** out); /* pinned host memory */
 int32_t nb_host_free(void* p);
 

@@ -9,7 +9,7 @@ package raises if the library or a GPU is missing — there is no CPU path (see 
 test-only CPU restatement)."""
 from . import _lib
 from ._lib import (DimensionMismatch, NablaCudaError, UnsupportedOp, MATH_DEFAULT, MATH_TF32,
-                   MATH_3XTF32, MATH_FP32, MATH_BF16X3)
+                   MATH_3XTF32, MATH_FP32, MATH_BF16X3, MATH_FP16X3)
 from .device import BroadcastView, Context, DevArray, PinnedArray, get_context, set_context
 from .core import (Arg, Branch, Leaf, Node, Primitive, Tape, explicit_intercepts, grad, nabla,
                    oneslike, pos, propagate, reverse_tape, tape, unbox, unthunk, zeroslike, as_device)

@@ -16,7 +16,7 @@ NB_MAX_ARGS = 6
 NB_MAX_INSTR = 32
 NB_MAX_CONSTS = 16
 NB_F32, NB_F64 = 0, 1
-MATH_DEFAULT, MATH_TF32, MATH_3XTF32, MATH_FP32, MATH_BF16X3 = 0, 1, 2, 3, 4
+MATH_DEFAULT, MATH_TF32, MATH_3XTF32, MATH_FP32, MATH_BF16X3, MATH_FP16X3 = 0, 1, 2, 3, 4, 5
 STATUS_NAMES = {0: "NB_OK", 1: "NB_ERR_INVALID", 2: "NB_ERR_CUDA", 3: "NB_ERR_OOM",
                 4: "NB_ERR_UNSUPPORTED", 5: "NB_ERR_COMM", 6: "NB_ERR_SHAPE"}
 
@@ -87,6 +87,7 @@ _SIGS = {
     "nb_fill": ([_p, _p, _i32, _u64, _dbl], _i32),
     "nb_host_alloc": ([_u64, _pp], _i32),
     "nb_host_free": ([_p], _i32),
+    "nb_buffer_written": ([_p, _p, _u64], _i32),
     "nb_prog_create": ([_i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i32,
                         C.POINTER(_dbl), _pp], _i32),
     "nb_prog_destroy": ([_p], _i32),

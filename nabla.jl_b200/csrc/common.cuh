@@ -93,6 +93,7 @@ static inline size_t nb_dtype_size(int32_t dt) { return dt == NB_F64 ? 8 : 4; }
 // both adjoints), so the hi/lo copies are kept until the source buffer is written or released.  Every
 // entry point that writes device memory reports the destination here.
 void nb_note_write(nb_ctx* ctx, const void* dst);
+void nb_note_write_range(nb_ctx* ctx, const void* dst, size_t nbytes);
 void nb_split_cache_clear(nb_ctx* ctx);
 
 // internal allocator entry points (ctx.cu)

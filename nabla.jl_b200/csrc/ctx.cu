@@ -70,6 +70,7 @@ int32_t nb_pool_alloc(nb_ctx* ctx, size_t nbytes, void** out) {
 }
 
 int32_t nb_pool_release(nb_ctx* ctx, void* p) {
+  size_t block_bytes = 0;
   {
     std::lock_guard<std::mutex> lk(ctx->mu);
     auto it = ctx->live.find(p);
@@ -78,8 +79,10 @@ int32_t nb_pool_release(nb_ctx* ctx, void* p) {
       --it->second.refs;
       return NB_OK;
     }
+    block_bytes = it->second.size;
   }
-  nb_note_write(ctx, p);  // the block is about to be recycled: cached splits of it are stale
+  // the block is about to be recycled: cached splits of any array inside it (interior pointers included) are stale
+  nb_note_write_range(ctx, p, block_bytes);
   std::lock_guard<std::mutex> lk(ctx->mu);
   auto it = ctx->live.find(p);
   if (it == ctx->live.end()) return nb_fail(ctx, NB_ERR_INVALID, "nb_release: unknown buffer");
@@ -260,6 +263,12 @@ int32_t nb_d2d(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
   if (!nbytes) return NB_OK;
   nb_note_write(ctx, dst);
   NB_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToDevice, ctx->stream));
+  return NB_OK;
+}
+
+int32_t nb_buffer_written(nb_ctx* ctx, const void* ptr, uint64_t nbytes) {
+  NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
+  if (ptr) nb_note_write_range(ctx, ptr, (size_t)nbytes);
   return NB_OK;
 }
 

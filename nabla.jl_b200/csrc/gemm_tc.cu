@@ -50,6 +50,7 @@
 //     (ozaki.cu): int32 TMEM accumulators, Float64 epilogue.
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include <cstring>
 
@@ -110,12 +111,19 @@ struct EpiArgs {
   void* s_hi;             // nullable: split copies of C (bf16 for BF16x3, f32 for 3xTF32), leading dim ld_s
   void* s_lo;
   int64_t ld_s;
+  int32_t s_fp16;         // the emitted 16-bit split is scaled binary16 (x * s_scale) instead of bfloat16
+  float s_scale;
   int32_t last_launch;    // this launch covers the end of K
 };
 
 struct GemmArgs {
   int64_t M, N, K;
   int32_t a_mn, b_mn;  // operand is MN-major in memory (A: not transposed, B: transposed)
+  // 16-bit split kinds: element format of each operand's hi/lo copies in the instruction descriptor (0 = binary16
+  // scaled by a power of two per tensor, 1 = bfloat16) and the device-resident inverse scales (nullable = 1)
+  uint32_t a_fmt, b_fmt;
+  const float* a_sinv;
+  const float* b_sinv;
   float alpha, beta;
   float* C;
   int64_t ldc;
@@ -296,6 +304,22 @@ __device__ __forceinline__ void split1(float x, __nv_bfloat16& hi, __nv_bfloat16
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
+// scaled binary16: hi = fp16(s*x), lo = fp16(s*x - hi): 22 significant bits for every element within 2^18 of the
+// tensor's largest magnitude (s is the power of two that puts that magnitude just below 2^15), an absolute floor of
+// 2^-40 of it below; the product's epilogue multiplies by the inverse scales
+__device__ __forceinline__ void split1s(float x, float s, __half& hi, __half& lo) {
+  const float xs = x * s;
+  hi = __float2half_rn(xs);
+  lo = __float2half_rn(xs - __half2float(hi));
+}
+
+__device__ __forceinline__ float eff_alpha(const float alpha, const float* a_sinv, const float* b_sinv) {
+  float a = alpha;
+  if (a_sinv) a *= __ldg(a_sinv);
+  if (b_sinv) a *= __ldg(b_sinv);
+  return a;
+}
+
 __device__ __forceinline__ float epi_act(int op, float x) {
   switch (op) {
     case NB_OP_IDENTITY: return x;
@@ -360,7 +384,7 @@ struct EpiAcc {
     const int a = lane >> 2, b = lane & 3;
     const int64_t R0 = gw + 4 * a;
     const bool row_ok = R0 < g.M;
-    const float alpha = g.alpha, beta = g.beta;
+    const float alpha = eff_alpha(g.alpha, g.a_sinv, g.b_sinv), beta = g.beta;
     const int ek = g.epi.last_launch ? g.epi.kind : EPI_NONE;
     float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ek == EPI_FWD && g.epi.bias && row_ok) bias4 = __ldg(reinterpret_cast<const float4*>(g.epi.bias + R0));
@@ -422,8 +446,14 @@ struct EpiAcc {
           if (ek != EPI_NONE && g.epi.s_hi) {
             __align__(16) SplitT h[4];
             __align__(16) SplitT l[4];
+            if (KIND == KIND_BF16X3 && g.epi.s_fp16) {
 #pragma unroll
-            for (int i = 0; i < 4; ++i) split1(x[gq][i], h[i], l[i]);
+              for (int i = 0; i < 4; ++i)
+                split1s(x[gq][i], g.epi.s_scale, *reinterpret_cast<__half*>(&h[i]), *reinterpret_cast<__half*>(&l[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 4; ++i) split1(x[gq][i], h[i], l[i]);
+            }
             SplitT* hp = (SplitT*)g.epi.s_hi + R0 + col * g.epi.ld_s;
             SplitT* lp = (SplitT*)g.epi.s_lo + R0 + col * g.epi.ld_s;
             if (sizeof(SplitT) == 2) {
@@ -478,7 +508,7 @@ struct EpiAcc {
     if (g.vec_store) { store_vec(g, gm - lane, n0, part, lane); return; }
     using SplitT = typename std::conditional<KIND == KIND_BF16X3, __nv_bfloat16, float>::type;
     if (gm >= g.M) return;
-    const float alpha = g.alpha, beta = g.beta;
+    const float alpha = eff_alpha(g.alpha, g.a_sinv, g.b_sinv), beta = g.beta;
     const int ek = g.epi.last_launch ? g.epi.kind : EPI_NONE;
     const float bias = (ek == EPI_FWD && g.epi.bias) ? __ldg(g.epi.bias + gm) : 0.f;
     float rsum = 0.f;
@@ -522,7 +552,10 @@ struct EpiAcc {
 #pragma unroll
         for (int j = 0; j < SB; ++j) {
           SplitT h, l;
-          split1(x[j], h, l);
+          if (KIND == KIND_BF16X3 && g.epi.s_fp16)
+            split1s(x[j], g.epi.s_scale, *reinterpret_cast<__half*>(&h), *reinterpret_cast<__half*>(&l));
+          else
+            split1(x[j], h, l);
           if (j < jmax) { hp[(int64_t)j * g.epi.ld_s] = h; lp[(int64_t)j * g.epi.ld_s] = l; }
         }
       }
@@ -698,7 +731,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      const uint32_t idesc = (KT::CFMT << 4) | (KT::FMT << 7) | (KT::FMT << 10) | ((uint32_t)g.a_mn << 15) |
+      const uint32_t idesc = (KT::CFMT << 4) | ((KIND == KIND_BF16X3 ? g.a_fmt : KT::FMT) << 7) |
+                             ((KIND == KIND_BF16X3 ? g.b_fmt : KT::FMT) << 10) | ((uint32_t)g.a_mn << 15) |
                              ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint32_t a_kstep = g.a_mn ? KT::MN_KSTEP : 32u;  // K-major: UMMA_K elements = 32 bytes
       const uint32_t b_kstep = g.b_mn ? KT::MN_KSTEP : 32u;
@@ -1053,7 +1087,8 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   } else if (warp == 1) {
     // ===================== MMA issuer (leader CTA only) =====================
     if (leader && lane == 0) {
-      const uint32_t idesc = (KT::CFMT << 4) | (KT::FMT << 7) | (KT::FMT << 10) | ((uint32_t)g.a_mn << 15) |
+      const uint32_t idesc = (KT::CFMT << 4) | ((KIND == KIND_BF16X3 ? g.a_fmt : KT::FMT) << 7) |
+                             ((KIND == KIND_BF16X3 ? g.b_fmt : KT::FMT) << 10) | ((uint32_t)g.a_mn << 15) |
                              ((uint32_t)g.b_mn << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
       const uint32_t a_kstep = g.a_mn ? KT::MN_KSTEP : 32u;
       const uint32_t b_kstep = g.b_mn ? KT::MN_KSTEP : 32u;
@@ -1180,17 +1215,103 @@ __global__ void __launch_bounds__(256) k_split(const float* __restrict__ x, int6
   }
 }
 
+// Scaled binary16 split (NB_MATH_FP16X3): sc[0] = power-of-two scale, sc[1] = its inverse (device-resident, written
+// by k_scale_from_absmax or fixed by the producer of the array).
+__global__ void __launch_bounds__(256) k_split_h(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld_in,
+                                                 __half* __restrict__ hi, __half* __restrict__ lo, int64_t ld_out,
+                                                 int vec, const float* __restrict__ sc) {
+  const float s = __ldg(sc);
+  const int64_t r4 = (rows + 3) >> 2;
+  for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) {
+    const float* xc = x + c * ld_in;
+    __half* hc = hi + c * ld_out;
+    __half* lc = lo + c * ld_out;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r4; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i << 2;
+      float v[4];
+      if (vec && r + 3 < rows) {
+        const float4 q = *reinterpret_cast<const float4*>(xc + r);
+        v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) v[e] = r + e < rows ? xc[r + e] : 0.f;
+      }
+      __align__(8) __half h[4];
+      __align__(8) __half l[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) split1s(v[e], s, h[e], l[e]);
+      if (r + 3 < rows) {
+        *reinterpret_cast<uint2*>(hc + r) = *reinterpret_cast<const uint2*>(h);
+        *reinterpret_cast<uint2*>(lc + r) = *reinterpret_cast<const uint2*>(l);
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (r + e < rows) { hc[r + e] = h[e]; lc[r + e] = l[e]; }
+      }
+    }
+  }
+}
+
+// max |x| over a column-major (rows x cols, ld) array into *out (bit pattern of a non-negative float: unsigned
+// integer order == float order; the word is zeroed before the launch).  max is order-independent: deterministic.
+__global__ void __launch_bounds__(256) k_absmax_f32(const float* __restrict__ x, int64_t rows, int64_t cols, int64_t ld,
+                                                    int vec, unsigned int* __restrict__ out) {
+  float m = 0.f;
+  const int64_t r4 = (rows + 3) >> 2;
+  for (int64_t c = blockIdx.y; c < cols; c += gridDim.y) {
+    const float* xc = x + c * ld;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r4; i += (int64_t)gridDim.x * blockDim.x) {
+      const int64_t r = i << 2;
+      if (vec && r + 3 < rows) {
+        const float4 q = *reinterpret_cast<const float4*>(xc + r);
+        m = fmaxf(fmaxf(m, fmaxf(fabsf(q.x), fabsf(q.y))), fmaxf(fabsf(q.z), fabsf(q.w)));
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (r + e < rows) m = fmaxf(m, fabsf(xc[r + e]));
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0 && m > 0.f) atomicMax(out, __float_as_uint(m));
+}
+
+// sc[0] = 2^(15 - e) with max|x| = f * 2^e, f in [0.5, 1)  (so max|x| * sc[0] < 2^15 < 65504), sc[1] = 1 / sc[0]
+__global__ void k_scale_from_absmax(const unsigned int* __restrict__ amax, float* __restrict__ sc) {
+  const float mx = __uint_as_float(*amax);
+  float s = 1.f;
+  if (mx > 0.f && mx < INFINITY) {
+    int e;
+    frexpf(mx, &e);
+    int p = 15 - e;
+    p = p > 100 ? 100 : (p < -100 ? -100 : p);
+    s = ldexpf(1.f, p);
+  }
+  sc[0] = s;
+  sc[1] = 1.f / s;
+}
+
+__global__ void k_set_scale(float* __restrict__ sc, float s) {
+  sc[0] = s;
+  sc[1] = 1.f / s;
+}
+
 // ---- host ---------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
+enum { FMT_FP16 = 0, FMT_BF16 = 1 };  // values of the instruction descriptor's a/b format field (kind::f16)
+
 struct SplitEntry {
   const void* src;
   int64_t rows, cols, ld_in, ld_out;
   int kind;
+  int fmt;      // KIND_BF16X3 only: FMT_BF16 or FMT_FP16 (scaled binary16)
   void* hi;
   void* lo;
+  float* sc;    // FMT_FP16: {scale, 1/scale} on the device (owned by the entry), else nullptr
   uint64_t stamp;
 };
 
@@ -1285,48 +1406,93 @@ int32_t run_split(nb_ctx* ctx, const float* x, int64_t rows, int64_t cols, int64
   return NB_OK;
 }
 
-// the cache takes ownership of e.hi / e.lo (LRU eviction releases them to the pool)
+static void entry_release(nb_ctx* ctx, const SplitEntry& e) {
+  nb_pool_release(ctx, e.hi);
+  nb_pool_release(ctx, e.lo);
+  if (e.sc) nb_pool_release(ctx, e.sc);
+}
+
+// the cache takes ownership of e.hi / e.lo / e.sc (LRU eviction releases them to the pool)
 void cache_insert(nb_ctx* ctx, GemmState* st, SplitEntry e) {
-  std::vector<std::pair<void*, void*>> evict;
+  std::vector<SplitEntry> evict;
   {
     std::lock_guard<std::mutex> lk(st->cache_mu);
     if (st->cache.size() >= st->max_entries) {
       size_t v = 0;
       for (size_t i = 1; i < st->cache.size(); ++i)
         if (st->cache[i].stamp < st->cache[v].stamp) v = i;
-      evict.push_back({st->cache[v].hi, st->cache[v].lo});
+      evict.push_back(st->cache[v]);
       st->cache.erase(st->cache.begin() + v);
     }
     e.stamp = ++st->clock;
     st->cache.push_back(e);
   }
-  for (auto& pr : evict) { nb_pool_release(ctx, pr.first); nb_pool_release(ctx, pr.second); }
+  for (auto& v : evict) entry_release(ctx, v);
 }
 
-// returns the cached split of (src, rows, cols, ld_in) or creates it; the entry owns hi/lo
-int32_t get_split(nb_ctx* ctx, GemmState* st, int kind, const float* src, int64_t rows, int64_t cols, int64_t ld_in,
-                  int64_t ld_out, int esize, void** hi, void** lo) {
-  const bool use_cache = !ctx->capturing;
-  if (use_cache) {
+// Split of the column-major source (rows x cols, ld_in), cached until the source buffer is written or released.
+// `fmt` is the wanted 16-bit format (KIND_BF16X3); with `any_fmt` a cached split of the other format is accepted too
+// (the MMA takes binary16 and bfloat16 operands in any combination).  The entry (and the cache) owns hi / lo / sc.
+// Inside a CUDA-graph capture the cache works the same way — the entries then describe buffers of the capture and
+// are dropped when it ends (nb_graph_begin / nb_graph_end / nb_graph_launch clear the cache).
+int32_t get_split(nb_ctx* ctx, GemmState* st, int kind, int fmt, bool any_fmt, const float* src, int64_t rows,
+                  int64_t cols, int64_t ld_in, int64_t ld_out, int esize, SplitEntry* out) {
+  {
     std::lock_guard<std::mutex> lk(st->cache_mu);
+    SplitEntry* other = nullptr;
     for (auto& e : st->cache)
       if (e.src == src && e.rows == rows && e.cols == cols && e.ld_in == ld_in && e.kind == kind) {
-        e.stamp = ++st->clock;
-        *hi = e.hi; *lo = e.lo;
-        return NB_OK;
+        if (kind != KIND_BF16X3 || e.fmt == fmt) {
+          e.stamp = ++st->clock;
+          *out = e;
+          return NB_OK;
+        }
+        other = &e;
       }
+    if (other && any_fmt) {
+      other->stamp = ++st->clock;
+      *out = *other;
+      return NB_OK;
+    }
   }
+  SplitEntry e{src, rows, cols, ld_in, ld_out, kind, kind == KIND_BF16X3 ? fmt : FMT_BF16, nullptr, nullptr, nullptr, 0};
   const size_t bytes = (size_t)(ld_out * cols) * esize;
-  int32_t rc = nb_pool_alloc(ctx, bytes, hi);
+  int32_t rc = nb_pool_alloc(ctx, bytes, &e.hi);
   if (rc != NB_OK) return rc;
-  rc = nb_pool_alloc(ctx, bytes, lo);
-  if (rc != NB_OK) { nb_pool_release(ctx, *hi); return rc; }
-  if (kind == KIND_BF16X3)
-    rc = run_split<__nv_bfloat16>(ctx, src, rows, cols, ld_in, (__nv_bfloat16*)*hi, (__nv_bfloat16*)*lo, ld_out);
-  else
-    rc = run_split<float>(ctx, src, rows, cols, ld_in, (float*)*hi, (float*)*lo, ld_out);
-  if (rc != NB_OK) { nb_pool_release(ctx, *hi); nb_pool_release(ctx, *lo); return rc; }
-  if (use_cache) cache_insert(ctx, st, SplitEntry{src, rows, cols, ld_in, ld_out, kind, *hi, *lo, 0});
+  rc = nb_pool_alloc(ctx, bytes, &e.lo);
+  if (rc != NB_OK) { nb_pool_release(ctx, e.hi); return rc; }
+  if (kind == KIND_BF16X3 && fmt == FMT_FP16) {
+    void* scp = nullptr;
+    rc = nb_pool_alloc(ctx, 16, &scp);
+    if (rc != NB_OK) { nb_pool_release(ctx, e.hi); nb_pool_release(ctx, e.lo); return rc; }
+    e.sc = (float*)scp;
+    // power-of-two scale from max|x| (one extra read of the source), then the split itself
+    unsigned int* amax = (unsigned int*)(e.sc + 2);
+    cudaMemsetAsync(amax, 0, sizeof(unsigned int), ctx->stream);
+    const int vec = ((uintptr_t)src % 16 == 0) && (ld_in % 4 == 0);
+    int64_t gx = ((rows + 3) / 4 + 255) / 256;
+    if (gx > 64) gx = 64;
+    int64_t gy = cols;
+    const int64_t want = (int64_t)ctx->num_sms * 16;
+    if (gx * gy > want) gy = (want + gx - 1) / gx;
+    if (gy > 65535) gy = 65535;
+    if (gy < 1) gy = 1;
+    k_absmax_f32<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ctx->stream>>>(src, rows, cols, ld_in, vec, amax);
+    ctx->stats.kernel_launches++;
+    k_scale_from_absmax<<<1, 1, 0, ctx->stream>>>(amax, e.sc);
+    ctx->stats.kernel_launches++;
+    k_split_h<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ctx->stream>>>(src, rows, cols, ld_in, (__half*)e.hi,
+                                                                        (__half*)e.lo, ld_out, vec, e.sc);
+    ctx->stats.kernel_launches++;
+    if (cudaGetLastError() != cudaSuccess) rc = nb_fail(ctx, NB_ERR_CUDA, "operand split launch failed");
+  } else if (kind == KIND_BF16X3) {
+    rc = run_split<__nv_bfloat16>(ctx, src, rows, cols, ld_in, (__nv_bfloat16*)e.hi, (__nv_bfloat16*)e.lo, ld_out);
+  } else {
+    rc = run_split<float>(ctx, src, rows, cols, ld_in, (float*)e.hi, (float*)e.lo, ld_out);
+  }
+  if (rc != NB_OK) { entry_release(ctx, e); return rc; }
+  cache_insert(ctx, st, e);
+  *out = e;
   return NB_OK;
 }
 
@@ -1336,20 +1502,51 @@ int32_t get_split(nb_ctx* ctx, GemmState* st, int kind, const float* src, int64_
 void nb_note_write(nb_ctx* ctx, const void* dst) {
   GemmState* st = (GemmState*)ctx->gemm_state;
   if (!st || !dst) return;
-  std::vector<std::pair<void*, void*>> drop;
+  std::vector<SplitEntry> drop;
   {
     std::lock_guard<std::mutex> lk(st->cache_mu);
     if (st->cache.empty()) return;
+    // by address RANGE: the ABI accepts interior pointers (sub-matrices, ld > rows), so a write anywhere inside a
+    // cached source — or a source starting inside the written block's first element — invalidates the entry
+    const char* d = (const char*)dst;
     for (size_t i = 0; i < st->cache.size();) {
-      if (st->cache[i].src == dst) {
-        drop.push_back({st->cache[i].hi, st->cache[i].lo});
+      const SplitEntry& e = st->cache[i];
+      const char* lo = (const char*)e.src;
+      const char* hi = lo + (size_t)(e.ld_in * (e.cols > 0 ? e.cols - 1 : 0) + e.rows) * sizeof(float);
+      if (d >= lo && d < hi) {
+        drop.push_back(e);
         st->cache.erase(st->cache.begin() + i);
       } else {
         ++i;
       }
     }
   }
-  for (auto& pr : drop) { nb_pool_release(ctx, pr.first); nb_pool_release(ctx, pr.second); }
+  for (auto& e : drop) entry_release(ctx, e);
+}
+
+// Same, for a write of `nbytes` starting at dst (every cached source overlapping the range is dropped).
+void nb_note_write_range(nb_ctx* ctx, const void* dst, size_t nbytes) {
+  GemmState* st = (GemmState*)ctx->gemm_state;
+  if (!st || !dst) return;
+  std::vector<SplitEntry> drop;
+  {
+    std::lock_guard<std::mutex> lk(st->cache_mu);
+    if (st->cache.empty()) return;
+    const char* d0 = (const char*)dst;
+    const char* d1 = d0 + (nbytes ? nbytes : 1);
+    for (size_t i = 0; i < st->cache.size();) {
+      const SplitEntry& e = st->cache[i];
+      const char* lo = (const char*)e.src;
+      const char* hi = lo + (size_t)(e.ld_in * (e.cols > 0 ? e.cols - 1 : 0) + e.rows) * sizeof(float);
+      if (d0 < hi && lo < d1) {
+        drop.push_back(e);
+        st->cache.erase(st->cache.begin() + i);
+      } else {
+        ++i;
+      }
+    }
+  }
+  for (auto& e : drop) entry_release(ctx, e);
 }
 
 void nb_split_cache_clear(nb_ctx* ctx) {
@@ -1360,7 +1557,7 @@ void nb_split_cache_clear(nb_ctx* ctx) {
     std::lock_guard<std::mutex> lk(st->cache_mu);
     all.swap(st->cache);
   }
-  for (auto& e : all) { nb_pool_release(ctx, e.hi); nb_pool_release(ctx, e.lo); }
+  for (auto& e : all) entry_release(ctx, e);
 }
 
 void nb_gemm_state_free(nb_ctx* ctx) {
@@ -1382,6 +1579,11 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
   if (m * n * k < (int64_t)1 << 18) return NB_ERR_UNSUPPORTED;  // tiny: one tile would idle 147 SMs
   if (m >= (1ll << 31) || n >= (1ll << 31) || k >= (1ll << 31)) return NB_ERR_UNSUPPORTED;
   const int kind = math_mode == NB_MATH_TF32 ? KIND_TF32 : math_mode == NB_MATH_3XTF32 ? KIND_3XTF32 : KIND_BF16X3;
+  // 16-bit split kinds: NB_MATH_FP16X3 (and NB_MATH_DEFAULT) wants both operands as scaled binary16 (22 bits);
+  // NB_MATH_BF16X3 wants bfloat16 (16 bits, any dynamic range) but re-uses a cached binary16 split of an operand
+  // when there is one (forward values in the adjoint products: more accurate and no second split pass)
+  const int want_fmt = math_mode == NB_MATH_BF16X3 ? FMT_BF16 : FMT_FP16;
+  static const bool mixed_ok = !(getenv("NB_GEMM_MIXED_FMT") && atoi(getenv("NB_GEMM_MIXED_FMT")) == 0);
   if (kind == KIND_TF32) {
     if (((uintptr_t)A | (uintptr_t)B) & 15) return NB_ERR_UNSUPPORTED;
     if ((lda & 3) || (ldb & 3)) return NB_ERR_UNSUPPORTED;
@@ -1397,7 +1599,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     if (n <= 128) BN = 128;
     if (const char* e = getenv("NB_GEMM_BN")) BN = atoi(e) == 128 ? 128 : 256;
   }
-  // CTA-pair kernel (256 x 256 tiles) for BF16x3 when there are enough pair tiles to fill the 74 pairs
+  // CTA-pair kernel (256 x 256 tiles) for the 16-bit split kinds when there are enough pair tiles to fill the 74 pairs
   bool use_pair = false;
   if (kind == KIND_BF16X3) {
     const int64_t pt = ((m + 255) / 256) * ((n + 255) / 256);
@@ -1408,23 +1610,23 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
   const int esize = kind == KIND_BF16X3 ? 2 : 4;
   const void* src[4] = {A, A, B, B};  // A hi, A lo, B hi, B lo
   int64_t ld_a = lda, ld_b = ldb;
-  void* tmp[4] = {nullptr, nullptr, nullptr, nullptr};  // uncached splits (graph capture): released below
+  SplitEntry ea{}, eb{};
+  ea.fmt = eb.fmt = FMT_BF16;
   if (kind != KIND_TF32) {
     const int64_t pad = 16 / esize;  // leading dimensions of the split copies: 16-byte multiples
     ld_a = (a_r + pad - 1) / pad * pad;
     ld_b = (b_r + pad - 1) / pad * pad;
-    void *ah, *al, *bh, *bl;
-    int32_t rc = get_split(ctx, st, kind, A, a_r, a_c, lda, ld_a, esize, &ah, &al);
+    const bool any = mixed_ok && want_fmt == FMT_BF16;
+    int32_t rc = get_split(ctx, st, kind, want_fmt, any, A, a_r, a_c, lda, ld_a, esize, &ea);
     if (rc != NB_OK) return rc;
-    rc = get_split(ctx, st, kind, B, b_r, b_c, ldb, ld_b, esize, &bh, &bl);
-    if (rc != NB_OK) {
-      if (ctx->capturing) { nb_pool_release(ctx, ah); nb_pool_release(ctx, al); }
-      return rc;
-    }
-    src[0] = ah; src[1] = al; src[2] = bh; src[3] = bl;
-    if (ctx->capturing) { tmp[0] = ah; tmp[1] = al; tmp[2] = bh; tmp[3] = bl; }
+    rc = get_split(ctx, st, kind, want_fmt, any, B, b_r, b_c, ldb, ld_b, esize, &eb);
+    if (rc != NB_OK) return rc;
+    src[0] = ea.hi; src[1] = ea.lo; src[2] = eb.hi; src[3] = eb.lo;
+    // the operands' buffers must outlive this launch even if the cache drops the entries before it returns
+    // (stream-ordered pool: a released block is only re-used by LATER work on the same stream, so no retain needed)
   }
   const CUtensorMapDataType dt = kind == KIND_BF16X3 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32;
+  // (binary16 and bfloat16 tiles are moved as the same 16-bit type: TMA only copies and zero-fills)
   const uint32_t bk = 128 / esize, mnc = 128 / esize;
   // MN-major -> inner dim is the MN extent, box {mnc, bk}; K-major -> inner dim k, box {bk, tile rows}
   const CUtensorMapSwizzle swz_mn = kind == KIND_BF16X3 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B;
@@ -1446,6 +1648,9 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     g.M = m; g.N = n; g.K = k;
     g.a_mn = a_mn; g.b_mn = b_mn;
     g.alpha = alpha; g.beta = beta;
+    g.a_fmt = (uint32_t)ea.fmt; g.b_fmt = (uint32_t)eb.fmt;
+    g.a_sinv = ea.sc ? ea.sc + 1 : nullptr;
+    g.b_sinv = eb.sc ? eb.sc + 1 : nullptr;
     g.C = C; g.ldc = ldc;
     const int tile_rows = use_pair ? 256 : BM;
     g.tiles_m = (int32_t)((m + tile_rows - 1) / tile_rows);
@@ -1454,6 +1659,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     memset(&g.epi, 0, sizeof(g.epi));
     void* rs_partial = nullptr;
     void *e_hi = nullptr, *e_lo = nullptr;
+    float* e_sc = nullptr;
     int64_t e_ld = 0;
     if (fused) {
       g.epi.kind = epi->kind;
@@ -1465,7 +1671,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
         rc = nb_pool_alloc(ctx, (size_t)g.tiles_n * 2 * (size_t)m * sizeof(float), &rs_partial);
         g.epi.rowsum_partial = (float*)rs_partial;
       }
-      if (rc == NB_OK && epi->emit_split && kind != KIND_TF32 && !ctx->capturing) {
+      if (rc == NB_OK && epi->emit_split && kind != KIND_TF32) {
         const int64_t pad = 16 / esize;
         e_ld = (m + pad - 1) / pad * pad;
         const size_t bytes = (size_t)(e_ld * n) * esize;
@@ -1477,6 +1683,20 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
           rc = NB_OK;
         }
         g.epi.s_hi = e_hi; g.epi.s_lo = e_lo; g.epi.ld_s = e_ld;
+        // A forward value bounded by one in magnitude (tanh, logistic) is emitted as scaled binary16 with the fixed
+        // scale 2^15 when this product itself runs in the binary16 mode: the next forward product then reads 22-bit
+        // operands without an absmax pass.  Everything else (sensitivities, unbounded activations) stays bfloat16.
+        if (e_hi && kind == KIND_BF16X3 && want_fmt == FMT_FP16 && epi->kind == 1 &&
+            (epi->op == NB_OP_TANH || epi->op == NB_OP_LOGISTIC)) {
+          void* scp = nullptr;
+          if (nb_pool_alloc(ctx, 16, &scp) == NB_OK) {
+            e_sc = (float*)scp;
+            k_set_scale<<<1, 1, 0, ctx->stream>>>(e_sc, 32768.f);
+            ctx->stats.kernel_launches++;
+            g.epi.s_fp16 = 1;
+            g.epi.s_scale = 32768.f;
+          }
+        }
       }
     }
     {
@@ -1535,12 +1755,11 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
       nb_pool_release(ctx, rs_partial);
     }
     if (e_hi) {
-      if (rc == NB_OK) cache_insert(ctx, st, SplitEntry{C, m, n, ldc, e_ld, kind, e_hi, e_lo, 0});
-      else { nb_pool_release(ctx, e_hi); nb_pool_release(ctx, e_lo); }
+      SplitEntry ne{C, m, n, ldc, e_ld, kind, e_sc ? FMT_FP16 : FMT_BF16, e_hi, e_lo, e_sc, 0};
+      if (rc == NB_OK) cache_insert(ctx, st, ne);
+      else entry_release(ctx, ne);
     }
   }
-  for (int i = 0; i < 4; ++i)
-    if (tmp[i]) nb_pool_release(ctx, tmp[i]);
   return rc;
 }
 

@@ -25,7 +25,16 @@ class Context:
         self.h = h
         self.device = device
         self.L = L
+        # Float32 GEMM arithmetic (include/nabla_cuda.h nb_math_mode).  MATH_DEFAULT is a policy, not one mode:
+        # forward products run FP16X3 (22-bit operands: their error is amplified by saturating activations —
+        # width-8192 MLP: BF16X3 forward products put 7e-4 on the gradient, outside rtol 1e-4), adjoint products
+        # run BF16X3 (16-bit split of the sensitivities, any dynamic range; their error enters the gradient linearly)
+        # re-using the cached 22-bit splits of the forward values.  Any other value applies to every product.
         self.math_mode = _lib.MATH_DEFAULT
+        names = {"fp16x3": _lib.MATH_FP16X3, "bf16x3": _lib.MATH_BF16X3, "3xtf32": _lib.MATH_3XTF32,
+                 "tf32": _lib.MATH_TF32, "fp32": _lib.MATH_FP32}
+        self._fwd_math = names.get(os.environ.get("NB_F32_FWD_MATH", "").lower())
+        self._adj_math = names.get(os.environ.get("NB_F32_ADJ_MATH", "").lower())
         self._progs = {}
         self.nranks, self.rank = 1, 0
         self._deferred = []   # weak references to launches that have been deferred (fusion.py)
@@ -38,6 +47,18 @@ class Context:
             self._progs.clear()
             self.L.nb_ctx_destroy(self.h)
             self.h = None
+
+    def forward_math(self):
+        """nb_math_mode of a forward (primal) product."""
+        if self.math_mode != _lib.MATH_DEFAULT:
+            return self.math_mode
+        return self._fwd_math if self._fwd_math is not None else _lib.MATH_FP16X3
+
+    def adjoint_math(self):
+        """nb_math_mode of an adjoint product (Ā = Ȳ·Bᵀ, B̄ = Aᵀ·Ȳ)."""
+        if self.math_mode != _lib.MATH_DEFAULT:
+            return self.math_mode
+        return self._adj_math if self._adj_math is not None else _lib.MATH_BF16X3
 
     def sync(self):
         check(self.L.nb_sync(self.h), self.h)

@@ -121,8 +121,9 @@ class Deferred:
     The result array holds this object in ``.pending``; the object only holds a weak reference back, so an
     intermediate nobody keeps (and its operands) is released by reference counting."""
 
-    def __init__(self, ctx, tA, tB, alpha, A, B, m, n, k):
+    def __init__(self, ctx, tA, tB, alpha, A, B, m, n, k, math=None):
         self.ctx = ctx
+        self.math = ctx.forward_math() if math is None else math
         self.tA, self.tB, self.alpha, self.A, self.B = tA, tB, alpha, A, B
         self.m, self.n, self.k = m, n, k
         self.stage = 0
@@ -143,7 +144,7 @@ class Deferred:
         return out
 
     def extended(self):
-        d = Deferred(self.ctx, self.tA, self.tB, self.alpha, self.A, self.B, self.m, self.n, self.k)
+        d = Deferred(self.ctx, self.tA, self.tB, self.alpha, self.A, self.B, self.m, self.n, self.k, self.math)
         d.stage, d.kind, d.op, d.bias, d.ysaved = self.stage, self.kind, self.op, self.bias, self.ysaved
         return d
 
@@ -172,7 +173,7 @@ class Deferred:
     def _launch(self, out, rowsum):
         ctx, m, n, k = self.ctx, self.m, self.n, self.k
         if self.kind == 0 and rowsum is None:
-            K.gemm(self.tA, self.tB, self.alpha, self.A, self.B, 0.0, out, m, n, k)
+            K.gemm(self.tA, self.tB, self.alpha, self.A, self.B, 0.0, out, m, n, k, math=self.math)
             return
         epi = nb_gemm_epilogue()
         epi.kind = self.kind or 1
@@ -189,7 +190,7 @@ class Deferred:
         try:
             with K._timed(ctx, f"gemm_{self.tA}{self.tB}_{m}x{n}x{k}", 2.0 * m * n * k, "FLOP"):
                 check(ctx.L.nb_gemm_fused(ctx.h, self.tA.encode(), self.tB.encode(), m, n, k, float(self.alpha),
-                                          pa, lda, pb, ldb, pc, m, out.nb_dtype, ctx.math_mode, C.byref(epi)),
+                                          pa, lda, pb, ldb, pc, m, out.nb_dtype, self.math, C.byref(epi)),
                       ctx.h)
             return
         except UnsupportedOp:
@@ -201,7 +202,7 @@ class Deferred:
         from .scalar import CATALOGUE, compile_scalar
         ctx, m, n, k = self.ctx, self.m, self.n, self.k
         z = ctx.empty((m, n), out.dtype)
-        K.gemm(self.tA, self.tB, self.alpha, self.A, self.B, 0.0, z, m, n, k)
+        K.gemm(self.tA, self.tB, self.alpha, self.A, self.B, 0.0, z, m, n, k, math=self.math)
         f = CATALOGUE[_NAME[self.op]]
         if self.kind == 2:
             K.bcast_pullback(compile_scalar(f, 1), z, self.ysaved, [self.ysaved], [out], [False])
@@ -216,7 +217,7 @@ class Deferred:
                            accumulate=self.rowsum_acc)
 
 
-def defer_product(tA, tB, alpha, A, B, m, n, k):
+def defer_product(tA, tB, alpha, A, B, m, n, k, math=None):
     """-> a lazy (m x n) result for ``alpha*op(A)*op(B)``, or None when the product should run now.
 
     Deferred: Float32 products on the tensor-core path (not the FP32 SIMT cross-check mode), also inside a
@@ -226,9 +227,10 @@ def defer_product(tA, tB, alpha, A, B, m, n, k):
     ctx = A.ctx
     if not ctx.fuse or A.dtype.itemsize != 4 or m * n * k < (1 << 18) or min(m, n, k) < 1:
         return None
-    if ctx.math_mode == _lib.MATH_FP32:
+    math = ctx.forward_math() if math is None else math
+    if math == _lib.MATH_FP32:
         return None
-    return Deferred(ctx, tA, tB, alpha, A, B, m, n, k).new_result()
+    return Deferred(ctx, tA, tB, alpha, A, B, m, n, k, math).new_result()
 
 
 def _pending(x, kinds=(0,), max_stage=0):

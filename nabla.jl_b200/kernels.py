@@ -95,15 +95,17 @@ def bcast_pullback(prog, ybar, y_saved, args, outs, accumulate):
     return outs
 
 
-def gemm(tA, tB, alpha, A, B, beta, Cm, m, n, k, lda=None, ldb=None, ldc=None):
+def gemm(tA, tB, alpha, A, B, beta, Cm, m, n, k, lda=None, ldb=None, ldc=None, math=None):
+    """``math``: nb_math_mode of this product (default: the context's forward-product mode)."""
     ctx = Cm.ctx
+    math = ctx.forward_math() if math is None else math
     lda = lda or (k if tA == "T" else m)
     ldb = ldb or (n if tB == "T" else k)
     ldc = ldc or m
     pa, pb, pc = A.ptr, B.ptr, Cm.ptr   # (forces deferred operands BEFORE the timed region starts)
     with _timed(ctx, f"gemm_{tA}{tB}_{m}x{n}x{k}", 2.0 * m * n * k, "FLOP"):
         check(ctx.L.nb_gemm(ctx.h, tA.encode(), tB.encode(), m, n, k, float(alpha), pa, lda, pb, ldb,
-                            float(beta), pc, ldc, Cm.nb_dtype, ctx.math_mode), ctx.h)
+                            float(beta), pc, ldc, Cm.nb_dtype, math), ctx.h)
     return Cm
 
 

@@ -367,19 +367,21 @@ def _matmul_fused(y, ybar, rvs):
     d_tape = rvs.tape
     ctx, dt = A.ctx, A.dtype
     ybar = K.materialize(ybar)
+    adj = ctx.adjoint_math()
     if kind == "mm":
         m, k = A.shape
         n = B.shape[1]
         if isinstance(An, Node):
             out, beta = _slot_target(d_tape, An.pos, A.shape, ctx, dt)
-            K.gemm("N", "T", 1.0, ybar, B, beta, out, m, k, n)      # Ȳ (m×n) · Bᵀ (n×k)
+            K.gemm("N", "T", 1.0, ybar, B, beta, out, m, k, n, math=adj)      # Ȳ (m×n) · Bᵀ (n×k)
         if isinstance(Bn, Node):
-            lazy = fusion.defer_product("T", "N", 1.0, A, ybar, k, n, m) if d_tape[Bn.pos - 1] is UNDEF else None
+            lazy = (fusion.defer_product("T", "N", 1.0, A, ybar, k, n, m, math=adj)
+                    if d_tape[Bn.pos - 1] is UNDEF else None)
             if lazy is not None:   # the pullback of the Branch that produced B may join this launch
                 d_tape[Bn.pos - 1] = lazy
             else:
                 out, beta = _slot_target(d_tape, Bn.pos, B.shape, ctx, dt)
-                K.gemm("T", "N", 1.0, A, ybar, beta, out, k, n, m)      # Aᵀ (k×m) · Ȳ (m×n)
+                K.gemm("T", "N", 1.0, A, ybar, beta, out, k, n, m, math=adj)      # Aᵀ (k×m) · Ȳ (m×n)
     elif kind == "mv":
         m, k = A.shape
         if isinstance(An, Node):
@@ -480,6 +482,7 @@ def _gemm_fused(y, ybar, rvs):
     ybar = K.materialize(ybar)
     d_tape = rvs.tape
     ctx, dt = A.ctx, A.dtype
+    adj = ctx.adjoint_math()
     if len(y.args) == 5 and isinstance(y.args[2], Node):
         aN = y.args[2]  # ᾱ = <Ȳ, op(A) op(B)> = <Ȳ, Y> / α
         tmp = ctx.empty((), dt)
@@ -489,15 +492,15 @@ def _gemm_fused(y, ybar, rvs):
     if isinstance(An, Node):
         out, beta = _slot_target(d_tape, An.pos, A.shape, ctx, dt)
         if not tAt:   # Ā (m×k) = α Ȳ op(B)ᵀ
-            K.gemm("N", "N" if tBt else "T", alpha, ybar, B, beta, out, m, k, n)
+            K.gemm("N", "N" if tBt else "T", alpha, ybar, B, beta, out, m, k, n, math=adj)
         else:         # Ā (k×m) = α op(B) Ȳᵀ
-            K.gemm("T" if tBt else "N", "T", alpha, B, ybar, beta, out, k, m, n)
+            K.gemm("T" if tBt else "N", "T", alpha, B, ybar, beta, out, k, m, n, math=adj)
     if isinstance(Bn, Node):
         out, beta = _slot_target(d_tape, Bn.pos, B.shape, ctx, dt)
         if not tBt:   # B̄ (k×n) = α op(A)ᵀ Ȳ
-            K.gemm("N" if tAt else "T", "N", alpha, A, ybar, beta, out, k, n, m)
+            K.gemm("N" if tAt else "T", "N", alpha, A, ybar, beta, out, k, n, m, math=adj)
         else:         # B̄ (n×k) = α Ȳᵀ op(A)
-            K.gemm("T", "T" if tAt else "N", alpha, ybar, A, beta, out, n, k, m)
+            K.gemm("T", "T" if tAt else "N", alpha, ybar, A, beta, out, n, k, m, math=adj)
 
 
 _gemm = Primitive("gemm", _gemm_forward, fused=_gemm_fused, returns_saved=True)
