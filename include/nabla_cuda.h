@@ -210,7 +210,9 @@ int32_t nb_gemm(nb_ctx* ctx, char tA, char tB, int64_t m, int64_t n, int64_t k, 
  *                      (identity, tanh, logistic, exp, sqrt, inv, ...: DiffRules forms used by fmad, core.jl:285-292)
  *   rowsum (nullable)  rowsum[i] (+)= sum_j C[i,j]                 the bias sensitivity: unbroadcast of the
  *                      `.+` pullback (functional.jl:61-63), deterministic two-phase sum
- *   emit_split         also keep the tensor-core operand split of C for the products that consume it next
+ *   emit_split         bit 0: also keep the tensor-core operand split of C (in this product's own 16-bit format) for
+ *                      the products that consume it next; bit 1: a forward value emitted as binary16 is ALSO emitted
+ *                      as bfloat16, for the adjoint products that run in NB_MATH_BF16X3
  * Only the Float32 tensor-core path implements it: NB_ERR_UNSUPPORTED (nothing launched) otherwise, and the
  * caller runs the unfused sequence nb_gemm + nb_bcast_fwd / nb_bcast_pullback. */
 typedef struct nb_gemm_epilogue {

@@ -24,6 +24,10 @@
 #include "ops.cuh"
 #include "bcast_types.cuh"
 
+int32_t nb_gemm_skinny(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
+                       int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int32_t dtype,
+                       const nb_gemm_epilogue* epi, int32_t math_mode);  // gemm_skinny.cu
+
 namespace {
 using namespace nbb;
 
@@ -1243,8 +1247,15 @@ int32_t nb_fill(nb_ctx* ctx, void* dst, int32_t dtype, uint64_t count, double va
 int32_t nb_gemv(nb_ctx* ctx, char tA, int64_t m, int64_t n, double alpha, const void* A,
                 int64_t lda, const void* x, double beta, void* y, int32_t dtype) {
   NB_REQUIRE(ctx, ctx && A && x && y, NB_ERR_INVALID, "NULL argument");
-  NB_REQUIRE(ctx, lda == m, NB_ERR_UNSUPPORTED, "nb_gemv: only dense (lda == m) matrices are supported");
+  NB_REQUIRE(ctx, lda >= m, NB_ERR_SHAPE, "nb_gemv: leading dimension too small (DimensionMismatch)");
   const bool tr = tA == 'T' || tA == 't' || tA == 'C' || tA == 'c';
+  if (m > 0 && n > 0) {  // the streaming skinny-GEMM kernels (gemm_skinny.cu): A read once with 16-byte loads, any lda
+    nb_note_write(ctx, y);
+    int32_t rc = nb_gemm_skinny(ctx, tr, false, tr ? n : m, 1, tr ? m : n, alpha, A, lda, x, tr ? m : n, beta, y,
+                                tr ? n : m, dtype, nullptr, 0);
+    if (rc != NB_ERR_UNSUPPORTED) return rc;
+  }
+  NB_REQUIRE(ctx, lda == m, NB_ERR_UNSUPPORTED, "nb_gemv: small matrices must be dense (lda == m)");
   static const nb_prog mul = {2, 1, 0, {NB_OP_MUL}, {0}, {1}, {0}};
   const int64_t ylen = tr ? n : m;
   if (beta != 0.0 && beta != 1.0) {  // y *= beta first
@@ -1269,7 +1280,13 @@ int32_t nb_gemv(nb_ctx* ctx, char tA, int64_t m, int64_t n, double alpha, const 
 int32_t nb_ger(nb_ctx* ctx, int64_t m, int64_t n, double alpha, const void* x, const void* y,
                double beta, void* A, int64_t lda, int32_t dtype) {
   NB_REQUIRE(ctx, ctx && A && x && y, NB_ERR_INVALID, "NULL argument");
-  NB_REQUIRE(ctx, lda == m, NB_ERR_UNSUPPORTED, "nb_ger: only dense (lda == m) matrices are supported");
+  NB_REQUIRE(ctx, lda >= m, NB_ERR_SHAPE, "nb_ger: leading dimension too small (DimensionMismatch)");
+  if (m > 0 && n > 0) {  // k = 1 product: the small-K kernel of gemm_skinny.cu (any lda, any beta)
+    nb_note_write(ctx, A);
+    int32_t rc = nb_gemm_skinny(ctx, false, false, m, n, 1, alpha, x, m, y, 1, beta, A, lda, dtype, nullptr, 0);
+    if (rc != NB_ERR_UNSUPPORTED) return rc;
+  }
+  NB_REQUIRE(ctx, lda == m, NB_ERR_UNSUPPORTED, "nb_ger: small matrices must be dense (lda == m)");
   NB_REQUIRE(ctx, beta == 0.0 || beta == 1.0, NB_ERR_UNSUPPORTED, "nb_ger: beta must be 0 or 1");
   static const nb_prog mul = {2, 1, 0, {NB_OP_MUL}, {0}, {1}, {0}};
   nb_tensor args[2] = {nb_tensor{(void*)x, dtype, 2, {m, 1, 1, 1}}, nb_tensor{(void*)y, dtype, 2, {1, n, 1, 1}}};

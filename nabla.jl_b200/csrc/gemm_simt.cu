@@ -17,6 +17,10 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
                         const float* A, int64_t lda, const float* B, int64_t ldb, float beta,
                         float* C, int64_t ldc, int32_t math_mode, const nb_gemm_epilogue* epi);
 
+int32_t nb_gemm_skinny(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha, const void* A,
+                       int64_t lda, const void* B, int64_t ldb, double beta, void* C, int64_t ldc, int32_t dtype,
+                       const nb_gemm_epilogue* epi, int32_t math_mode);  // gemm_skinny.cu
+
 namespace {
 
 constexpr int BM = 64, BN = 64, BK = 16, TM = 4, TN = 4;
@@ -152,6 +156,10 @@ int32_t nb_gemm(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k
     NB_LAUNCH_CHECK(ctx);
     return NB_OK;
   }
+  {  // one dimension <= 16: HBM-bound streaming kernels, plain FMA in the element type (gemm_skinny.cu)
+    int32_t rc = nb_gemm_skinny(ctx, tA, tB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, dtype, nullptr, math_mode);
+    if (rc != NB_ERR_UNSUPPORTED) return rc;
+  }
   if (dtype == NB_F64) {
     // large products: exact integer slice products on the tensor cores (ozaki.cu); NB_F64_OZAKI=0 or
     // math_mode == NB_MATH_FP32 (the "no tensor-core tricks" cross-check mode) keeps everything on DMMA
@@ -193,7 +201,14 @@ int32_t nb_gemm_fused(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int
   // Float64: not fused.  A fused DMMA epilogue was built and measured (same box, graph replay of the Float64
   // examples): MLP 0.93 ms vs 0.81 ms, VAE 1.60 vs 1.42 — the DMMA kernel is not persistent, so the epilogue work
   // becomes a serial tail of every CTA instead of overlapping the next tile, and it slowed the plain products too.
-  if (dtype != NB_F32 || math_mode == NB_MATH_FP32 || alpha == 0.0) return NB_ERR_UNSUPPORTED;
+  if (alpha == 0.0) return NB_ERR_UNSUPPORTED;
+  if (math_mode != NB_MATH_FP32 || dtype == NB_F64) {
+    nb_note_write(ctx, C);
+    if (epi->rowsum) nb_note_write(ctx, epi->rowsum);
+    int32_t rc = nb_gemm_skinny(ctx, tA, tB, m, n, k, alpha, A, lda, B, ldb, 0.0, C, ldc, dtype, epi, math_mode);
+    if (rc != NB_ERR_UNSUPPORTED) return rc;
+  }
+  if (dtype != NB_F32 || math_mode == NB_MATH_FP32) return NB_ERR_UNSUPPORTED;
   nb_note_write(ctx, C);
   if (epi->rowsum) nb_note_write(ctx, epi->rowsum);
   return nb_gemm_tcgen05(ctx, tA, tB, m, n, k, (float)alpha, (const float*)A, lda, (const float*)B, ldb, 0.f,

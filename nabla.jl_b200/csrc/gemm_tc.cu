@@ -113,6 +113,8 @@ struct EpiArgs {
   int64_t ld_s;
   int32_t s_fp16;         // the emitted 16-bit split is scaled binary16 (x * s_scale) instead of bfloat16
   float s_scale;
+  void* s2_hi;            // nullable: a second, bfloat16 split of C (same ld_s) next to a binary16 one — forward values
+  void* s2_lo;            // feed the next forward product (binary16) AND the adjoint products (bfloat16)
   int32_t last_launch;    // this launch covers the end of K
 };
 
@@ -463,6 +465,14 @@ struct EpiAcc {
               *reinterpret_cast<uint4*>(hp) = *reinterpret_cast<const uint4*>(h);
               *reinterpret_cast<uint4*>(lp) = *reinterpret_cast<const uint4*>(l);
             }
+            if (KIND == KIND_BF16X3 && g.epi.s2_hi) {
+              __align__(8) __nv_bfloat16 h2[4];
+              __align__(8) __nv_bfloat16 l2[4];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) split1(x[gq][i], h2[i], l2[i]);
+              *reinterpret_cast<uint2*>((__nv_bfloat16*)g.epi.s2_hi + R0 + col * g.epi.ld_s) = *reinterpret_cast<const uint2*>(h2);
+              *reinterpret_cast<uint2*>((__nv_bfloat16*)g.epi.s2_lo + R0 + col * g.epi.ld_s) = *reinterpret_cast<const uint2*>(l2);
+            }
           }
         }
       }
@@ -557,6 +567,12 @@ struct EpiAcc {
           else
             split1(x[j], h, l);
           if (j < jmax) { hp[(int64_t)j * g.epi.ld_s] = h; lp[(int64_t)j * g.epi.ld_s] = l; }
+          if (KIND == KIND_BF16X3 && g.epi.s2_hi && j < jmax) {
+            __nv_bfloat16 h2, l2;
+            split1(x[j], h2, l2);
+            ((__nv_bfloat16*)g.epi.s2_hi)[gm + (nb + j) * g.epi.ld_s] = h2;
+            ((__nv_bfloat16*)g.epi.s2_lo)[gm + (nb + j) * g.epi.ld_s] = l2;
+          }
         }
       }
     }
@@ -1431,29 +1447,22 @@ void cache_insert(nb_ctx* ctx, GemmState* st, SplitEntry e) {
 }
 
 // Split of the column-major source (rows x cols, ld_in), cached until the source buffer is written or released.
-// `fmt` is the wanted 16-bit format (KIND_BF16X3); with `any_fmt` a cached split of the other format is accepted too
-// (the MMA takes binary16 and bfloat16 operands in any combination).  The entry (and the cache) owns hi / lo / sc.
+// `fmt` is the 16-bit format (KIND_BF16X3): both operands of one tcgen05.mma must have the SAME format (a binary16 A
+// with a bfloat16 B raises an illegal-instruction fault on sm_100a — measured), so an array that is multiplied in both
+// modes has both splits cached.  The entry (and the cache) owns hi / lo / sc.
 // Inside a CUDA-graph capture the cache works the same way — the entries then describe buffers of the capture and
 // are dropped when it ends (nb_graph_begin / nb_graph_end / nb_graph_launch clear the cache).
-int32_t get_split(nb_ctx* ctx, GemmState* st, int kind, int fmt, bool any_fmt, const float* src, int64_t rows,
+int32_t get_split(nb_ctx* ctx, GemmState* st, int kind, int fmt, const float* src, int64_t rows,
                   int64_t cols, int64_t ld_in, int64_t ld_out, int esize, SplitEntry* out) {
   {
     std::lock_guard<std::mutex> lk(st->cache_mu);
-    SplitEntry* other = nullptr;
     for (auto& e : st->cache)
-      if (e.src == src && e.rows == rows && e.cols == cols && e.ld_in == ld_in && e.kind == kind) {
-        if (kind != KIND_BF16X3 || e.fmt == fmt) {
-          e.stamp = ++st->clock;
-          *out = e;
-          return NB_OK;
-        }
-        other = &e;
+      if (e.src == src && e.rows == rows && e.cols == cols && e.ld_in == ld_in && e.kind == kind &&
+          (kind != KIND_BF16X3 || e.fmt == fmt)) {
+        e.stamp = ++st->clock;
+        *out = e;
+        return NB_OK;
       }
-    if (other && any_fmt) {
-      other->stamp = ++st->clock;
-      *out = *other;
-      return NB_OK;
-    }
   }
   SplitEntry e{src, rows, cols, ld_in, ld_out, kind, kind == KIND_BF16X3 ? fmt : FMT_BF16, nullptr, nullptr, nullptr, 0};
   const size_t bytes = (size_t)(ld_out * cols) * esize;
@@ -1560,6 +1569,36 @@ void nb_split_cache_clear(nb_ctx* ctx) {
   for (auto& e : all) entry_release(ctx, e);
 }
 
+// Operand-split emission for kernels outside this file (gemm_skinny.cu): buffers for the 16-bit split of an m x n
+// Float32 result that the NEXT product will consume, registered in the cache once the producing launch is enqueued.
+// Sensitivities (and everything unbounded) are emitted as bfloat16; *hi stays NULL when nothing should be emitted.
+int32_t nb_split_emit_begin(nb_ctx* ctx, int32_t math_mode, int32_t epi_kind, int32_t epi_op, int64_t m, int64_t n,
+                            void** hi, void** lo, int64_t* ld, int32_t* fp16, float* scale, float** sc) {
+  *hi = *lo = nullptr;
+  *sc = nullptr;
+  *fp16 = 0;
+  *scale = 1.f;
+  (void)epi_kind; (void)epi_op;
+  if (math_mode == NB_MATH_TF32 || math_mode == NB_MATH_3XTF32 || math_mode == NB_MATH_FP32) return NB_OK;
+  if (math_mode != NB_MATH_BF16X3) return NB_OK;   // binary16 consumers compute their own scale (absmax pass)
+  GemmState* st = state_of(ctx);
+  if (!st->encode) return NB_OK;
+  const int64_t e_ld = (m + 7) / 8 * 8;
+  const size_t bytes = (size_t)(e_ld * n) * 2;
+  if (nb_pool_alloc(ctx, bytes, hi) != NB_OK) { *hi = nullptr; return NB_OK; }
+  if (nb_pool_alloc(ctx, bytes, lo) != NB_OK) { nb_pool_release(ctx, *hi); *hi = *lo = nullptr; return NB_OK; }
+  *ld = e_ld;
+  return NB_OK;
+}
+
+void nb_split_emit_end(nb_ctx* ctx, bool ok, const void* C, int64_t m, int64_t n, int64_t ldc, int64_t ld, void* hi,
+                       void* lo, float* sc) {
+  if (!hi) return;
+  SplitEntry e{C, m, n, ldc, ld, KIND_BF16X3, sc ? FMT_FP16 : FMT_BF16, hi, lo, sc, 0};
+  if (ok) cache_insert(ctx, state_of(ctx), e);
+  else entry_release(ctx, e);
+}
+
 void nb_gemm_state_free(nb_ctx* ctx) {
   nb_split_cache_clear(ctx);
   if (ctx->gemm_state && ((GemmState*)ctx->gemm_state)->tile_counter) cudaFree(((GemmState*)ctx->gemm_state)->tile_counter);
@@ -1579,11 +1618,9 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
   if (m * n * k < (int64_t)1 << 18) return NB_ERR_UNSUPPORTED;  // tiny: one tile would idle 147 SMs
   if (m >= (1ll << 31) || n >= (1ll << 31) || k >= (1ll << 31)) return NB_ERR_UNSUPPORTED;
   const int kind = math_mode == NB_MATH_TF32 ? KIND_TF32 : math_mode == NB_MATH_3XTF32 ? KIND_3XTF32 : KIND_BF16X3;
-  // 16-bit split kinds: NB_MATH_FP16X3 (and NB_MATH_DEFAULT) wants both operands as scaled binary16 (22 bits);
-  // NB_MATH_BF16X3 wants bfloat16 (16 bits, any dynamic range) but re-uses a cached binary16 split of an operand
-  // when there is one (forward values in the adjoint products: more accurate and no second split pass)
+  // 16-bit split kinds: NB_MATH_FP16X3 (and NB_MATH_DEFAULT) splits both operands as scaled binary16 (22 bits),
+  // NB_MATH_BF16X3 as bfloat16 (16 bits, any dynamic range)
   const int want_fmt = math_mode == NB_MATH_BF16X3 ? FMT_BF16 : FMT_FP16;
-  static const bool mixed_ok = !(getenv("NB_GEMM_MIXED_FMT") && atoi(getenv("NB_GEMM_MIXED_FMT")) == 0);
   if (kind == KIND_TF32) {
     if (((uintptr_t)A | (uintptr_t)B) & 15) return NB_ERR_UNSUPPORTED;
     if ((lda & 3) || (ldb & 3)) return NB_ERR_UNSUPPORTED;
@@ -1616,10 +1653,9 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     const int64_t pad = 16 / esize;  // leading dimensions of the split copies: 16-byte multiples
     ld_a = (a_r + pad - 1) / pad * pad;
     ld_b = (b_r + pad - 1) / pad * pad;
-    const bool any = mixed_ok && want_fmt == FMT_BF16;
-    int32_t rc = get_split(ctx, st, kind, want_fmt, any, A, a_r, a_c, lda, ld_a, esize, &ea);
+    int32_t rc = get_split(ctx, st, kind, want_fmt, A, a_r, a_c, lda, ld_a, esize, &ea);
     if (rc != NB_OK) return rc;
-    rc = get_split(ctx, st, kind, want_fmt, any, B, b_r, b_c, ldb, ld_b, esize, &eb);
+    rc = get_split(ctx, st, kind, want_fmt, B, b_r, b_c, ldb, ld_b, esize, &eb);
     if (rc != NB_OK) return rc;
     src[0] = ea.hi; src[1] = ea.lo; src[2] = eb.hi; src[3] = eb.lo;
     // the operands' buffers must outlive this launch even if the cache drops the entries before it returns
@@ -1658,7 +1694,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     g.tile_counter = st->tile_counter;
     memset(&g.epi, 0, sizeof(g.epi));
     void* rs_partial = nullptr;
-    void *e_hi = nullptr, *e_lo = nullptr;
+    void *e_hi = nullptr, *e_lo = nullptr, *e2_hi = nullptr, *e2_lo = nullptr;
     float* e_sc = nullptr;
     int64_t e_ld = 0;
     if (fused) {
@@ -1695,6 +1731,14 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
             ctx->stats.kernel_launches++;
             g.epi.s_fp16 = 1;
             g.epi.s_scale = 32768.f;
+            if (epi->emit_split & 2) {  // the adjoint products will want this forward value in bfloat16 too
+              if (nb_pool_alloc(ctx, bytes, &e2_hi) == NB_OK && nb_pool_alloc(ctx, bytes, &e2_lo) == NB_OK) {
+                g.epi.s2_hi = e2_hi; g.epi.s2_lo = e2_lo;
+              } else {
+                if (e2_hi) nb_pool_release(ctx, e2_hi);
+                e2_hi = e2_lo = nullptr;
+              }
+            }
           }
         }
       }
@@ -1707,6 +1751,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
         if (g.epi.y) v = v && al16(g.epi.y) && (g.epi.ldy % 4 == 0);
         if (g.epi.rowsum_partial) v = v && al16(g.epi.rowsum_partial);
         if (g.epi.s_hi) v = v && al16(g.epi.s_hi) && al16(g.epi.s_lo) && (g.epi.ld_s % 8 == 0);
+        if (g.epi.s2_hi) v = v && al16(g.epi.s2_hi) && al16(g.epi.s2_lo);
       }
       if (const char* e = getenv("NB_GEMM_VEC_STORE")) v = v && atoi(e) != 0;
       g.vec_store = v ? 1 : 0;
@@ -1758,6 +1803,11 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
       SplitEntry ne{C, m, n, ldc, e_ld, kind, e_sc ? FMT_FP16 : FMT_BF16, e_hi, e_lo, e_sc, 0};
       if (rc == NB_OK) cache_insert(ctx, st, ne);
       else entry_release(ctx, ne);
+    }
+    if (e2_hi) {
+      SplitEntry n2{C, m, n, ldc, e_ld, kind, FMT_BF16, e2_hi, e2_lo, nullptr, 0};
+      if (rc == NB_OK) cache_insert(ctx, st, n2);
+      else entry_release(ctx, n2);
     }
   }
   return rc;

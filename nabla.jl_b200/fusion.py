@@ -184,6 +184,9 @@ class Deferred:
         epi.rowsum = rowsum.ptr if rowsum is not None else None
         epi.rowsum_acc = 1 if self.rowsum_acc else 0
         epi.emit_split = 1 if m * n >= (1 << 16) else 0
+        if epi.emit_split and epi.kind == 1 and ctx.adjoint_math() == _lib.MATH_BF16X3 \
+                and self.math in (_lib.MATH_FP16X3, _lib.MATH_DEFAULT):
+            epi.emit_split |= 2   # a forward value: the adjoint products (bfloat16 splits) will read it as well
         lda = k if self.tA == "T" else m
         ldb = n if self.tB == "T" else k
         pa, pb, pc = self.A.ptr, self.B.ptr, out.ptr   # (forces deferred operands before the timed region)
