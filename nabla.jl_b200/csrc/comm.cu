@@ -132,7 +132,8 @@ int32_t nb_allreduce_sum_async(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, c
   NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
   if (ctx->nranks == 1 && !ctx->nccl_comm) return NB_OK;
   NB_REQUIRE(ctx, ctx->nccl_comm, NB_ERR_COMM, "nb_allreduce_sum_async: nb_comm_init was not called");
-  NB_REQUIRE(ctx, !ctx->capturing, NB_ERR_UNSUPPORTED, "overlapped reductions cannot be captured into a graph");
+  // (inside nb_graph_begin/end the fork below pulls the communicator stream into the capture; NCCL collectives are
+  //  capturable, and nb_comm_join — required before nb_graph_end — joins it back)
   if (!ctx->comm_stream) {
     NB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
     NB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));

@@ -1763,8 +1763,17 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     // long K is launched in ranges so that the operand panel of a rasterisation group fits the L2
     int64_t KRANGE = 8192;
     if (const char* e = getenv("NB_GEMM_KRANGE")) KRANGE = atoll(e) >= 64 ? atoll(e) / 64 * 64 : KRANGE;
-    int64_t kchunk = kind == KIND_3XTF32 ? KindT<KIND_3XTF32>::KCHUNK : KindT<KIND_BF16X3>::KCHUNK;
+    // K accumulated in TMEM before the epilogue folds it into its register sum.  The tensor core adds every
+    // tcgen05.mma into the FP32 accumulator with TRUNCATION, a bias that grows linearly with the number of adds:
+    // measured per product (8192 x 512 x 8192, tools/sweep_kchunk.py) 7.1e-6 at 2048, 1.7e-6 at 512, 8.4e-7 at 256,
+    // 4.1e-7 at 128 for the binary16 split (tf32: twice that, its MMA covers half the K).  The accurate modes
+    // (FP16x3, 3xTF32: forward products, whose error saturating activations amplify ~80x at width 8192) fold every
+    // 128; BF16x3 (adjoint products: operand-limited at 4.5e-6 anyway) keeps 2048.  Cost of 128: -15 % on a
+    // 8192 x 32768 x 8192 product (the fold's TMEM reads sit between two short MMA chunks).
+    int64_t kchunk = math_mode == NB_MATH_BF16X3 ? KindT<KIND_BF16X3>::KCHUNK : 128;
     if (const char* e = getenv("NB_GEMM_KCHUNK")) kchunk = atoll(e) >= 64 ? atoll(e) / 64 * 64 : kchunk;
+    if (math_mode != NB_MATH_BF16X3)
+      if (const char* e = getenv("NB_GEMM_KCHUNK_ACC")) kchunk = atoll(e) >= 64 ? atoll(e) / 64 * 64 : kchunk;
     g.kchunk_kb = (int32_t)(kchunk / (128 / esize));
     g.hint_a = g.hint_b = 0;
     if (const char* e = getenv("NB_GEMM_HINT")) {  // 1: A evict_last  2: B evict_last  +4: the other evict_first

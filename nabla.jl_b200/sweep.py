@@ -13,7 +13,7 @@ import ctypes as C
 import numpy as np
 
 from ._lib import check
-from .core import Leaf, Node, Tape, nabla, unbox, unthunk, zeroslike
+from .core import Leaf, Node, Tape, nabla, oneslike, unbox, unthunk, zeroslike
 from .device import get_context
 from .scalar import CATALOGUE, compile_scalar
 
@@ -155,27 +155,62 @@ class OverlappedShardedGradient:
 
     ``data_objective`` is this rank's shard of the batch-dependent term (its gradients are summed over
     ranks); ``shared_objective`` is the batch-independent term (the prior), evaluated identically on
-    every rank and never reduced.  Sweep 1 (data) starts the allreduce of each parameter sensitivity
-    on the communicator stream the moment the sensitivity is final (``propagate(..., on_final)``): the
-    last layer's weights travel over NVLink while the GEMMs of the layers below still run.  Sweep 2
-    (shared) then accumulates in place into the reduced buffers (the reverse tape is pre-filled with
-    them, so the reference's accumulate path ``add!!`` does the sum).  On one rank this launches exactly
-    the kernels of the single ``∇(data + shared)`` sweep in the same accumulation order."""
+    every rank.  Per step:
 
-    def __init__(self, data_objective, shared_objective, params, comm):
+    1. the shared term is swept FIRST with the seed ȳ = 1/G: its sensitivities (−λ/G·W for the prior of
+       examples/mlp.jl:61-65; exact for G a power of two) pre-fill the reverse tape of the data sweep — the reference's
+       own pre-filled-slot path (``compute_Dv_update``, src/finite_differencing.jl:57-85);
+    2. the data term is swept: every rule accumulates into the pre-filled slot (``add!!``, core.jl:203-205 — β = 1 in the
+       GEMM epilogue, ``+=`` in the row-sum), and the moment a parameter's sensitivity is final
+       (``propagate(..., on_final)``) its allreduce(sum) is started on the communicator's stream, so the weights of the
+       last layers travel over NVLink while the GEMMs of the layers below still run;
+    3. the sweep stream joins the communicator stream.  Nothing runs after the last exchange: the sum over ranks of
+       (data shard + shared/G) is the full gradient.
+
+    With ``capture=True`` the whole step — both sweeps, every NCCL call on the side stream and the join — is recorded once
+    as ONE CUDA graph and replayed (the tape signature of a fixed model is constant; NCCL collectives are capturable),
+    which removes the host launch path (~90 launches + 11 collectives per step) from the critical path."""
+
+    def __init__(self, data_objective, shared_objective, params, comm, capture=False):
         self.comm, self.ctx = comm, comm.ctx
         self.params = list(params)
         self.f_data, self.f_shared = data_objective, shared_objective
+        self._graph = None
+        self._keep = None
+        if capture:
+            self._capture()
 
-    def step(self):
-        from .core import oneslike, propagate, reverse_tape
+    # -- one step, enqueued on the context (and communicator) streams ---------------------------------------------
+    def _enqueue(self, keep_tapes=False):
+        from .core import UNDEF, own, propagate, reverse_tape
         from .kernels import bcast_fwd
-        comm = self.comm
-        # ---- sweep 1: data term, allreduce of every final leaf slot overlapped with the sweep
+        comm, ctx = self.comm, self.ctx
+        G = comm.nranks
+        # ---- sweep A: shared term, seeded with 1/G
+        pre = [None] * len(self.params)
+        y2v = None
+        tapes = []
+        if self.f_shared is not None:
+            t2 = Tape()
+            leaves2 = [Leaf(t2, p) for p in self.params]
+            y2 = self.f_shared(*leaves2)
+            if isinstance(y2, Node):
+                y2v = unbox(y2)
+                rt2 = propagate(t2, reverse_tape(y2, ctx.full(y2v.shape, 1.0 / G, y2v.dtype)))
+                for i, l in enumerate(leaves2):
+                    if rt2.isassigned(l):
+                        pre[i] = own(unthunk(rt2.raw(l)))
+                tapes.append((t2, rt2))
+                if not keep_tapes:
+                    t2.tape.clear()
+        # ---- sweep B: data term accumulates into the pre-filled slots; allreduce of every final leaf slot overlapped
         t = Tape()
         leaves = [Leaf(t, p) for p in self.params]
         y = self.f_data(*leaves)
         rt = reverse_tape(y, oneslike(y))
+        for l, g in zip(leaves, pre):
+            if g is not None:
+                rt.tape[l.pos - 1] = g
         grads = {}
 
         def on_final(leaf_pos, rvs):
@@ -188,24 +223,66 @@ class OverlappedShardedGradient:
 
         propagate(t, rt, on_final=on_final)
         yd = unbox(y)
-        comm.allreduce_sum_async([yd])
-        g1 = [grads.get(l.pos) for l in leaves]
-        t.tape.clear()
-        # ---- sweep 2: shared term accumulates in place into the reduced buffers
-        t2 = Tape()
-        leaves2 = [Leaf(t2, p) for p in self.params]
-        y2 = self.f_shared(*leaves2)
-        comm.join()                      # the reduced sensitivities are about to be updated
-        rt2 = reverse_tape(y2, oneslike(y2))
-        for l, g in zip(leaves2, g1):
-            if g is not None:
-                rt2.tape[l.pos - 1] = g
-        propagate(t2, rt2)
-        out = [unthunk(rt2.raw(l)) if rt2.isassigned(l) else zeroslike(l) for l in leaves2]
-        ytot = self.ctx.empty((), yd.dtype)
-        bcast_fwd(_ADD_PROG, [yd, unbox(y2)], ytot)
-        t2.tape.clear()
-        return ytot, out
+        rest = []
+        for l in leaves:            # parameters only the shared term touches: G copies of g/G
+            if l.pos not in grads and rt.tape[l.pos - 1] is not UNDEF:
+                grads[l.pos] = unthunk(rt.raw(l.pos))
+                rest.append(grads[l.pos])
+        comm.allreduce_sum_async([yd] + rest)
+        out = [grads[l.pos] if l.pos in grads else zeroslike(l) for l in leaves]
+        comm.join()
+        if y2v is not None:
+            ytot = ctx.empty((), yd.dtype)
+            bcast_fwd(_ADD_PROG, [yd, y2v], ytot)
+        else:
+            ytot = yd
+        tapes.append((t, rt))
+        if not keep_tapes:
+            t.tape.clear()
+        return ytot, out, tapes
+
+    def _capture(self):
+        ctx = self.ctx
+        L, h = ctx.L, ctx.h
+        self._enqueue()          # eager once: compiles programs, sizes the pool (no cudaMalloc inside the capture)
+        ctx.sync()
+        ctx.flush_deferred()
+        check(L.nb_graph_begin(h), h)
+        try:
+            y, grads, tapes = self._enqueue(keep_tapes=True)
+            for g in grads:
+                g.ptr               # deferred launches belong inside the capture
+            y.ptr
+            ctx.flush_deferred(only_side_outputs=True)
+        except BaseException:
+            g = C.c_void_p()
+            L.nb_graph_end(h, C.byref(g))
+            if g:
+                L.nb_graph_destroy(g)
+            raise
+        g = C.c_void_p()
+        check(L.nb_graph_end(h, C.byref(g)), h)
+        self._graph = g
+        self._keep = (y, grads, tapes)   # the graph refers to these buffers by address
+
+    def step(self):
+        if self._graph is not None:
+            check(self.ctx.L.nb_graph_launch(self.ctx.h, self._graph), self.ctx.h)
+            return self._keep[0], self._keep[1]
+        y, grads, _ = self._enqueue()
+        return y, grads
+
+    def close(self):
+        if self._graph is not None and self.ctx.h:
+            self.ctx.L.nb_graph_destroy(self._graph)
+        self._graph = None
+        self._keep = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class ShardedGradient:

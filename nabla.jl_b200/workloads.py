@@ -99,6 +99,37 @@ def vae_log_joint(nb, X, noise, Wh, Wmu, Wsig, Vh, Vf, lam, scal, dz, eps=1e-12,
     return scal * elbo + logprior
 
 
+def vae_data_objective(nb, X, noise, scal, dz, eps=1e-12):
+    """The batch-dependent part of ``vae_log_joint`` for THIS shard's columns of X and of the noise:
+    ``scal * (loglik - klqp_data)`` with ``scal`` from the GLOBAL batch (examples/vae.jl:59, 77-90)."""
+    logistic = logistic_of(nb)
+
+    def obj(Wh, Wmu, Wsig, Vh, Vf):
+        h_enc = nb.broadcast(nb.tanh, nb.matmul(Wh, X))
+        mu = nb.matmul(Wmu, h_enc)
+        sig = nb.broadcast(nb.exp, nb.matmul(Wsig, h_enc))
+        z = nb.broadcast(nb.add, mu, nb.broadcast(nb.mul, sig, noise))
+        f = nb.broadcast(logistic, nb.matmul(Vf, nb.broadcast(nb.tanh, nb.matmul(Vh, z))))
+        one_minus_X = nb.broadcast(nb.sub, 1.0, X)
+        t1 = nb.broadcast(nb.mul, X, nb.broadcast(nb.log, nb.broadcast(nb.add, f, eps)))
+        t2 = nb.broadcast(nb.mul, one_minus_X, nb.broadcast(nb.log, nb.broadcast(nb.sub, 1.0 + eps, f)))
+        loglik = nb.sum(nb.broadcast(nb.add, t1, t2))
+        sig2 = nb.broadcast(nb.mul, sig, sig)
+        kl = 0.5 * (nb.sum(sig2) + nb.sum(nb.abs2, mu) - nb.sum(nb.broadcast(nb.log, sig2)))
+        return scal * (loglik - kl)
+    return obj
+
+
+def vae_shared_objective(nb, lam, scal, dz):
+    """The batch-independent part: the log-prior (examples/vae.jl:70-71) and the constant ``D`` of klvae
+    (examples/vae.jl:39), which enters the objective as ``+ scal * D / 2``."""
+    def obj(Wh, Wmu, Wsig, Vh, Vf):
+        logprior = (-0.5 * lam) * (nb.sum(nb.abs2, Wh) + nb.sum(nb.abs2, Wmu) + nb.sum(nb.abs2, Wsig)
+                                   + nb.sum(nb.abs2, Vh) + nb.sum(nb.abs2, Vf))
+        return logprior + (0.5 * scal * float(dz))
+    return obj
+
+
 def vae_objective(nb, X, noise, lam, scal, dz, prior_scale=1.0):
     def obj(*params):
         return vae_log_joint(nb, X, noise, *params, lam=lam, scal=scal, dz=dz, prior_scale=prior_scale)

@@ -68,5 +68,5 @@ if "--mlp" in sys.argv or len(sys.argv) == 1:
         ctx._fwd_math, ctx._adj_math = f, a
         y, g = nb.nabla(wl.mlp_objective(nb, Xd, Yd, 1e-3, 5), get_output=True)(*W, *b)
         errs = [rel(x.numpy(), r) for x, r in zip(g, gr)]
-        print(name, "y", f"{abs(float(y.numpy()) - float(orc.unbox(yr))) / abs(float(orc.unbox(yr))):.1e}",
+        print(name, "y", f"{abs(float(nb.to_host(y)) - float(orc.unbox(yr))) / abs(float(orc.unbox(yr))):.1e}",
               "max", f"{max(errs):.2e}", [f"{e:.1e}" for e in errs], flush=True)

@@ -772,9 +772,10 @@ def test_gemm_tensor_core_modes(nb, ctx, mode, tol):
         ctx.math_mode = old
 
 
-def test_overlapped_sharded_gradient_single_rank_is_bitwise_the_plain_sweep(nb, ctx):
-    """data objective + shared objective evaluated as two sweeps (the multi-GPU path, nranks = 1 here)
-    launches the same kernels in the same accumulation order as ∇(mlp_log_joint): bitwise equal."""
+def test_overlapped_sharded_gradient_single_rank_equals_the_plain_sweep(nb, ctx):
+    """shared objective (swept first, its sensitivities pre-fill the reverse tape) + data objective (accumulates into
+    them: the reference's pre-filled-slot path) on one rank against the plain ∇(mlp_log_joint) sweep — the same terms
+    summed in the other order, so equal to rounding; also as a CUDA-graph replay of the whole step."""
     import nabla_jl_b200.workloads as wl
     dims, B = (20, 16, 12, 10), 64
     W, b, X, Y = wl.mlp_inputs(dims, B, np.float64, seed=0)
@@ -785,9 +786,18 @@ def test_overlapped_sharded_gradient_single_rank_is_bitwise_the_plain_sweep(nb, 
     og = nb.OverlappedShardedGradient(wl.mlp_data_objective(nb, Xd, Yd, 3), wl.mlp_prior_objective(nb, 1e-3, 3),
                                       params, comm)
     y, g = og.step()
-    np.testing.assert_allclose(float(_np(y)), float(_np(yr)), rtol=1e-15)
+    np.testing.assert_allclose(float(_np(y)), float(_np(yr)), rtol=1e-14)
     for a, r in zip(g, gr):
-        np.testing.assert_array_equal(_np(a), _np(r))
+        np.testing.assert_allclose(_np(a), _np(r), rtol=1e-13, atol=1e-13 * float(np.max(np.abs(_np(r)))))
+    oc = nb.OverlappedShardedGradient(wl.mlp_data_objective(nb, Xd, Yd, 3), wl.mlp_prior_objective(nb, 1e-3, 3),
+                                      params, comm, capture=True)
+    for _ in range(2):
+        y2, g2 = oc.step()
+    ctx.sync()
+    np.testing.assert_allclose(float(_np(y2)), float(_np(yr)), rtol=1e-14)
+    for a, r in zip(g2, gr):
+        np.testing.assert_allclose(_np(a), _np(r), rtol=1e-13, atol=1e-13 * float(np.max(np.abs(_np(r)))))
+    oc.close()
     # the hook fires once per parameter, in descending order of each Leaf's first consumer
     t = nb.Tape()
     leaves = [nb.Leaf(t, p) for p in params]
