@@ -48,21 +48,38 @@ __device__ __forceinline__ void stvec(T* p, const T (&v)[Vec<T>::N]) {
 
 constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
+// The small operand S (R <= 16 rows) is re-laid out once per call into the form each streaming kernel reads with
+// aligned 16-byte loads and no shared-memory staging (it stays L1/L2 resident: R x K elements, <= 4 MB):
+//   k_skinny_cc reads Sp[k][MRP]  (the R values of one k contiguous, padded to a multiple of 4)
+//   k_skinny_kc reads St[r][Kp]   (row r contiguous along k, Kp a multiple of 128, zero padded)
+template <typename T>
+__global__ void __launch_bounds__(256) k_pack_s(const T* __restrict__ S, int64_t sr, int64_t sk, int R, int64_t K,
+                                                T* __restrict__ out, int64_t o_r, int64_t o_k, int RP, int64_t Kp) {
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= (int64_t)RP * Kp) return;
+  // thread order follows the OUTPUT's contiguous index so the writes coalesce
+  int64_t k;
+  int r;
+  if (o_r == 1) { r = (int)(e % RP); k = e / RP; } else { k = e % Kp; r = (int)(e / Kp); }
+  out[(int64_t)r * o_r + k * o_k] = (r < R && k < K) ? S[(int64_t)r * sr + k * sk] : T(0);
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // out[r, c] = sum_k S[r, k] * G[c + k * ldg]      the big operand G has the OUTPUT index c contiguous
 // (small M: C = A * B' with B stored n x k;  small N: C' = B' * A' with A stored m x k).  Threads own V consecutive
-// c, CTAs own 256 * V of them and one K range; partial sums go to ws[z][r][c].
+// c, CTAs own 256 * V of them and one K range (split-K over gridDim.z); partial sums go to ws[z][r][c].
+// No barriers: eight 16-byte loads of G in flight per thread, S read through L1 as warp-uniform 16-byte loads.
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int MR>
 __global__ void __launch_bounds__(256) k_skinny_cc(const T* __restrict__ G, int64_t ldg, int64_t ncols, int64_t K,
-                                                   const T* __restrict__ S, int64_t sr, int64_t sk, int R,
-                                                   T* __restrict__ ws, int64_t kper, int vec_ok) {
+                                                   const T* __restrict__ Sp, int R, T* __restrict__ ws, int64_t kper,
+                                                   int vec_ok) {
   constexpr int V = Vec<T>::N;
-  constexpr int KC = 64;
-  constexpr int MRP = round_up(MR, V);
-  __shared__ __align__(16) T Ss[KC][MRP];
+  constexpr int MRP = round_up(MR, 4);
+  constexpr int UK = 8;
   const int tid = threadIdx.x;
   const int64_t c0 = ((int64_t)blockIdx.x * 256 + tid) * V;
+  if (c0 >= ncols) return;
   const int64_t kb = (int64_t)blockIdx.z * kper;
   const int64_t ke = kb + kper < K ? kb + kper : K;
   const bool fast = vec_ok && c0 + V <= ncols;
@@ -71,57 +88,36 @@ __global__ void __launch_bounds__(256) k_skinny_cc(const T* __restrict__ G, int6
   for (int r = 0; r < MR; ++r)
 #pragma unroll
     for (int v = 0; v < V; ++v) acc[r][v] = T(0);
-
-  for (int64_t k0 = kb; k0 < ke; k0 += KC) {
-    __syncthreads();
-    for (int e = tid; e < KC * MRP; e += 256) {
-      const int kk = e / MRP, r = e % MRP;
-      Ss[kk][r] = (r < R && k0 + kk < ke) ? S[(int64_t)r * sr + (k0 + kk) * sk] : T(0);
-    }
-    __syncthreads();
-    const int kn = (int)(ke - k0 < KC ? ke - k0 : KC);
-    if (c0 >= ncols) continue;
-    const T* gp = G + c0 + k0 * ldg;
-    if (fast) {
-      int kk = 0;
-      for (; kk + 4 <= kn; kk += 4) {   // four independent 16-byte loads in flight per thread
-        T b[4][V];
+  const T* gp = G + c0;
+  int64_t k = kb;
+  if (fast) {
+    for (; k + UK <= ke; k += UK) {
+      T b[UK][V];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) ldvec<T>(gp + (int64_t)(kk + u) * ldg, b[u]);
+      for (int u = 0; u < UK; ++u) ldvec<T>(gp + (k + u) * ldg, b[u]);
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+      for (int u = 0; u < UK; ++u) {
+        T s[MRP];
 #pragma unroll
-          for (int r = 0; r < MR; ++r) {
-            const T s = Ss[kk + u][r];
+        for (int q = 0; q < MRP / V; ++q) ldvec<T>(Sp + (k + u) * MRP + q * V, *reinterpret_cast<T(*)[V]>(&s[q * V]));
 #pragma unroll
-            for (int v = 0; v < V; ++v) acc[r][v] = fma(s, b[u][v], acc[r][v]);
-          }
-      }
-      for (; kk < kn; ++kk) {
-        T b[V];
-        ldvec<T>(gp + (int64_t)kk * ldg, b);
+        for (int r = 0; r < MR; ++r)
 #pragma unroll
-        for (int r = 0; r < MR; ++r) {
-          const T s = Ss[kk][r];
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[r][v] = fma(s, b[v], acc[r][v]);
-        }
-      }
-    } else {
-      for (int kk = 0; kk < kn; ++kk) {
-        T b[V];
-#pragma unroll
-        for (int v = 0; v < V; ++v) b[v] = c0 + v < ncols ? gp[(int64_t)kk * ldg + v] : T(0);
-#pragma unroll
-        for (int r = 0; r < MR; ++r) {
-          const T s = Ss[kk][r];
-#pragma unroll
-          for (int v = 0; v < V; ++v) acc[r][v] = fma(s, b[v], acc[r][v]);
-        }
+          for (int v = 0; v < V; ++v) acc[r][v] = fma(s[r], b[u][v], acc[r][v]);
       }
     }
   }
-  if (c0 >= ncols) return;
+  for (; k < ke; ++k) {
+    T b[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) b[v] = c0 + v < ncols ? gp[k * ldg + v] : T(0);
+#pragma unroll
+    for (int r = 0; r < MR; ++r) {
+      const T s = Sp[k * MRP + r];
+#pragma unroll
+      for (int v = 0; v < V; ++v) acc[r][v] = fma(s, b[v], acc[r][v]);
+    }
+  }
 #pragma unroll
   for (int r = 0; r < MR; ++r) {
     if (r >= R) break;
@@ -139,20 +135,19 @@ __global__ void __launch_bounds__(256) k_skinny_cc(const T* __restrict__ G, int6
 // ------------------------------------------------------------------------------------------------------------
 // out[r, c] = sum_k S[r, k] * G[k + c * ldg]      the big operand G has the REDUCTION index k contiguous
 // (small M: C = A * B with B stored k x n;  small N: C' = B' * A with A stored k x m).  A warp owns NC columns of G
-// and walks K with 16-byte loads per lane; S is staged through shared memory in chunks; warp-shuffle reduction at
-// the end; partial sums (split-K over gridDim.z) go to ws[z][r][c].
+// and walks K with 16-byte loads per lane (two batches = 2 * NC loads in flight per lane); S comes from the packed
+// k-contiguous copy through L1; warp-shuffle reduction at the end; split-K partials go to ws[z][r][c].
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int MR>
 __global__ void __launch_bounds__(256) k_skinny_kc(const T* __restrict__ G, int64_t ldg, int64_t ncols, int64_t K,
-                                                   const T* __restrict__ S, int64_t sr, int64_t sk, int R,
-                                                   T* __restrict__ ws, int64_t kper, int vec_ok) {
+                                                   const T* __restrict__ St, int64_t Kp, int R, T* __restrict__ ws,
+                                                   int64_t kper, int vec_ok) {
   constexpr int V = Vec<T>::N;
   constexpr int NC = 4;
-  constexpr int IT = 4;                 // warp iterations per staged chunk
-  constexpr int KC = 32 * V * IT;       // 512 (f32) / 256 (f64) reduction indices per chunk
-  __shared__ __align__(16) T Ss[MR][KC];
+  constexpr int STEP = 32 * V;   // reduction indices per warp iteration
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t cb = ((int64_t)blockIdx.x * 8 + warp) * NC;
+  if (cb >= ncols) return;
   const int64_t kb = (int64_t)blockIdx.z * kper;
   const int64_t ke = kb + kper < K ? kb + kper : K;
   T acc[MR][NC];
@@ -160,49 +155,49 @@ __global__ void __launch_bounds__(256) k_skinny_kc(const T* __restrict__ G, int6
   for (int r = 0; r < MR; ++r)
 #pragma unroll
     for (int c = 0; c < NC; ++c) acc[r][c] = T(0);
-
-  for (int64_t k0 = kb; k0 < ke; k0 += KC) {
-    __syncthreads();
-    if (sk == 1) {
-      for (int e = tid; e < MR * KC; e += 256) {
-        const int r = e / KC, kk = e % KC;
-        Ss[r][kk] = (r < R && k0 + kk < ke) ? S[(int64_t)r * sr + (k0 + kk)] : T(0);
-      }
-    } else {
-      for (int e = tid; e < MR * KC; e += 256) {
-        const int kk = e / MR, r = e % MR;
-        Ss[r][kk] = (r < R && k0 + kk < ke) ? S[(int64_t)r * sr + (k0 + kk) * sk] : T(0);
-      }
-    }
-    __syncthreads();
-    if (cb >= ncols) continue;
+  const bool colfull = cb + NC <= ncols;
+  int64_t k0 = kb;
+  if (vec_ok && colfull) {
+    for (; k0 + 2 * STEP <= ke; k0 += 2 * STEP) {
+      const int64_t kg = k0 + lane * V;
+      T b0[NC][V], b1[NC][V];
 #pragma unroll
-    for (int it = 0; it < IT; ++it) {
-      const int kk = (it * 32 + lane) * V;
-      const int64_t kg = k0 + kk;
-      if (k0 + (int64_t)it * 32 * V >= ke) break;   // warp-uniform
-      T b[NC][V];
-      if (vec_ok && kg + V <= ke && cb + NC <= ncols) {
+      for (int c = 0; c < NC; ++c) ldvec<T>(G + (cb + c) * ldg + kg, b0[c]);
 #pragma unroll
-        for (int c = 0; c < NC; ++c) ldvec<T>(G + (cb + c) * ldg + kg, b[c]);
-      } else {
-#pragma unroll
-        for (int c = 0; c < NC; ++c)
-#pragma unroll
-          for (int v = 0; v < V; ++v) b[c][v] = (cb + c < ncols && kg + v < ke) ? G[(cb + c) * ldg + kg + v] : T(0);
-      }
+      for (int c = 0; c < NC; ++c) ldvec<T>(G + (cb + c) * ldg + kg + STEP, b1[c]);
 #pragma unroll
       for (int r = 0; r < MR; ++r) {
-        T s[V];
-        ldvec<T>(&Ss[r][kk], s);
+        T s0[V], s1[V];
+        ldvec<T>(St + (int64_t)r * Kp + kg, s0);
+        ldvec<T>(St + (int64_t)r * Kp + kg + STEP, s1);
 #pragma unroll
         for (int c = 0; c < NC; ++c)
 #pragma unroll
-          for (int v = 0; v < V; ++v) acc[r][c] = fma(s[v], b[c][v], acc[r][c]);
+          for (int v = 0; v < V; ++v) acc[r][c] = fma(s0[v], b0[c][v], acc[r][c]);
+#pragma unroll
+        for (int c = 0; c < NC; ++c)
+#pragma unroll
+          for (int v = 0; v < V; ++v) acc[r][c] = fma(s1[v], b1[c][v], acc[r][c]);
       }
     }
   }
-  if (cb >= ncols) return;
+  for (; k0 < ke; k0 += STEP) {   // tails, ragged columns, unaligned operands
+    const int64_t kg = k0 + lane * V;
+    T b[NC][V];
+#pragma unroll
+    for (int c = 0; c < NC; ++c)
+#pragma unroll
+      for (int v = 0; v < V; ++v) b[c][v] = (cb + c < ncols && kg + v < ke) ? G[(cb + c) * ldg + kg + v] : T(0);
+#pragma unroll
+    for (int r = 0; r < MR; ++r) {
+      T s[V];
+      ldvec<T>(St + (int64_t)r * Kp + kg, s);   // (Kp is padded with zeros to a multiple of STEP)
+#pragma unroll
+      for (int c = 0; c < NC; ++c)
+#pragma unroll
+        for (int v = 0; v < V; ++v) acc[r][c] = fma(s[v], b[c][v], acc[r][c]);
+    }
+  }
   // butterfly: every lane ends with the warp's total; lane (r * NC + c) % 32 stores element (r, c)
 #pragma unroll
   for (int r = 0; r < MR; ++r) {
@@ -293,8 +288,33 @@ __global__ void __launch_bounds__(256) k_gemm_smallk(const SmallK<T> g) {
     T bias[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) bias[v] = (g.ekind == 1 && g.bias && i0 + v < g.m) ? g.bias[i0 + v] : T(0);
+    // the one full-size array the epilogue READS (the saved y of a pullback, or C when beta != 0) is prefetched one
+    // column group ahead, so its loads are in flight while the current group is computed and stored
+    const T* auxp = g.ekind == 2 ? g.y : (g.beta != T(0) ? g.C : nullptr);
+    const int64_t auxld = g.ekind == 2 ? g.ldy : g.ldc;
+    const bool need_aux = fast && auxp != nullptr;
+    T auxn[U][V];
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+#pragma unroll
+      for (int v = 0; v < V; ++v) auxn[u][v] = T(0);
+    if (need_aux) {
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (u < ncb) ldvec<T>(auxp + i0 + (j0 + u) * auxld, auxn[u]);
+    }
     for (int jj = 0; jj < ncb; jj += U) {
       T x[U][V];
+      T aux[U][V];
+      if (need_aux) {
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+#pragma unroll
+          for (int v = 0; v < V; ++v) aux[u][v] = auxn[u][v];
+#pragma unroll
+        for (int u = 0; u < U; ++u)
+          if (jj + U + u < ncb) ldvec<T>(auxp + i0 + (j0 + jj + U + u) * auxld, auxn[u]);
+      }
 #pragma unroll
       for (int u = 0; u < U; ++u) {
 #pragma unroll
@@ -311,33 +331,27 @@ __global__ void __launch_bounds__(256) k_gemm_smallk(const SmallK<T> g) {
         for (int v = 0; v < V; ++v) x[u][v] *= g.alpha;
       }
       if (fast) {
-        // all loads of the U columns first (independent, in flight together), then arithmetic, then stores
-        T aux[U][V];
-        if (g.beta != T(0)) {
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (jj + u < ncb) ldvec<T>(g.C + i0 + (j0 + jj + u) * g.ldc, aux[u]);
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (jj + u < ncb)
-#pragma unroll
-              for (int v = 0; v < V; ++v) x[u][v] = fma(g.beta, aux[u][v], x[u][v]);
-        }
         if (g.ekind == 2) {
-#pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (jj + u < ncb) ldvec<T>(g.y + i0 + (j0 + jj + u) * g.ldy, aux[u]);
 #pragma unroll
           for (int u = 0; u < U; ++u)
             if (jj + u < ncb)
 #pragma unroll
               for (int v = 0; v < V; ++v) x[u][v] *= nb_dunary<T>(g.eop, T(0), aux[u][v]);
-        } else if (g.ekind == 1) {
+        } else {
+          if (g.beta != T(0)) {
 #pragma unroll
-          for (int u = 0; u < U; ++u)
-            if (jj + u < ncb)
+            for (int u = 0; u < U; ++u)
+              if (jj + u < ncb)
 #pragma unroll
-              for (int v = 0; v < V; ++v) x[u][v] = nb_eval<T>(g.eop, x[u][v] + bias[v], T(0));
+                for (int v = 0; v < V; ++v) x[u][v] = fma(g.beta, aux[u][v], x[u][v]);
+          }
+          if (g.ekind == 1) {
+#pragma unroll
+            for (int u = 0; u < U; ++u)
+              if (jj + u < ncb)
+#pragma unroll
+                for (int v = 0; v < V; ++v) x[u][v] = nb_eval<T>(g.eop, x[u][v] + bias[v], T(0));
+          }
         }
 #pragma unroll
         for (int u = 0; u < U; ++u) {
@@ -438,7 +452,7 @@ int32_t dispatch_mr(int R, Args... args) {
 struct StreamArgs {
   nb_ctx* ctx;
   const void* G; int64_t ldg, ncols, K;
-  const void* S; int64_t sr, sk;
+  const void* Sp; int64_t Kp;
   int R;
   void* ws; int64_t kper; int nsplit; int vec_ok;
 };
@@ -448,8 +462,8 @@ struct LaunchCC {
   static int32_t run(const StreamArgs& a) {
     constexpr int V = Vec<T>::N;
     dim3 grid((unsigned)((a.ncols + 256 * V - 1) / (256 * V)), 1, (unsigned)a.nsplit);
-    k_skinny_cc<T, MR><<<grid, 256, 0, a.ctx->stream>>>((const T*)a.G, a.ldg, a.ncols, a.K, (const T*)a.S, a.sr, a.sk,
-                                                        a.R, (T*)a.ws, a.kper, a.vec_ok);
+    k_skinny_cc<T, MR><<<grid, 256, 0, a.ctx->stream>>>((const T*)a.G, a.ldg, a.ncols, a.K, (const T*)a.Sp, a.R,
+                                                        (T*)a.ws, a.kper, a.vec_ok);
     NB_LAUNCH_CHECK(a.ctx);
     return NB_OK;
   }
@@ -458,12 +472,17 @@ template <typename T, int MR>
 struct LaunchKC {
   static int32_t run(const StreamArgs& a) {
     dim3 grid((unsigned)((a.ncols + 31) / 32), 1, (unsigned)a.nsplit);
-    k_skinny_kc<T, MR><<<grid, 256, 0, a.ctx->stream>>>((const T*)a.G, a.ldg, a.ncols, a.K, (const T*)a.S, a.sr, a.sk,
-                                                        a.R, (T*)a.ws, a.kper, a.vec_ok);
+    k_skinny_kc<T, MR><<<grid, 256, 0, a.ctx->stream>>>((const T*)a.G, a.ldg, a.ncols, a.K, (const T*)a.Sp, a.Kp, a.R,
+                                                        (T*)a.ws, a.kper, a.vec_ok);
     NB_LAUNCH_CHECK(a.ctx);
     return NB_OK;
   }
 };
+
+inline int padded_mr(int R) {   // the MR the dispatcher instantiates for R rows, rounded up to a multiple of 4
+  const int mr = R <= 4 ? R : R <= 6 ? 6 : R <= 8 ? 8 : R <= 10 ? 10 : R <= 12 ? 12 : 16;
+  return (mr + 3) / 4 * 4;
+}
 
 // out[r, c] = sum_k S[r, k] * G(k, c): G is the streamed operand; g_c_contig says which of its indices is contiguous
 template <typename T>
@@ -471,9 +490,9 @@ int32_t run_stream(nb_ctx* ctx, bool g_c_contig, const T* G, int64_t ldg, int64_
                    int64_t sr, int64_t sk, int R, double alpha, double beta, T* C, int64_t ldc, bool swapped,
                    const nb_gemm_epilogue* epi) {
   constexpr int V = Vec<T>::N;
-  // CTAs along the output index; split K until ~4 CTAs per SM are resident (each keeps 4+ loads per thread in flight)
+  // CTAs along the output index; split K until ~4 CTAs per SM are resident (each keeps 8 loads per thread in flight)
   const int64_t gx = g_c_contig ? (ncols + 256 * V - 1) / (256 * V) : (ncols + 31) / 32;
-  const int64_t kquant = g_c_contig ? 64 : 32 * V * 4;
+  const int64_t kquant = g_c_contig ? 64 : 32 * V * 2;
   int64_t nsplit = (4ll * ctx->num_sms + gx - 1) / gx;
   const int64_t maxsplit = (K + kquant - 1) / kquant;
   if (nsplit > maxsplit) nsplit = maxsplit;
@@ -481,10 +500,20 @@ int32_t run_stream(nb_ctx* ctx, bool g_c_contig, const T* G, int64_t ldg, int64_
   if (nsplit < 1) nsplit = 1;
   int64_t kper = ((K + nsplit - 1) / nsplit + kquant - 1) / kquant * kquant;
   nsplit = (K + kper - 1) / kper;
-  void* ws = nullptr;
+  const int RP = padded_mr(R);
+  const int64_t Kp = (K + 32 * V - 1) / (32 * V) * (32 * V);
+  void *ws = nullptr, *sp = nullptr;
   int32_t rc = nb_pool_alloc(ctx, (size_t)(nsplit * R * ncols) * sizeof(T), &ws);
   if (rc != NB_OK) return rc;
-  StreamArgs a{ctx, G, ldg, ncols, K, S, sr, sk, R, ws, kper, (int)nsplit, 0};
+  rc = nb_pool_alloc(ctx, (size_t)RP * (size_t)Kp * sizeof(T), &sp);
+  if (rc != NB_OK) { nb_pool_release(ctx, ws); return rc; }
+  {
+    const int64_t tot = (int64_t)RP * Kp;
+    k_pack_s<T><<<(unsigned)((tot + 255) / 256), 256, 0, ctx->stream>>>(S, sr, sk, R, K, (T*)sp,
+                                                                      g_c_contig ? 1 : Kp, g_c_contig ? RP : 1, RP, Kp);
+    ctx->stats.kernel_launches++;
+  }
+  StreamArgs a{ctx, G, ldg, ncols, K, sp, Kp, R, ws, kper, (int)nsplit, 0};
   a.vec_ok = al16(G) && (ldg % V == 0);
   rc = g_c_contig ? dispatch_mr<T, LaunchCC>(R, a) : dispatch_mr<T, LaunchKC>(R, a);
   if (rc == NB_OK) {
@@ -495,6 +524,7 @@ int32_t run_stream(nb_ctx* ctx, bool g_c_contig, const T* G, int64_t ldg, int64_
     ctx->stats.kernel_launches++;
     if (cudaGetLastError() != cudaSuccess) rc = nb_fail(ctx, NB_ERR_CUDA, "k_skinny_finish launch failed");
   }
+  nb_pool_release(ctx, sp);
   nb_pool_release(ctx, ws);
   return rc;
 }

@@ -134,6 +134,8 @@ struct GemmArgs {
   int32_t group_m;        // tile-rows per rasterisation group (see tile_coords)
   int64_t k_begin, k_end; // K range of this launch (multiples of the K step except at the very end)
   int32_t kchunk_kb;      // K blocks accumulated in TMEM before the epilogue folds them into C
+  int32_t kchunk_first_kb;  // length of the FIRST TWO chunks of every tile (>= kchunk_kb): they are issued while the
+                            // epilogue still stores the previous tile, so they are the MMA's runway (see chunk_len)
   uint64_t hint_a, hint_b;  // L2 eviction policies of the operand loads (0 = none)
   int32_t vec_store;        // epilogue may use 16-byte accesses along the rows (alignment checked on the host)
   int32_t serpentine;       // odd waves walk K backwards: the panel slices used last are still in the L2
@@ -152,6 +154,12 @@ struct GemmArgs {
 };
 
 constexpr int SCHED_SLOTS = 4;
+
+// Chunk schedule of one tile, identical in the MMA issuer and the epilogue: chunks 0 and 1 have kchunk_first_kb K
+// blocks, the rest kchunk_kb.
+__device__ __forceinline__ int chunk_len(const GemmArgs& g, int chunk_index) {
+  return chunk_index < 2 ? g.kchunk_first_kb : g.kchunk_kb;
+}
 
 // Tile rasterisation: groups of `group_m` tile-rows are swept along n with m fastest inside the group, so the
 // ~74 tiles in flight form a group_m x ~9 block that shares group_m A panels and ~9 B panels; long K is launched
@@ -781,8 +789,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           }
           continue;
         }
-        for (int kb0 = 0; kb0 < nkb; kb0 += g.kchunk_kb) {
-          const int kb1 = min(nkb, kb0 + g.kchunk_kb);
+        for (int kb0 = 0, ci = 0; kb0 < nkb; kb0 += chunk_len(g, ci), ++ci) {
+          const int kb1 = min(nkb, kb0 + chunk_len(g, ci));
           mbar_wait(&tempty[a], aph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
@@ -842,7 +850,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         a64.store(g, (int64_t)tm * BM + q * 32 + lane, (int64_t)tn * BN + half * (BN / 2));
         continue;
       }
-      for (int kb0 = 0; kb0 < nkb; kb0 += g.kchunk_kb) {
+      for (int kb0 = 0, ci = 0; kb0 < nkb; kb0 += chunk_len(g, ci), ++ci) {
         mbar_wait(&tfull[a], aph);
         tc_fence_after();
         acc.fold(tmem_base + (uint32_t)(a * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16), kb0 == 0);
@@ -1116,8 +1124,8 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         mbar_arrive(&sempty[q]);
         if (++q == SCHED_SLOTS) { q = 0; qph ^= 1; }
         if (t >= ntiles) break;
-        for (int kb0 = 0; kb0 < nkb; kb0 += g.kchunk_kb) {
-          const int kb1 = min(nkb, kb0 + g.kchunk_kb);
+        for (int kb0 = 0, ci = 0; kb0 < nkb; kb0 += chunk_len(g, ci), ++ci) {
+          const int kb1 = min(nkb, kb0 + chunk_len(g, ci));
           mbar_wait(&tempty[a], aph ^ 1);
           tc_fence_after();
           const uint32_t d_tmem = tmem_base + (uint32_t)(a * BN);
@@ -1167,7 +1175,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
       if (t >= ntiles) break;
       int tm, tn;
       tile_coords(t, g.tiles_m, g.tiles_n, g.group_m, tm, tn);
-      for (int kb0 = 0; kb0 < nkb; kb0 += g.kchunk_kb) {
+      for (int kb0 = 0, ci = 0; kb0 < nkb; kb0 += chunk_len(g, ci), ++ci) {
         mbar_wait(&tfull[a], aph);
         tc_fence_after();
         acc.fold(tmem_base + (uint32_t)(a * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16), kb0 == 0);
@@ -1263,6 +1271,82 @@ __global__ void __launch_bounds__(256) k_split_h(const float* __restrict__ x, in
 #pragma unroll
         for (int e = 0; e < 4; ++e)
           if (r + e < rows) { hc[r + e] = h[e]; lc[r + e] = l[e]; }
+      }
+    }
+  }
+}
+
+// C = f.(C .+ bias) in place, plus the 16-bit operand splits of the result — the forward epilogue of nb_gemm_fused run
+// as its own streaming pass (read 4 B, write 4 + 4 [+ 4] B per element) when the product itself must fold its TMEM
+// accumulator every 128 K: the fused epilogue (tanh + two splits, ~45 us per 128 x 256 tile) would sit between the
+// folds and stall the tensor pipe; a plain store does not.  s_hi/s_lo: first split (binary16 scaled by s_scale when
+// s_fp16, else bfloat16); s2_hi/s2_lo: optional second, bfloat16 split.
+__global__ void __launch_bounds__(256) k_bias_act_split(float* __restrict__ C, int64_t ldc, int64_t rows, int64_t cols,
+                                                        const float* __restrict__ bias, int op, uint16_t* __restrict__ s_hi,
+                                                        uint16_t* __restrict__ s_lo, int64_t ld_s, int s_fp16, float s_scale,
+                                                        uint16_t* __restrict__ s2_hi, uint16_t* __restrict__ s2_lo, int vec) {
+  const int64_t r4 = (rows + 3) >> 2;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < r4; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i << 2;
+    const bool full = vec && r + 3 < rows;
+    float b[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) b[e] = (bias && r + e < rows) ? __ldg(bias + r + e) : 0.f;
+    constexpr int UC = 4;   // columns in flight per thread
+    for (int64_t c0 = (int64_t)blockIdx.y * UC; c0 < cols; c0 += (int64_t)gridDim.y * UC) {
+      float v[UC][4];
+#pragma unroll
+      for (int u = 0; u < UC; ++u) {
+        const int64_t c = c0 + u;
+        if (c < cols && full) {
+          const float4 q = __ldcs(reinterpret_cast<const float4*>(C + r + c * ldc));
+          v[u][0] = q.x; v[u][1] = q.y; v[u][2] = q.z; v[u][3] = q.w;
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e) v[u][e] = (c < cols && r + e < rows) ? C[r + e + c * ldc] : 0.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UC; ++u) {
+        const int64_t c = c0 + u;
+        if (c >= cols) continue;
+        __align__(8) uint16_t h[4], l[4], h2[4], l2[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float x = epi_act(op, v[u][e] + b[e]);
+          v[u][e] = x;
+          if (s_fp16) {
+            __half hh, ll;
+            split1s(x, s_scale, hh, ll);
+            h[e] = __half_as_ushort(hh); l[e] = __half_as_ushort(ll);
+          } else {
+            __nv_bfloat16 hh, ll;
+            split1(x, hh, ll);
+            h[e] = __bfloat16_as_ushort(hh); l[e] = __bfloat16_as_ushort(ll);
+          }
+          __nv_bfloat16 h3, l3;
+          split1(x, h3, l3);
+          h2[e] = __bfloat16_as_ushort(h3); l2[e] = __bfloat16_as_ushort(l3);
+        }
+        if (full) {
+          *reinterpret_cast<float4*>(C + r + c * ldc) = make_float4(v[u][0], v[u][1], v[u][2], v[u][3]);
+          if (s_hi) {
+            *reinterpret_cast<uint2*>(s_hi + r + c * ld_s) = *reinterpret_cast<const uint2*>(h);
+            *reinterpret_cast<uint2*>(s_lo + r + c * ld_s) = *reinterpret_cast<const uint2*>(l);
+          }
+          if (s2_hi) {
+            *reinterpret_cast<uint2*>(s2_hi + r + c * ld_s) = *reinterpret_cast<const uint2*>(h2);
+            *reinterpret_cast<uint2*>(s2_lo + r + c * ld_s) = *reinterpret_cast<const uint2*>(l2);
+          }
+        } else {
+#pragma unroll
+          for (int e = 0; e < 4; ++e)
+            if (r + e < rows) {
+              C[r + e + c * ldc] = v[u][e];
+              if (s_hi) { s_hi[r + e + c * ld_s] = h[e]; s_lo[r + e + c * ld_s] = l[e]; }
+              if (s2_hi) { s2_hi[r + e + c * ld_s] = h2[e]; s2_lo[r + e + c * ld_s] = l2[e]; }
+            }
+        }
       }
     }
   }
@@ -1693,12 +1777,16 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     g.tiles_n = (int32_t)((n + BN - 1) / BN);
     g.tile_counter = st->tile_counter;
     memset(&g.epi, 0, sizeof(g.epi));
+    // Forward epilogue as its own streaming pass (k_bias_act_split) when this product folds every 128 K
+    static const bool unfuse_on = !(getenv("NB_GEMM_UNFUSE_FWD") && atoi(getenv("NB_GEMM_UNFUSE_FWD")) == 0);
+    const bool unfuse = fused && unfuse_on && epi->kind == 1 && !epi->rowsum && math_mode != NB_MATH_BF16X3 &&
+                        kind == KIND_BF16X3 && k > 256;
     void* rs_partial = nullptr;
     void *e_hi = nullptr, *e_lo = nullptr, *e2_hi = nullptr, *e2_lo = nullptr;
     float* e_sc = nullptr;
     int64_t e_ld = 0;
     if (fused) {
-      g.epi.kind = epi->kind;
+      g.epi.kind = unfuse ? EPI_NONE : epi->kind;
       g.epi.op = epi->op;
       g.epi.bias = (const float*)epi->bias;
       g.epi.y = (const float*)epi->y;
@@ -1775,6 +1863,14 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     if (math_mode != NB_MATH_BF16X3)
       if (const char* e = getenv("NB_GEMM_KCHUNK_ACC")) kchunk = atoll(e) >= 64 ? atoll(e) / 64 * 64 : kchunk;
     g.kchunk_kb = (int32_t)(kchunk / (128 / esize));
+    // The first two chunks of a tile are issued while the epilogue warps still STORE the previous tile (they cannot
+    // fold meanwhile): with 128-chunks the MMA's runway would be 2 x 128 of K (~4 us) against a ~10 us plain store,
+    // and every tile would stall.  Chunks of 384 there (13 us of runway) cost little accuracy: the error variance of a
+    // tile is ~ sum c_i^3, so 2 x 384^3 + 58 x 128^3 at K = 8192 gives 5.8e-7 per product instead of 4.1e-7.
+    int64_t kfirst = math_mode == NB_MATH_BF16X3 ? kchunk : 3 * kchunk;
+    if (const char* e = getenv("NB_GEMM_KCHUNK_FIRST")) kfirst = atoll(e) >= 64 ? atoll(e) / 64 * 64 : kfirst;
+    if (kfirst < kchunk) kfirst = kchunk;
+    g.kchunk_first_kb = (int32_t)(kfirst / (128 / esize));
     g.hint_a = g.hint_b = 0;
     if (const char* e = getenv("NB_GEMM_HINT")) {  // 1: A evict_last  2: B evict_last  +4: the other evict_first
       const int h = atoi(e);
@@ -1798,6 +1894,22 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
       else if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
       else if (kind == KIND_3XTF32) rc = BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
       else rc = BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);
+    }
+    if (unfuse && rc == NB_OK) {
+      const int vec = (((uintptr_t)C & 15) == 0) && (ldc % 4 == 0) && (!g.epi.s_hi || g.epi.ld_s % 4 == 0) &&
+                      (!epi->bias || ((uintptr_t)epi->bias & 15) == 0);
+      int64_t gx = ((m + 3) / 4 + 255) / 256;
+      if (gx > 64) gx = 64;
+      int64_t gy = (n + 3) / 4;
+      const int64_t want = (int64_t)ctx->num_sms * 8;
+      if (gx * gy > want) gy = (want + gx - 1) / gx;
+      if (gy < 1) gy = 1;
+      if (gy > 65535) gy = 65535;
+      k_bias_act_split<<<dim3((unsigned)gx, (unsigned)gy), 256, 0, ctx->stream>>>(
+          C, ldc, m, n, (const float*)epi->bias, epi->op, (uint16_t*)g.epi.s_hi, (uint16_t*)g.epi.s_lo, g.epi.ld_s,
+          (kind == KIND_BF16X3) ? g.epi.s_fp16 : 0, g.epi.s_scale, (uint16_t*)g.epi.s2_hi, (uint16_t*)g.epi.s2_lo, vec);
+      ctx->stats.kernel_launches++;
+      if (cudaGetLastError() != cudaSuccess) rc = nb_fail(ctx, NB_ERR_CUDA, "k_bias_act_split launch failed");
     }
     if (rs_partial) {
       if (rc == NB_OK) {
@@ -1856,6 +1968,7 @@ int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* 
   g.tile_counter = st->tile_counter;
   g.k_begin = 0; g.k_end = kp;
   g.kchunk_kb = (int32_t)(kp / 128);  // one exact accumulation, no folds
+  g.kchunk_first_kb = g.kchunk_kb;
   g.serpentine = 1;
   const int64_t panel = (int64_t)BM * kp;
   int64_t gm = (70ll << 20) / (panel > 0 ? panel : 1);
@@ -1892,6 +2005,7 @@ int32_t nb_gemm_i8all(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, int32_t S, 
   g.tile_counter = st->tile_counter;
   g.k_begin = 0; g.k_end = kp;
   g.kchunk_kb = 1;
+  g.kchunk_first_kb = 1;
   g.group_m = 8;
   g.C64 = C; g.row_scale = row_scale; g.col_scale = col_scale; g.scale64 = alpha; g.beta64 = beta;
   const int32_t nkb0 = (int32_t)(kp / 128);
