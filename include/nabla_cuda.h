@@ -96,7 +96,12 @@ typedef enum nb_op {
   NB_OP_COSPI = 52, NB_OP_DEG2RAD = 53, NB_OP_RAD2DEG = 54,
   NB_OP_LOGISTIC = 55,  /* 1/(1+exp(-x)): examples/mlp.jl:42, examples/vae.jl:32, fused */
   NB_OP_ERF = 56, NB_OP_ERFC = 57,
-  NB_OP_UNARY_END = 58,
+  /* piecewise-constant functions (derivative zero, as ForwardDiff gives): the building blocks of value-dependent
+   * scalar functions such as `x > 0 ? x : 0.1x`, which fmad differentiates along the taken branch (core.jl:285-292) */
+  NB_OP_SIGN = 58,
+  NB_OP_STEP = 59,      /* x > 0 ? 1 : 0 */
+  NB_OP_FLOOR = 60, NB_OP_CEIL = 61, NB_OP_ROUND = 62, NB_OP_TRUNC = 63,
+  NB_OP_UNARY_END = 64,
   /* binary */
   NB_OP_ADD = 64, NB_OP_SUB = 65, NB_OP_MUL = 66, NB_OP_DIV = 67,
   NB_OP_LDIV = 68,      /* x \ y == y / x */
@@ -106,7 +111,13 @@ typedef enum nb_op {
   /* differentiable in the SECOND operand only (test/runtests.jl:43-47): operand a is the integer order, its partial is
    * NaN as in DiffRules; a non-integer order gives NaN (csrc/special.cuh) */
   NB_OP_BESSELJ = 75, NB_OP_BESSELY = 76, NB_OP_BESSELI = 77, NB_OP_BESSELK = 78, NB_OP_POLYGAMMA = 79,
-  NB_OP_BINARY_END = 80,
+  /* comparisons: 1.0 / 0.0, both partials zero */
+  NB_OP_GT = 80, NB_OP_LT = 81, NB_OP_GE = 82, NB_OP_LE = 83,
+  /* selection: MASK(c, v) = c != 0 ? v : 0, MASKN(c, v) = c == 0 ? v : 0; d/dv = the indicator, d/dc = 0.
+   * ifelse(c, a, b) = MASK(c, a) + MASKN(c, b): the branch not taken contributes exactly 0 to value and derivative
+   * (no 0 * Inf), i.e. the derivative of the taken branch, which is what ForwardDiff's duals give */
+  NB_OP_MASK = 84, NB_OP_MASKN = 85,
+  NB_OP_BINARY_END = 86,
   /* SpecialFunctions.jl unary functions of test/runtests.jl:34-36 (second unary range) */
   NB_OP_SF_BEGIN = 96,
   NB_OP_GAMMA = 96, NB_OP_DIGAMMA = 97, NB_OP_TRIGAMMA = 98, NB_OP_BESSELJ0 = 99, NB_OP_BESSELJ1 = 100,

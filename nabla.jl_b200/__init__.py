@@ -13,7 +13,7 @@ from ._lib import (DimensionMismatch, NablaCudaError, UnsupportedOp, MATH_DEFAUL
 from .device import BroadcastView, Context, DevArray, PinnedArray, get_context, set_context
 from .core import (Arg, Branch, Leaf, Node, Primitive, Tape, explicit_intercepts, grad, nabla,
                    oneslike, pos, propagate, reverse_tape, tape, unbox, unthunk, zeroslike, as_device)
-from .scalar import CATALOGUE, Program, ScalarFn, Sym, compile_scalar
+from .scalar import CATALOGUE, Program, ScalarFn, Sym, compile_scalar, ifelse
 from .rules import (Ref, adjoint, broadcast, dot, gemm, gemv, ldivide, map_, mapfoldl, mapfoldr,
                     mapreduce, matmul, mean, sum, transpose)
 

@@ -251,7 +251,7 @@ struct GenEvS {
         const bool same = (fl & NB_RF_SLOT_B) && ib == ia;  // f(x, x): both partials go to one adjoint
         T t[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) t[v] = g[v] * (same ? da[v] + db[v] : da[v]);
+        for (int v = 0; v < V; ++v) t[v] = nb_gmul(g[v], same ? da[v] + db[v] : da[v], G.guard != 0);
         if (!(fl & NB_RF_FIRST_A)) {
           T old[V];
           ld(nslots + ia, old);
@@ -263,7 +263,7 @@ struct GenEvS {
       if ((fl & NB_RF_SLOT_B) && ib != ia) {
         T t[V];
 #pragma unroll
-        for (int v = 0; v < V; ++v) t[v] = g[v] * db[v];
+        for (int v = 0; v < V; ++v) t[v] = nb_gmul(g[v], db[v], G.guard != 0);
         if (!(fl & NB_RF_FIRST_B)) {
           T old[V];
           ld(nslots + ib, old);

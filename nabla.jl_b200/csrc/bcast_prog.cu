@@ -143,7 +143,7 @@ struct ProgPack {
           if (fl & NB_RF_SLOT_A) {
             T t[V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) t[v] = g[v] * (same ? da[v] + db[v] : da[v]);
+            for (int v = 0; v < V; ++v) t[v] = nb_gmul(g[v], same ? da[v] + db[v] : da[v], G.guard != 0);
             if (!(fl & NB_RF_FIRST_A)) {
               T old[V];
               ld(nslots + ia, u, old);
@@ -155,7 +155,7 @@ struct ProgPack {
           if ((fl & NB_RF_SLOT_B) && !same) {
             T t[V];
 #pragma unroll
-            for (int v = 0; v < V; ++v) t[v] = g[v] * db[v];
+            for (int v = 0; v < V; ++v) t[v] = nb_gmul(g[v], db[v], G.guard != 0);
             if (!(fl & NB_RF_FIRST_B)) {
               T old[V];
               ld(nslots + ib, u, old);

@@ -211,11 +211,11 @@ int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_
   constexpr int DMMA_SMEM = 4 * (int)sizeof(double) * BK * LD;  // two stages of As and Bs
 #define NB_DMMA(TA_, TB_)                                                                                       \
   do {                                                                                                          \
-    static bool attr_done = false;                                                                              \
-    if (!attr_done) {                                                                                           \
+    static bool attr_done[64] = {};  /* per device: cudaFuncSetAttribute applies to the current device only */                                                                              \
+    if (!attr_done[ctx->device & 63]) {                                                                                           \
       NB_CUDA_OK(ctx, cudaFuncSetAttribute(k_gemm_dmma<TA_, TB_>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
                                            DMMA_SMEM));                                                         \
-      attr_done = true;                                                                                         \
+      attr_done[ctx->device & 63] = true;                                                                                         \
     }                                                                                                           \
     k_gemm_dmma<TA_, TB_><<<grid, 256, DMMA_SMEM, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, vecA,     \
                                                         vecB, (int)tiles_m, kps, ws);                           \

@@ -46,6 +46,17 @@ __device__ __forceinline__ void stvec(T* p, const T (&v)[Vec<T>::N]) {
   *reinterpret_cast<VT*>(p) = q;
 }
 
+// the streamed operand is read exactly once: keep it out of L1 so the small operand (re-read by every warp) stays there
+template <typename T>
+__device__ __forceinline__ void ldstream(const T* p, T (&v)[Vec<T>::N]) {
+  if constexpr (sizeof(T) == 4) {
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]) : "l"(p));
+  } else {
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1]) : "l"(p));
+  }
+}
+
 constexpr int round_up(int a, int b) { return (a + b - 1) / b * b; }
 
 // The small operand S (R <= 16 rows) is re-laid out once per call into the form each streaming kernel reads with
@@ -71,16 +82,19 @@ __global__ void __launch_bounds__(256) k_pack_s(const T* __restrict__ S, int64_t
 // No barriers: eight 16-byte loads of G in flight per thread, S read through L1 as warp-uniform 16-byte loads.
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int MR>
-__global__ void __launch_bounds__(256) k_skinny_cc(const T* __restrict__ G, int64_t ldg, int64_t ncols, int64_t K,
-                                                   const T* __restrict__ Sp, int R, T* __restrict__ ws, int64_t kper,
-                                                   int vec_ok) {
+__global__ void __launch_bounds__(256, 3) k_skinny_cc(const T* __restrict__ G, int64_t ldg, int64_t ncols, int64_t K,
+                                                      const T* __restrict__ Sp, int R, T* __restrict__ ws, int64_t kper,
+                                                      int vec_ok, int ncg, int nitems) {
   constexpr int V = Vec<T>::N;
   constexpr int MRP = round_up(MR, 4);
   constexpr int UK = 8;
   const int tid = threadIdx.x;
-  const int64_t c0 = ((int64_t)blockIdx.x * 256 + tid) * V;
-  if (c0 >= ncols) return;
-  const int64_t kb = (int64_t)blockIdx.z * kper;
+  // work item = (column group, K range); the grid is exactly one resident wave and strides over the items
+  for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+  const int cg = w % ncg, z = w / ncg;
+  const int64_t c0 = ((int64_t)cg * 256 + tid) * V;
+  if (c0 >= ncols) continue;
+  const int64_t kb = (int64_t)z * kper;
   const int64_t ke = kb + kper < K ? kb + kper : K;
   const bool fast = vec_ok && c0 + V <= ncols;
   T acc[MR][V];
@@ -94,7 +108,7 @@ __global__ void __launch_bounds__(256) k_skinny_cc(const T* __restrict__ G, int6
     for (; k + UK <= ke; k += UK) {
       T b[UK][V];
 #pragma unroll
-      for (int u = 0; u < UK; ++u) ldvec<T>(gp + (k + u) * ldg, b[u]);
+      for (int u = 0; u < UK; ++u) ldstream<T>(gp + (k + u) * ldg, b[u]);
 #pragma unroll
       for (int u = 0; u < UK; ++u) {
         T s[MRP];
@@ -121,7 +135,7 @@ __global__ void __launch_bounds__(256) k_skinny_cc(const T* __restrict__ G, int6
 #pragma unroll
   for (int r = 0; r < MR; ++r) {
     if (r >= R) break;
-    T* wp = ws + ((int64_t)blockIdx.z * R + r) * ncols + c0;
+    T* wp = ws + ((int64_t)z * R + r) * ncols + c0;
     if (c0 + V <= ncols && (ncols % V) == 0) {
       stvec<T>(wp, acc[r]);
     } else {
@@ -129,6 +143,7 @@ __global__ void __launch_bounds__(256) k_skinny_cc(const T* __restrict__ G, int6
       for (int v = 0; v < V; ++v)
         if (c0 + v < ncols) wp[v] = acc[r][v];
     }
+  }
   }
 }
 
@@ -139,16 +154,18 @@ __global__ void __launch_bounds__(256) k_skinny_cc(const T* __restrict__ G, int6
 // k-contiguous copy through L1; warp-shuffle reduction at the end; split-K partials go to ws[z][r][c].
 // ------------------------------------------------------------------------------------------------------------
 template <typename T, int MR>
-__global__ void __launch_bounds__(256) k_skinny_kc(const T* __restrict__ G, int64_t ldg, int64_t ncols, int64_t K,
-                                                   const T* __restrict__ St, int64_t Kp, int R, T* __restrict__ ws,
-                                                   int64_t kper, int vec_ok) {
+__global__ void __launch_bounds__(256, 2) k_skinny_kc(const T* __restrict__ G, int64_t ldg, int64_t ncols, int64_t K,
+                                                      const T* __restrict__ St, int64_t Kp, int R, T* __restrict__ ws,
+                                                      int64_t kper, int vec_ok, int ncg, int nitems) {
   constexpr int V = Vec<T>::N;
-  constexpr int NC = 4;
+  constexpr int NC = sizeof(T) == 8 ? 2 : 4;   // columns per warp (Float64 accumulators take two registers each)
   constexpr int STEP = 32 * V;   // reduction indices per warp iteration
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int64_t cb = ((int64_t)blockIdx.x * 8 + warp) * NC;
-  if (cb >= ncols) return;
-  const int64_t kb = (int64_t)blockIdx.z * kper;
+  for (int w = blockIdx.x; w < nitems; w += gridDim.x) {
+  const int cg = w % ncg, z = w / ncg;
+  const int64_t cb = ((int64_t)cg * 8 + warp) * NC;
+  if (cb >= ncols) continue;
+  const int64_t kb = (int64_t)z * kper;
   const int64_t ke = kb + kper < K ? kb + kper : K;
   T acc[MR][NC];
 #pragma unroll
@@ -162,9 +179,9 @@ __global__ void __launch_bounds__(256) k_skinny_kc(const T* __restrict__ G, int6
       const int64_t kg = k0 + lane * V;
       T b0[NC][V], b1[NC][V];
 #pragma unroll
-      for (int c = 0; c < NC; ++c) ldvec<T>(G + (cb + c) * ldg + kg, b0[c]);
+      for (int c = 0; c < NC; ++c) ldstream<T>(G + (cb + c) * ldg + kg, b0[c]);
 #pragma unroll
-      for (int c = 0; c < NC; ++c) ldvec<T>(G + (cb + c) * ldg + kg + STEP, b1[c]);
+      for (int c = 0; c < NC; ++c) ldstream<T>(G + (cb + c) * ldg + kg + STEP, b1[c]);
 #pragma unroll
       for (int r = 0; r < MR; ++r) {
         T s0[V], s1[V];
@@ -207,8 +224,9 @@ __global__ void __launch_bounds__(256) k_skinny_kc(const T* __restrict__ G, int6
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       if (lane == ((r * NC + c) & 31) && r < R && cb + c < ncols)
-        ws[((int64_t)blockIdx.z * R + r) * ncols + cb + c] = v;
+        ws[((int64_t)z * R + r) * ncols + cb + c] = v;
     }
+  }
   }
 }
 
@@ -221,18 +239,27 @@ __global__ void __launch_bounds__(256) k_skinny_finish(const T* __restrict__ ws,
                                                        int ekind, int eop, const T* __restrict__ bias,
                                                        const T* __restrict__ y, int64_t ldy) {
   const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int r = blockIdx.y;   // one thread per element: the partial sums of an element are summed in order
   if (c >= ncols) return;
-  for (int r = 0; r < R; ++r) {
-    T s = T(0);
-    for (int z = 0; z < nsplit; ++z) s += ws[((int64_t)z * R + r) * ncols + c];
-    const int64_t i = swapped ? c : r, j = swapped ? r : c;
-    T v = alpha * s;
-    T* cp = C + i + j * ldc;
-    if (beta != T(0)) v += beta * *cp;
-    if (ekind == 1) v = nb_eval<T>(eop, v + (bias ? bias[i] : T(0)), T(0));
-    else if (ekind == 2) v *= nb_dunary<T>(eop, T(0), y[i + j * ldy]);
-    *cp = v;
+  const T* wp = ws + (int64_t)r * ncols + c;
+  const int64_t zs = (int64_t)R * ncols;
+  T s = T(0);
+  int z = 0;
+  for (; z + 8 <= nsplit; z += 8) {   // eight independent loads in flight, added in order
+    T t[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) t[u] = wp[(int64_t)(z + u) * zs];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) s += t[u];
   }
+  for (; z < nsplit; ++z) s += wp[(int64_t)z * zs];
+  const int64_t i = swapped ? c : r, j = swapped ? r : c;
+  T v = alpha * s;
+  T* cp = C + i + j * ldc;
+  if (beta != T(0)) v += beta * *cp;
+  if (ekind == 1) v = nb_eval<T>(eop, v + (bias ? bias[i] : T(0)), T(0));
+  else if (ekind == 2) v *= nb_dunary<T>(eop, T(0), y[i + j * ldy]);
+  *cp = v;
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -260,7 +287,7 @@ __device__ __forceinline__ uint16_t f2bf(float x) { return __bfloat16_as_ushort(
 __device__ __forceinline__ uint16_t f2h(float x) { return __half_as_ushort(__float2half_rn(x)); }
 
 template <typename T, int KK>
-__global__ void __launch_bounds__(256) k_gemm_smallk(const SmallK<T> g) {
+__global__ void __launch_bounds__(256, 2) k_gemm_smallk(const SmallK<T> g) {
   constexpr int V = Vec<T>::N;
   constexpr int NCB = 128, U = 4;
   constexpr int KKP = round_up(KK, V);
@@ -435,7 +462,7 @@ __global__ void __launch_bounds__(256) k_rowsum_finish_t(const T* __restrict__ p
 inline bool al16(const void* p) { return ((uintptr_t)p & 15) == 0; }
 
 template <typename T, template <typename, int> class Launcher, typename... Args>
-int32_t dispatch_mr(int R, Args... args) {
+int32_t dispatch_mr(int R, Args&... args) {
   switch (R) {
     case 1: return Launcher<T, 1>::run(args...);
     case 2: return Launcher<T, 2>::run(args...);
@@ -455,25 +482,43 @@ struct StreamArgs {
   const void* Sp; int64_t Kp;
   int R;
   void* ws; int64_t kper; int nsplit; int vec_ok;
+  int ncg;        // column groups (256 * V columns for cc, 32 for kc)
+  int query;      // 1: only report the resident CTA capacity in `capacity` (no launch)
+  int capacity;
 };
 
 template <typename T, int MR>
 struct LaunchCC {
-  static int32_t run(const StreamArgs& a) {
-    constexpr int V = Vec<T>::N;
-    dim3 grid((unsigned)((a.ncols + 256 * V - 1) / (256 * V)), 1, (unsigned)a.nsplit);
-    k_skinny_cc<T, MR><<<grid, 256, 0, a.ctx->stream>>>((const T*)a.G, a.ldg, a.ncols, a.K, (const T*)a.Sp, a.R,
-                                                        (T*)a.ws, a.kper, a.vec_ok);
+  static int32_t run(StreamArgs& a) {
+    auto kern = k_skinny_cc<T, MR>;
+    if (a.query) {
+      int occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0);
+      a.capacity = (occ > 0 ? occ : 1) * a.ctx->num_sms;
+      return NB_OK;
+    }
+    const int nitems = a.ncg * a.nsplit;
+    const int grid = nitems < a.capacity ? nitems : a.capacity;
+    kern<<<grid, 256, 0, a.ctx->stream>>>((const T*)a.G, a.ldg, a.ncols, a.K, (const T*)a.Sp, a.R, (T*)a.ws, a.kper,
+                                          a.vec_ok, a.ncg, nitems);
     NB_LAUNCH_CHECK(a.ctx);
     return NB_OK;
   }
 };
 template <typename T, int MR>
 struct LaunchKC {
-  static int32_t run(const StreamArgs& a) {
-    dim3 grid((unsigned)((a.ncols + 31) / 32), 1, (unsigned)a.nsplit);
-    k_skinny_kc<T, MR><<<grid, 256, 0, a.ctx->stream>>>((const T*)a.G, a.ldg, a.ncols, a.K, (const T*)a.Sp, a.Kp, a.R,
-                                                        (T*)a.ws, a.kper, a.vec_ok);
+  static int32_t run(StreamArgs& a) {
+    auto kern = k_skinny_kc<T, MR>;
+    if (a.query) {
+      int occ = 1;
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, 256, 0);
+      a.capacity = (occ > 0 ? occ : 1) * a.ctx->num_sms;
+      return NB_OK;
+    }
+    const int nitems = a.ncg * a.nsplit;
+    const int grid = nitems < a.capacity ? nitems : a.capacity;
+    kern<<<grid, 256, 0, a.ctx->stream>>>((const T*)a.G, a.ldg, a.ncols, a.K, (const T*)a.Sp, a.Kp, a.R, (T*)a.ws,
+                                          a.kper, a.vec_ok, a.ncg, nitems);
     NB_LAUNCH_CHECK(a.ctx);
     return NB_OK;
   }
@@ -490,20 +535,40 @@ int32_t run_stream(nb_ctx* ctx, bool g_c_contig, const T* G, int64_t ldg, int64_
                    int64_t sr, int64_t sk, int R, double alpha, double beta, T* C, int64_t ldc, bool swapped,
                    const nb_gemm_epilogue* epi) {
   constexpr int V = Vec<T>::N;
-  // CTAs along the output index; split K until ~4 CTAs per SM are resident (each keeps 8 loads per thread in flight)
-  const int64_t gx = g_c_contig ? (ncols + 256 * V - 1) / (256 * V) : (ncols + 31) / 32;
+  StreamArgs a{};
+  a.ctx = ctx; a.G = G; a.ldg = ldg; a.ncols = ncols; a.K = K; a.R = R;
+  a.vec_ok = al16(G) && (ldg % V == 0);
+  a.query = 1;
+  int32_t rc = g_c_contig ? dispatch_mr<T, LaunchCC>(R, a) : dispatch_mr<T, LaunchKC>(R, a);
+  if (rc != NB_OK) return rc;
+  a.query = 0;
+  // Work items = column groups x K ranges, run by ONE resident wave of CTAs striding over them: split K so that the
+  // items fill whole rounds of that wave (a 1.3-wave grid leaves two thirds of the part idle for the last third)
+  const int64_t kc_cols = 8 * (sizeof(T) == 8 ? 2 : 4);   // columns per CTA of k_skinny_kc
+  const int64_t ncg = g_c_contig ? (ncols + 256 * V - 1) / (256 * V) : (ncols + kc_cols - 1) / kc_cols;
   const int64_t kquant = g_c_contig ? 64 : 32 * V * 2;
-  int64_t nsplit = (4ll * ctx->num_sms + gx - 1) / gx;
   const int64_t maxsplit = (K + kquant - 1) / kquant;
+  const int64_t cap = a.capacity;
+  int64_t nsplit = 1;
+  if (ncg < cap) {
+    nsplit = cap / ncg;   // one round
+  } else {
+    double best = 0.0;
+    for (int64_t t = 1; t <= 8; ++t) {
+      const int64_t items = ncg * t;
+      const double eff = (double)items / (double)(((items + cap - 1) / cap) * cap);
+      if (eff > best + 0.02) { best = eff; nsplit = t; }
+    }
+  }
   if (nsplit > maxsplit) nsplit = maxsplit;
-  if (nsplit > 512) nsplit = 512;
+  if (nsplit > 1024) nsplit = 1024;
   if (nsplit < 1) nsplit = 1;
   int64_t kper = ((K + nsplit - 1) / nsplit + kquant - 1) / kquant * kquant;
   nsplit = (K + kper - 1) / kper;
   const int RP = padded_mr(R);
   const int64_t Kp = (K + 32 * V - 1) / (32 * V) * (32 * V);
   void *ws = nullptr, *sp = nullptr;
-  int32_t rc = nb_pool_alloc(ctx, (size_t)(nsplit * R * ncols) * sizeof(T), &ws);
+  rc = nb_pool_alloc(ctx, (size_t)(nsplit * R * ncols) * sizeof(T), &ws);
   if (rc != NB_OK) return rc;
   rc = nb_pool_alloc(ctx, (size_t)RP * (size_t)Kp * sizeof(T), &sp);
   if (rc != NB_OK) { nb_pool_release(ctx, ws); return rc; }
@@ -513,12 +578,11 @@ int32_t run_stream(nb_ctx* ctx, bool g_c_contig, const T* G, int64_t ldg, int64_
                                                                       g_c_contig ? 1 : Kp, g_c_contig ? RP : 1, RP, Kp);
     ctx->stats.kernel_launches++;
   }
-  StreamArgs a{ctx, G, ldg, ncols, K, sp, Kp, R, ws, kper, (int)nsplit, 0};
-  a.vec_ok = al16(G) && (ldg % V == 0);
+  a.Sp = sp; a.Kp = Kp; a.ws = ws; a.kper = kper; a.nsplit = (int)nsplit; a.ncg = (int)ncg;
   rc = g_c_contig ? dispatch_mr<T, LaunchCC>(R, a) : dispatch_mr<T, LaunchKC>(R, a);
   if (rc == NB_OK) {
     const int ek = epi ? epi->kind : 0;
-    k_skinny_finish<T><<<(unsigned)((ncols + 255) / 256), 256, 0, ctx->stream>>>(
+    k_skinny_finish<T><<<dim3((unsigned)((ncols + 255) / 256), (unsigned)R), 256, 0, ctx->stream>>>(
         (const T*)ws, (int)nsplit, R, ncols, (T)alpha, (T)beta, C, ldc, swapped ? 1 : 0, ek, epi ? epi->op : 0,
         epi ? (const T*)epi->bias : nullptr, epi ? (const T*)epi->y : nullptr, epi ? epi->ldy : 0);
     ctx->stats.kernel_launches++;

@@ -300,6 +300,17 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// 64 columns in one instruction: the fold of a short K chunk is a latency chain (barrier -> TMEM load -> add -> barrier)
+// between two short MMA chunks, so fewer, wider loads matter more than register economy
+__device__ __forceinline__ void tmem_ld64(uint32_t taddr, uint32_t (&v)[64]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x64.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32, %33, %34, %35, %36, %37, %38, %39, %40, %41, %42, %43, %44, %45, %46, %47, %48, %49, %50, %51, %52, %53, %54, %55, %56, %57, %58, %59, %60, %61, %62, %63}, [%64];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31]), "=r"(v[32]), "=r"(v[33]), "=r"(v[34]), "=r"(v[35]), "=r"(v[36]), "=r"(v[37]), "=r"(v[38]), "=r"(v[39]), "=r"(v[40]), "=r"(v[41]), "=r"(v[42]), "=r"(v[43]), "=r"(v[44]), "=r"(v[45]), "=r"(v[46]), "=r"(v[47]), "=r"(v[48]), "=r"(v[49]), "=r"(v[50]), "=r"(v[51]), "=r"(v[52]), "=r"(v[53]), "=r"(v[54]), "=r"(v[55]), "=r"(v[56]), "=r"(v[57]), "=r"(v[58]), "=r"(v[59]), "=r"(v[60]), "=r"(v[61]), "=r"(v[62]), "=r"(v[63])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
 // ---- operand splits -------------------------------------------------------------------------------
 // tf32: hi = round-to-nearest tf32(x) (low 13 mantissa bits zero), lo = x - hi (exact), stored as f32
 __device__ __forceinline__ void split1(float x, float& hi, float& lo) {
@@ -354,6 +365,21 @@ struct EpiAcc {
   float r[NCOL];
 
   __device__ __forceinline__ void fold(uint32_t taddr, bool first) {
+    if constexpr (NCOL % 64 == 0 && !kind_is_i8(KIND)) {
+#pragma unroll
+      for (int c = 0; c < NCOL / 64; ++c) {
+        uint32_t v[64];
+        tmem_ld64(taddr + (uint32_t)(c * 64), v);
+        if (first) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) r[c * 64 + j] = __uint_as_float(v[j]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 64; ++j) r[c * 64 + j] += __uint_as_float(v[j]);
+        }
+      }
+      return;
+    }
 #pragma unroll
     for (int c = 0; c < NCOL / 32; ++c) {
       uint32_t v[32];
@@ -1459,10 +1485,10 @@ template <int BN, int KIND>
 int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   using C_ = Cfg<BN, KIND>;
   auto kern = k_gemm_tc<BN, KIND>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  /* per device: cudaFuncSetAttribute applies to the current device only */
+  if (!attr_done[ctx->device & 63]) {
     NB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   const int ntiles = g.tiles_m * g.tiles_n;
   const int grid = ntiles < ctx->num_sms ? ntiles : ctx->num_sms;
@@ -1475,10 +1501,10 @@ int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
 template <int KIND>
 int32_t launch_pair(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   using C2 = Cfg2T<KIND>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static bool attr_done[64] = {};  /* per device: cudaFuncSetAttribute applies to the current device only */
+  if (!attr_done[ctx->device & 63]) {
     NB_CUDA_OK(ctx, cudaFuncSetAttribute(k_gemm_tc_pair<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::SMEM));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   const int ntiles = g.tiles_m * g.tiles_n;
   int max_pairs = ctx->num_sms / 2;
@@ -1867,7 +1893,8 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     // fold meanwhile): with 128-chunks the MMA's runway would be 2 x 128 of K (~4 us) against a ~10 us plain store,
     // and every tile would stall.  Chunks of 384 there (13 us of runway) cost little accuracy: the error variance of a
     // tile is ~ sum c_i^3, so 2 x 384^3 + 58 x 128^3 at K = 8192 gives 5.8e-7 per product instead of 4.1e-7.
-    int64_t kfirst = math_mode == NB_MATH_BF16X3 ? kchunk : 3 * kchunk;
+    int64_t kfirst = kchunk;
+    if (math_mode != NB_MATH_BF16X3 && k >= 32 * kchunk) kfirst = 3 * kchunk;  // only where 2 long chunks weigh little
     if (const char* e = getenv("NB_GEMM_KCHUNK_FIRST")) kfirst = atoll(e) >= 64 ? atoll(e) / 64 * 64 : kfirst;
     if (kfirst < kchunk) kfirst = kchunk;
     g.kchunk_first_kb = (int32_t)(kfirst / (128 / esize));

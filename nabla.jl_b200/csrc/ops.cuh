@@ -21,7 +21,14 @@ struct nb_prog {
   uint8_t hop[NB_MAX_INSTR];     // dense dispatch index (NB_HOP_*): the switch becomes a jump table
   uint8_t rflags[NB_MAX_INSTR];  // NB_RF_* : what the reverse step of instruction i reads and how it writes
   uint32_t arg_live;             // bit k: operand k reaches the result (otherwise its sensitivity is zero)
+  // the program selects between branches (NB_OP_MASK / NB_OP_MASKN): a zero adjoint then contributes exactly zero
+  // (0 * Inf from the branch NOT taken must not reach the result: ForwardDiff never evaluates its derivative)
+  uint32_t guard;
 };
+
+// adjoint * partial, with the selection guard above
+template <typename T>
+__device__ __forceinline__ T nb_gmul(T g, T d, bool guard) { return (guard && g == T(0)) ? T(0) : g * d; }
 
 enum {
   NB_HOP_IDENTITY = 0, NB_HOP_NEG, NB_HOP_ABS2, NB_HOP_SQRT, NB_HOP_INV, NB_HOP_EXP, NB_HOP_LOG, NB_HOP_TANH,
@@ -55,6 +62,9 @@ __host__ __device__ constexpr int nb_partial_needs(int op, int wrt /*0=a,1=b*/) 
   const int A = 1, B = 2, Y = 4;
   switch (op) {
     case NB_OP_IDENTITY: case NB_OP_NEG: case NB_OP_DEG2RAD: case NB_OP_RAD2DEG: return 0;
+    case NB_OP_SIGN: case NB_OP_STEP: case NB_OP_FLOOR: case NB_OP_CEIL: case NB_OP_ROUND: case NB_OP_TRUNC: return 0;
+    case NB_OP_GT: case NB_OP_LT: case NB_OP_GE: case NB_OP_LE: return 0;
+    case NB_OP_MASK: case NB_OP_MASKN: return wrt == 0 ? 0 : A;   // d/dv is the indicator of the condition (operand a)
     case NB_OP_TANH: case NB_OP_EXP: case NB_OP_LOGISTIC: case NB_OP_SQRT: case NB_OP_INV:
     case NB_OP_TAN: case NB_OP_EXP2: case NB_OP_EXP10: case NB_OP_CBRT: case NB_OP_COT:
     case NB_OP_COTH: case NB_OP_TAND: case NB_OP_COTD: case NB_OP_EXPM1:
@@ -233,6 +243,18 @@ __device__ __forceinline__ T nb_eval_full(int op, T a, T b) {
     case NB_OP_MAX: return fmax(a, b);
     case NB_OP_MIN: return fmin(a, b);
     case NB_OP_ATAN2: return atan2(a, b);
+    case NB_OP_SIGN: return a > T(0) ? one : (a < T(0) ? -one : a);   // sign(+-0) = +-0, sign(NaN) = NaN (Julia)
+    case NB_OP_STEP: return a > T(0) ? one : T(0);
+    case NB_OP_FLOOR: return floor(a);
+    case NB_OP_CEIL: return ceil(a);
+    case NB_OP_ROUND: return rint(a);   // Julia's round: ties to even
+    case NB_OP_TRUNC: return trunc(a);
+    case NB_OP_GT: return a > b ? one : T(0);
+    case NB_OP_LT: return a < b ? one : T(0);
+    case NB_OP_GE: return a >= b ? one : T(0);
+    case NB_OP_LE: return a <= b ? one : T(0);
+    case NB_OP_MASK: return a != T(0) ? b : T(0);
+    case NB_OP_MASKN: return a == T(0) ? b : T(0);
     case NB_OP_BETA: return exp(lgamma(a) + lgamma(b) - lgamma(a + b));
     case NB_OP_BESSELJ: return T(nb_bessel(0, (double)a, (double)b));
     case NB_OP_BESSELY: return T(nb_bessel(1, (double)a, (double)b));
@@ -273,6 +295,7 @@ __device__ __forceinline__ T nb_dunary_full(int op, T a, T y) {
     case NB_OP_IDENTITY: return one;
     case NB_OP_NEG: return -one;
     case NB_OP_ABS: return a > T(0) ? one : (a < T(0) ? -one : T(0));
+    case NB_OP_SIGN: case NB_OP_STEP: case NB_OP_FLOOR: case NB_OP_CEIL: case NB_OP_ROUND: case NB_OP_TRUNC: return T(0);
     case NB_OP_ABS2: return T(2) * a;
     case NB_OP_SQRT: return T(0.5) / y;
     case NB_OP_CBRT: return one / (T(3) * y * y);
@@ -407,6 +430,9 @@ __device__ __forceinline__ T nb_dbinary(int op, int wrt, T a, T b, T y) {
       T den = a * a + b * b;
       return wrt == 0 ? b / den : -a / den;
     }
+    case NB_OP_GT: case NB_OP_LT: case NB_OP_GE: case NB_OP_LE: return T(0);
+    case NB_OP_MASK: return wrt == 0 ? T(0) : (a != T(0) ? one : T(0));
+    case NB_OP_MASKN: return wrt == 0 ? T(0) : (a == T(0) ? one : T(0));
     case NB_OP_BETA: {
       const double pab = nb_polygamma<0>((double)a + (double)b);
       return y * T(nb_polygamma<0>((double)(wrt == 0 ? a : b)) - pab);
@@ -502,6 +528,9 @@ inline void nb_prog_derive(nb_prog& P) {
     }
     P.rflags[i] = f;
   }
+  P.guard = 0;
+  for (int i = 0; i < n; ++i)
+    if (P.op[i] == NB_OP_MASK || P.op[i] == NB_OP_MASKN) P.guard = 1;
   P.arg_live = 0;
   for (int k = 0; k < na; ++k)
     if (written[k] || n == 0) P.arg_live |= 1u << k;
@@ -661,13 +690,14 @@ __device__ __forceinline__ void nb_prog_grad_vec(const nb_prog& P, T (*vals)[V],
       for (int v = 0; v < V; ++v) b[v] = T(0);
     }
     nb_partials_vec<T, V>(op, a, b, y, da, db);
+    const bool gd = P.guard != 0;
     if (ia >= 0) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) adj[ia][v] += g[v] * da[v];
+      for (int v = 0; v < V; ++v) adj[ia][v] += nb_gmul(g[v], da[v], gd);
     }
     if (bin && ib >= 0) {
 #pragma unroll
-      for (int v = 0; v < V; ++v) adj[ib][v] += g[v] * db[v];
+      for (int v = 0; v < V; ++v) adj[ib][v] += nb_gmul(g[v], db[v], gd);
     }
   }
 }

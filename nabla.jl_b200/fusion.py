@@ -28,7 +28,8 @@ from .device import DevArray
 _ID, _ADD = OPCODES["identity"], OPCODES["add"]
 _A, _B, _Y = 1, 2, 4
 
-_NEEDS_NONE = {"identity", "neg", "deg2rad", "rad2deg"}
+_NEEDS_NONE = {"identity", "neg", "deg2rad", "rad2deg", "sign", "step", "floor", "ceil", "round", "trunc",
+               "gt", "lt", "ge", "le"}
 _NEEDS_Y = {"tanh", "exp", "logistic", "sqrt", "inv", "tan", "exp2", "exp10", "cbrt", "cot", "coth", "tand",
             "cotd", "expm1"}
 _NEEDS_Y |= {"erfinv", "erfcinv", "invdigamma"}
@@ -50,6 +51,8 @@ def partial_needs(op, wrt=0):
         return _Y
     if name in _NEEDS_AY:
         return _A | _Y
+    if name in ("mask", "maskn"):
+        return 0 if wrt == 0 else _A
     if name == "mul":
         return _B if wrt == 0 else _A
     if name == "div":

@@ -60,9 +60,16 @@ class Sym:
     def __abs__(self): return Sym("op", op="abs", a=self)
 
     def __bool__(self):
-        raise UnsupportedOp(4, "data-dependent control flow cannot be traced into a device program")
+        raise UnsupportedOp(4, "data-dependent control flow (`if x > 0`, `a if c else b`, `and`/`or`) cannot be traced "
+                               "into a device program: write the selection as ifelse(x > 0, a, b), max_, min_, abs or "
+                               "sign — both branches are traced, the derivative is that of the branch taken")
 
-    __lt__ = __le__ = __gt__ = __ge__ = lambda self, o: self.__bool__()
+    # comparisons are VALUES (1.0 / 0.0, derivative zero) that ifelse / arithmetic consume
+    def __gt__(self, o): return self._bin("gt", o)
+    def __lt__(self, o): return self._bin("lt", o)
+    def __ge__(self, o): return self._bin("ge", o)
+    def __le__(self, o): return self._bin("le", o)
+    __hash__ = object.__hash__
 
 
 class ScalarFn:
@@ -87,6 +94,18 @@ class ScalarFn:
             return Sym("op", op=self.name, a=a, b=b)
         from . import rules  # scalar Nodes / device scalars: a 0-dim broadcast
         return rules.scalar_call(self, args)
+
+
+def ifelse(cond, a, b):
+    """``ifelse(cond, a, b)`` inside a traced scalar function: ``cond`` is a comparison of traced values (``x > 0``),
+    both branches are traced, and per element the value AND the derivative are those of the branch taken — what
+    ForwardDiff's duals give for ``x > 0 ? a : b`` under ``fmad`` (src/core.jl:285-292).  The branch not taken
+    contributes exactly zero (no ``0 * Inf``): lowered to ``MASK(c, a) + MASKN(c, b)`` (include/nabla_cuda.h)."""
+    if not isinstance(cond, Sym):
+        if isinstance(cond, (bool, numbers.Real)):
+            return a if cond else b
+        raise UnsupportedOp(4, "ifelse: the condition must be a comparison of traced values")
+    return Sym("op", op="add", a=Sym("op", op="mask", a=cond, b=Sym.lift(a)), b=Sym("op", op="maskn", a=cond, b=Sym.lift(b)))
 
 
 def _is_const(s, v=None):

@@ -37,7 +37,7 @@ __all__ = [
     "unthunk", "add_bang_bang", "check_errs", "oneslike", "zeroslike",
     "hcat", "vcat", "getindex", "reshape", "fill", "checkpoint", "R", "colon",
     "symm", "symv", "trmm", "trmv", "trsm", "trsv",
-    "kron", "plus_I", "copy",
+    "kron", "plus_I", "copy", "ifelse",
 ]
 
 _pysum = sum
@@ -277,8 +277,32 @@ def _invdigamma(y):
     return x if x.ndim else float(x)
 
 
+_ZERO = lambda x: 0.0 * x  # noqa: E731   (derivative of a piecewise-constant function, as ForwardDiff gives)
+
+
+def ifelse(cond, a, b):
+    """Julia ``ifelse(cond, a, b)`` / ``cond ? a : b`` element-wise: value and partial of the branch taken — comparisons
+    of ``Dual``s act on the values (ForwardDiff semantics, src/core.jl:285-292)."""
+    if isinstance(cond, Dual):
+        cond = cond.v
+    cond = np.asarray(cond) != 0
+    av, ad = Dual._split(a)
+    bv, bd = Dual._split(b)
+    val = np.where(cond, av, bv)
+    if ad is None and bd is None:
+        return val if val.ndim else val[()]
+    d = np.where(cond, 0.0 if ad is None else ad, 0.0 if bd is None else bd)
+    return Dual(val, d)
+
+
 _UNARY = {
     # name: (f, f')  -- SURVEY.md §8(c) catalogue
+    "sign": (np.sign, _ZERO),
+    "step": (lambda x: (x > 0) * 1.0, _ZERO),
+    "floor": (np.floor, _ZERO),
+    "ceil": (np.ceil, _ZERO),
+    "round": (np.rint, _ZERO),
+    "trunc": (np.trunc, _ZERO),
     "identity": (lambda x: x, lambda x: 1.0 + 0.0 * x),
     "neg": (lambda x: -x, lambda x: -1.0 + 0.0 * x),
     "abs": (np.abs, np.sign),
@@ -371,6 +395,14 @@ _BINARY = {
     "max": (np.maximum, lambda x, y: (x > y) * 1.0, lambda x, y: (x <= y) * 1.0),
     "min": (np.minimum, lambda x, y: (x < y) * 1.0, lambda x, y: (x >= y) * 1.0),
     "atan2": (np.arctan2, lambda x, y: y / (x * x + y * y), lambda x, y: -x / (x * x + y * y)),
+    "gt": (lambda x, y: (x > y) * 1.0, lambda x, y: 0.0 * (x + y), lambda x, y: 0.0 * (x + y)),
+    "lt": (lambda x, y: (x < y) * 1.0, lambda x, y: 0.0 * (x + y), lambda x, y: 0.0 * (x + y)),
+    "ge": (lambda x, y: (x >= y) * 1.0, lambda x, y: 0.0 * (x + y), lambda x, y: 0.0 * (x + y)),
+    "le": (lambda x, y: (x <= y) * 1.0, lambda x, y: 0.0 * (x + y), lambda x, y: 0.0 * (x + y)),
+    "mask": (lambda c, v: np.where(np.asarray(c) != 0, v, 0.0), lambda c, v: 0.0 * (c + v),
+             lambda c, v: (np.asarray(c) != 0) * 1.0 + 0.0 * v),
+    "maskn": (lambda c, v: np.where(np.asarray(c) == 0, v, 0.0), lambda c, v: 0.0 * (c + v),
+              lambda c, v: (np.asarray(c) == 0) * 1.0 + 0.0 * v),
     "beta": (lambda x, y: _sp.beta(x, y), lambda x, y: _sp.beta(x, y) * (_sp.digamma(x) - _sp.digamma(x + y)),
              lambda x, y: _sp.beta(x, y) * (_sp.digamma(y) - _sp.digamma(x + y))),
 }

@@ -44,6 +44,9 @@ UNARY = {
     "airyai": mp.airyai, "airyaiprime": lambda x: mp.airyai(x, derivative=1), "airybi": mp.airybi,
     "airybiprime": lambda x: mp.airybi(x, derivative=1),
     "dawson": lambda x: mp.sqrt(mp.pi) / 2 * mp.exp(-x * x) * mp.erfi(x), "erfi": mp.erfi, "invdigamma": invdigamma,
+    # piecewise-constant functions (none of the test points is a breakpoint; mp.diff gives exactly 0)
+    "sign": mp.sign, "step": lambda x: mp.mpf(1) if x > 0 else mp.mpf(0), "floor": mp.floor, "ceil": mp.ceil,
+    "round": mp.nint, "trunc": lambda x: mp.floor(x) if x >= 0 else mp.ceil(x),
 }
 SECOND = {"besselj": mp.besselj, "bessely": mp.bessely, "besseli": mp.besseli, "besselk": mp.besselk,
           "polygamma": mp.polygamma}

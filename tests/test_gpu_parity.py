@@ -1333,3 +1333,32 @@ def test_mlp_gradient_f64_chain_of_split_products(nb, orc):
     np.testing.assert_allclose(y, yr, rtol=1e-11)
     for a, b in zip(g, gr):
         close(a, b, scale=0.05)
+
+
+# ---------------------------------------------------------------------------------------------
+# value-dependent scalar functions: fmad differentiates ANY scalar f along the branch taken (core.jl:285-292)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_value_dependent_lambdas(nb, orc, dtype):
+    """`x > 0 ? x : 0.1x` and friends, written with ifelse (both branches traced, the derivative of the taken one):
+    values and sensitivities against the oracle's duals, whose comparisons act on values like ForwardDiff's."""
+    rng = np.random.default_rng(21)
+    sc = 1.0 if dtype == np.float64 else 1.0
+    x = rng.standard_normal((37, 29))
+    x[3, 4] = 0.0          # exactly on the breakpoint
+    y = rng.standard_normal((37, 29))
+    leaky = lambda ns: (lambda a: ns.ifelse(a > 0.0, a, 0.1 * a))
+    check_case(nb, orc, lambda ns, a: ns.broadcast(leaky(ns), a), [x], rng.standard_normal((37, 29)), dtype, sc)
+    # the branch NOT taken is NaN / Inf there (log of a negative number, 1/0): it must contribute exactly zero
+    safe_log = lambda ns: (lambda a: ns.ifelse(a > 0.0, ns.log(a), 0.0 * a))
+    check_case(nb, orc, lambda ns, a: ns.broadcast(safe_log(ns), a), [x], rng.standard_normal((37, 29)), dtype, sc)
+    safe_inv = lambda ns: (lambda a: ns.ifelse(a > 0.0, 1.0 / ns.sqrt(a), a * a))
+    check_case(nb, orc, lambda ns, a: ns.broadcast(safe_inv(ns), a), [x], rng.standard_normal((37, 29)), dtype, sc)
+    # two operands, unbroadcast of the second, comparison between operands
+    pick = lambda ns: (lambda a, b: ns.ifelse(a >= b, a * b, a - b))
+    check_case(nb, orc, lambda ns, a, b: ns.broadcast(pick(ns), a, b), [x, y[:, :1]], rng.standard_normal((37, 29)), dtype, sc)
+    # comparisons as values, step / sign / floor inside a composite
+    comp = lambda ns: (lambda a: ns.step(a) * ns.exp(a) + ns.sign(a) * a + ns.floor(a) * 0.5 + (a < 0.25) * a * a)
+    check_case(nb, orc, lambda ns, a: ns.broadcast(comp(ns), a), [x], rng.standard_normal((37, 29)), dtype, sc)
+    # inside a reduction
+    check_case(nb, orc, lambda ns, a: ns.sum(leaky(ns), a), [x], None, dtype, sc)

@@ -56,6 +56,10 @@ def test_julia_glue_opcode_table_matches_the_header():
     for k, v in consts.items():
         assert ops[k] == v
         seen[k] = v
+    m = re.search(r"OP_GT, OP_LT, OP_GE, OP_LE, OP_MASK, OP_MASKN = " + ", ".join([r"Int32\((\d+)\)"] * 6), src)
+    for k, v in zip(("gt", "lt", "ge", "le", "mask", "maskn"), map(int, m.groups())):
+        assert ops[k] == v
+        seen[k] = v
     missing = [n for n in scalar.UNARY + scalar.BINARY if n not in seen]
     assert not missing, f"catalogue ops without a Julia mapping: {missing}"
 
@@ -166,8 +170,8 @@ def test_opcodes_match_header():
     assert ops["add"] == 64 and ops["atan2"] == 73
     assert ops["beta"] == 74 and ops["gamma"] == 96 and ops["erfcx"] == 105
     assert ops["airyai"] == 106 and ops["invdigamma"] == 112 and ops["sf_end"] == 113
-    assert ops["besselj"] == 75 and ops["polygamma"] == 79 and ops["binary_end"] == 80
-    assert len(scalar.UNARY) == 58 + 17 and len(scalar.BINARY) == 16   # + every SpecialFunctions entry the reference lists
+    assert ops["besselj"] == 75 and ops["polygamma"] == 79 and ops["gt"] == 80 and ops["maskn"] == 85 and ops["binary_end"] == 86
+    assert len(scalar.UNARY) == 64 + 17 and len(scalar.BINARY) == 22   # + every SpecialFunctions entry the reference lists
     assert "sf_begin" not in scalar.UNARY and "binary_end" not in scalar.BINARY
 
 
@@ -536,3 +540,18 @@ def _ozaki_numpy(np, S, rec_tol, norm_tol, elem_tol):
     ref = A @ B
     assert np.linalg.norm(C - ref) / np.linalg.norm(ref) < norm_tol
     assert np.max(np.abs(C - ref) / (np.abs(A).max(1, keepdims=True) * np.abs(B).max(0, keepdims=True) * np.sqrt(k))) < elem_tol
+
+
+def test_tracer_lowers_selection_and_refuses_control_flow():
+    """ifelse / comparisons trace to MASK / MASKN / GT ... (include/nabla_cuda.h); Python control flow on a traced value
+    cannot be traced and raises UnsupportedOp (the Julia glue: TypeError for a non-Bool condition)."""
+    import nabla_jl_b200 as nb
+    ops = _lib.OPCODES
+    p = nb.compile_scalar(lambda x: nb.ifelse(x > 0.0, x, 0.1 * x), 1)
+    assert p.ops == (ops["gt"], ops["mask"], ops["mul"], ops["maskn"], ops["add"])
+    assert nb.compile_scalar(lambda x, y: (x <= y) * x, 2).ops == (ops["le"], ops["mul"])
+    for bad in (lambda x: x if x > 0 else 0.1 * x, lambda x: max(x, 0.0), lambda x: (x > 0 and x) or 0.0):
+        with pytest.raises(nb.UnsupportedOp):
+            nb.compile_scalar(bad, 1)
+    # a host-side constant condition is just Python
+    assert nb.ifelse(True, 1.0, 2.0) == 1.0
