@@ -12,7 +12,7 @@ import nabla_jl_b200 as nb  # noqa: E402
 from nabla_jl_b200 import kernels as K  # noqa: E402
 from nabla_jl_b200.fusion import nb_gemm_epilogue  # noqa: E402
 
-B = int(sys.argv[1]) if len(sys.argv) > 1 else 32768
+B = int(sys.argv[1]) if len(sys.argv) > 1 and sys.argv[1].isdigit() else 32768
 dt = np.float64 if "--f64" in sys.argv else np.float32
 s = np.dtype(dt).itemsize
 ctx = nb.get_context()
