@@ -762,8 +762,11 @@ def run_gpu(args):
         except Exception as e:  # the headline number stands on its own
             line["extra"] = {"error": repr(e)}
     if rank == 0:
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     barrier()
+    for drv in (locals().get("sg"), locals().get("sg_prof")):
+        if drv is not None:
+            drv.close()      # a captured step holds NCCL kernels: destroy the graph before the communicator
     comm.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -680,6 +680,8 @@ struct LeanKindF {
 // hot primitives: kernels of this translation unit; the rest of the catalogue: bcast_lean_cold_*.cu
 template <typename T>
 bool lean_any(int kind, int mode, const MRP& P, const LeanLaunch& a, cudaStream_t st) {
+  if (nb_is_fop(P.op))
+    return sizeof(T) == 4 ? nb_lean_fused_f32(kind, P.op, mode, P, a, st) : nb_lean_fused_f64(kind, P.op, mode, P, a, st);
   if (lean_hot_op(P.op)) return lean_dispatch<T>(P.op, mode, LeanKindF<T>{kind, P, a, st});
   if (nb_op_is_unary(P.op))
     return sizeof(T) == 4 ? nb_lean_cold_un_f32(kind, P.op, mode, P, a, st) : nb_lean_cold_un_f64(kind, P.op, mode, P, a, st);
@@ -947,7 +949,12 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
   static const nb_prog identity_prog = {1, 0, 0, {0}, {0}, {0}, {0}};
   const nb_prog& G = C.prog ? *C.prog : identity_prog;
   NB_REQUIRE(ctx, G.nargs == C.nargs, NB_ERR_INVALID, "program/operand count mismatch");
-  const bool fast = G.n_instr <= 1;
+  // un(bin(x0, x1)) over at most two operands / constants (`tanh.(A .+ b)`, `log.(f .+ eps)`): one fused primitive of
+  // the single-primitive kernels instead of a two-instruction program on the interpreter
+  static const bool fop_on = !(getenv("NB_FUSED_OPS") && atoi(getenv("NB_FUSED_OPS")) == 0);
+  const bool is_fop = fop_on && G.n_instr == 2 && G.nargs <= 2 && nb_op_is_binary(G.op[0]) && !nb_is_fop(G.op[0]) &&
+                      nb_op_is_unary(G.op[1]) && G.a[1] == G.nargs && nb_fop_supported(G.op[1], G.op[0]);
+  const bool fast = G.n_instr <= 1 || is_fop;
 
   MRP P;
   memset(&P, 0, sizeof(P));
@@ -977,6 +984,8 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
     // map the single instruction's two operands onto arg[0], arg[1]
     int op = G.n_instr ? G.op[0] : NB_OP_IDENTITY;
     int src[2] = {G.n_instr ? G.a[0] : 0, (G.n_instr && nb_op_is_binary(op)) ? G.b[0] : -1000};
+    if (is_fop)   // derivative of the outer function from the Branch's saved value when it is a function of y alone
+      op = nb_fop(G.op[1], G.op[0], C.pullback && C.ysaved && nb_fop_un_y_only(G.op[1]));
     P.op = op;
     P.nargs = 2;
     for (int s = 0; s < 2; ++s) {

@@ -85,6 +85,9 @@ bool nb_lean_cold_un_f32(int kind, int op, int mode, const nbb::MRP& P, const nb
 bool nb_lean_cold_un_f64(int kind, int op, int mode, const nbb::MRP& P, const nbb::LeanLaunch& a, cudaStream_t st);
 bool nb_lean_cold_bin_f32(int kind, int op, int mode, const nbb::MRP& P, const nbb::LeanLaunch& a, cudaStream_t st);
 bool nb_lean_cold_bin_f64(int kind, int op, int mode, const nbb::MRP& P, const nbb::LeanLaunch& a, cudaStream_t st);
+// fused un(bin(a, b)) primitives (bcast_lean_fused_*.cu; ops.cuh nb_fop)
+bool nb_lean_fused_f32(int kind, int op, int mode, const nbb::MRP& P, const nbb::LeanLaunch& a, cudaStream_t st);
+bool nb_lean_fused_f64(int kind, int op, int mode, const nbb::MRP& P, const nbb::LeanLaunch& a, cudaStream_t st);
 // composite programs on the lean kernels (bcast_prog.cu)
 struct nb_prog;
 bool nb_lean_prog(int dtype, int kind, int mode, const nbb::MRP& P, const nb_prog& G, const nbb::LeanLaunch& a, cudaStream_t st);

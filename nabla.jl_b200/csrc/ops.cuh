@@ -48,11 +48,31 @@ enum {
 #define NB_LN10 2.30258509299404568402
 #define NB_2_SQRTPI 1.12837916709551257390
 
+// Internal (not ABI) fused primitives un(bin(a, b)) — `tanh.(A .+ b)`, `log.(f .+ eps)`, `exp.(a .* b)` … as ONE
+// compile-time-specialised op of the lean kernels instead of a two-instruction program on the interpreter (113
+// thread-instructions per element, 17-28 % of the HBM peak).  bit 12 marks the family, bit 11 "the derivative of `un`
+// is taken from the saved forward value y" (only for un whose derivative is a function of y alone, and only when the
+// Branch's saved value is passed), bits 4-10 the unary op, bits 0-3 the binary op - NB_OP_ADD.
+__host__ __device__ constexpr int nb_fop(int un, int bin, int use_y) {
+  return 0x1000 | (use_y ? 0x800 : 0) | (un << 4) | (bin - NB_OP_ADD);
+}
+__host__ __device__ constexpr bool nb_is_fop(int op) { return (op & 0x1000) != 0; }
+__host__ __device__ constexpr int nb_fop_un(int op) { return (op >> 4) & 0x7F; }
+__host__ __device__ constexpr int nb_fop_bin(int op) { return NB_OP_ADD + (op & 0xF); }
+__host__ __device__ constexpr bool nb_fop_y(int op) { return (op & 0x800) != 0; }
+__host__ __device__ constexpr bool nb_fop_supported(int un, int bin) {
+  return (un == NB_OP_TANH || un == NB_OP_EXP || un == NB_OP_LOG || un == NB_OP_LOGISTIC || un == NB_OP_SQRT ||
+          un == NB_OP_ABS2) && (bin == NB_OP_ADD || bin == NB_OP_SUB || bin == NB_OP_MUL);
+}
+__host__ __device__ constexpr bool nb_fop_un_y_only(int un) {
+  return un == NB_OP_TANH || un == NB_OP_EXP || un == NB_OP_LOGISTIC || un == NB_OP_SQRT;
+}
+
 __host__ __device__ constexpr bool nb_op_is_unary(int op) {
   return (op >= 0 && op < NB_OP_UNARY_END) || (op >= NB_OP_SF_BEGIN && op < NB_OP_SF_END);
 }
 __host__ __device__ constexpr bool nb_op_is_binary(int op) {
-  return op >= NB_OP_ADD && op < NB_OP_BINARY_END;
+  return (op >= NB_OP_ADD && op < NB_OP_BINARY_END) || nb_is_fop(op);
 }
 
 // Which inputs does the partial derivative need?  bit0: operand a, bit1: operand b, bit2: y.
@@ -60,6 +80,8 @@ __host__ __device__ constexpr bool nb_op_is_binary(int op) {
 //  per wanted operand by nb_partial_needs)
 __host__ __device__ constexpr int nb_partial_needs(int op, int wrt /*0=a,1=b*/) {
   const int A = 1, B = 2, Y = 4;
+  if (nb_is_fop(op))   // f'(bin(a, b)) from the saved y or from both operands, times the inner partial
+    return (nb_fop_y(op) ? Y : (A | B)) | (nb_fop_bin(op) == NB_OP_MUL ? (wrt == 0 ? B : A) : 0);
   switch (op) {
     case NB_OP_IDENTITY: case NB_OP_NEG: case NB_OP_DEG2RAD: case NB_OP_RAD2DEG: return 0;
     case NB_OP_SIGN: case NB_OP_STEP: case NB_OP_FLOOR: case NB_OP_CEIL: case NB_OP_ROUND: case NB_OP_TRUNC: return 0;
@@ -171,9 +193,26 @@ __device__ __noinline__ double nb_polygamma(double x) {
 // value of a catalogue op: full table, inlined (folds to one expression when `op` is a compile-time
 // constant, as in the lean kernels)
 template <typename T>
+__device__ __forceinline__ T nb_eval_inner(int bin, T a, T b) {   // the binary half of a fused primitive
+  return bin == NB_OP_ADD ? a + b : bin == NB_OP_SUB ? a - b : a * b;
+}
+template <typename T>
+__device__ __forceinline__ T nb_eval_outer(int un, T t) {         // the unary half
+  switch (un) {
+    case NB_OP_TANH: return tanh(t);
+    case NB_OP_EXP: return exp(t);
+    case NB_OP_LOG: return log(t);
+    case NB_OP_LOGISTIC: return T(1) / (T(1) + exp(-t));
+    case NB_OP_SQRT: return sqrt(t);
+    default: return t * t;   // NB_OP_ABS2
+  }
+}
+
+template <typename T>
 __device__ __forceinline__ T nb_eval_full(int op, T a, T b) {
   const T one = T(1);
   const T d2r = T(NB_D2R), r2d = T(NB_R2D);
+  if (nb_is_fop(op)) return nb_eval_outer<T>(nb_fop_un(op), nb_eval_inner<T>(nb_fop_bin(op), a, b));
   switch (op) {
     case NB_OP_IDENTITY: return a;
     case NB_OP_NEG: return -a;
@@ -416,6 +455,25 @@ __device__ __forceinline__ T nb_dunary(int op, T a, T y) {
 template <typename T>
 __device__ __forceinline__ T nb_dbinary(int op, int wrt, T a, T b, T y) {
   const T one = T(1);
+  if (nb_is_fop(op)) {
+    const int un = nb_fop_un(op), bin = nb_fop_bin(op);
+    T fp;   // f'(t), t = bin(a, b)
+    if (nb_fop_y(op)) {
+      fp = un == NB_OP_TANH ? one - y * y : un == NB_OP_EXP ? y : un == NB_OP_LOGISTIC ? y * (one - y) : T(0.5) / y;
+    } else {
+      const T t = nb_eval_inner<T>(bin, a, b);
+      switch (un) {
+        case NB_OP_TANH: { const T w = tanh(t); fp = one - w * w; break; }
+        case NB_OP_EXP: fp = exp(t); break;
+        case NB_OP_LOG: fp = one / t; break;
+        case NB_OP_LOGISTIC: { const T w = one / (one + exp(-t)); fp = w * (one - w); break; }
+        case NB_OP_SQRT: fp = T(0.5) / sqrt(t); break;
+        default: fp = T(2) * t; break;
+      }
+    }
+    const T inner = bin == NB_OP_MUL ? (wrt == 0 ? b : a) : (bin == NB_OP_SUB && wrt == 1 ? -one : one);
+    return fp * inner;
+  }
   switch (op) {
     case NB_OP_ADD: return one;
     case NB_OP_SUB: return wrt == 0 ? one : -one;

@@ -241,7 +241,7 @@ def defer_product(tA, tB, alpha, A, B, m, n, k, math=None):
 
 def _pending(x, kinds=(0,), max_stage=0):
     d = getattr(x, "pending", None) if isinstance(x, DevArray) else None
-    if d is None or d.done or d.kind not in kinds or d.stage > max_stage or d.rowsum_ref is not None:
+    if not isinstance(d, Deferred) or d.done or d.kind not in kinds or d.stage > max_stage or d.rowsum_ref is not None:
         return None
     return d
 
@@ -291,7 +291,7 @@ def try_pullback_act(prog, ybar, y_saved, operand):
 def try_rowsum(ybar, out, acc):
     """The bias sensitivity ``sum(ȳ, dims=2)`` as a side output of the deferred launch that produces ȳ."""
     d = getattr(ybar, "pending", None) if isinstance(ybar, DevArray) else None
-    if d is None or d.done or d.rowsum_ref is not None or out.pending is not None:
+    if not isinstance(d, Deferred) or d.done or d.rowsum_ref is not None or out.pending is not None:
         return False
     if tuple(out.shape) not in ((d.m,), (d.m, 1)) or d.n == 1:
         return False

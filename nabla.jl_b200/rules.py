@@ -7,7 +7,7 @@ import numbers
 
 import numpy as np
 
-from . import fusion
+from . import ewfusion, fusion
 from . import kernels as K
 from ._lib import OPCODES, DimensionMismatch
 from .core import UNDEF, Node, Primitive, accumulate, as_device, own, unbox
@@ -94,6 +94,8 @@ def _mr_forward(fn, *operands, reduce=False, dims=None, mean=False, same_shape=F
     dtype = dev[0].dtype
     if not reduce:
         out = fusion.try_forward(prog, dev) if ctx.fuse else None  # `.+ bias` / `f.` after a deferred product
+        if out is None:   # small arrays: stay lazy so that the next broadcast / reduction composes with this one
+            out = ewfusion.try_forward(ctx, prog, dev, full, dtype)
         if out is None:
             out = ctx.empty(full, dtype)
             K.bcast_fwd(prog, dev, out)
@@ -101,7 +103,11 @@ def _mr_forward(fn, *operands, reduce=False, dims=None, mean=False, same_shape=F
     else:
         out = ctx.empty(_reduced_shape(full, dims), dtype)
         scale = 1.0 / _denom(full, dims) if mean else 1.0
-        K.bcast_reduce(prog, dev, out, scale=scale)
+        c = ewfusion.try_reduce(ctx, prog, dev, full)   # sum(f, lazy chain): one launch over the chain's leaves
+        if c is not None:
+            K.bcast_reduce(c[0], c[1], out, scale=scale)
+        else:
+            K.bcast_reduce(prog, dev, out, scale=scale)
     return out, (prog, dev, dev_pos, scale, reduce)
 
 
@@ -131,6 +137,10 @@ def _mr_fused(y, ybar, rvs):
         scaled = yb.ctx.empty(yb.shape, yb.dtype)
         K.bcast_reduce(None, [yb], scaled, scale=scale)
         ybar = scaled
+    # adjacent broadcast Branches whose intermediate value was never materialised: ONE fused pullback launch for the
+    # whole chain, straight to the inner Branches' operands (ewfusion.py)
+    if ewfusion.chain_pullback(y, ybar, rvs, own):
+        return
     if reduce and prog.single_op == _ID and len(dev) == 1 and isinstance(y.args[dev_pos[0] + 1], Node) and _LAZY_SUM:
         # plain sum(x; dims) / mean(x; dims): x̄ is ȳ broadcast back up (ChainRules returns it as an
         # InplaceableThunk).  A fresh slot gets the lazy BroadcastView — the consumer's pullback kernel reads ȳ
@@ -142,6 +152,8 @@ def _mr_fused(y, ybar, rvs):
             d_tape[xid - 1] = BroadcastView(base, dev[0].shape)
             return
     y_saved = None if reduce else y.val
+    if y_saved is not None and ewfusion.lazy_of(y_saved) is not None:
+        y_saved = None     # the value itself was never materialised (its consumers were fused): the kernel re-evaluates f
     kdev = dev
     if any(d.pending is not None for d in dev) or (y_saved is not None and y_saved.pending is not None):
         # hand the kernel only what the partials read: a deferred forward value (W*X, W*X .+ b) that nothing

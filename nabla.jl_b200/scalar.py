@@ -277,6 +277,11 @@ def _compile_scalar(f, nargs, const_args):
         root = Sym("op", op=f.name, a=syms[0], b=syms[1] if nargs == 2 else None)
     else:
         root = Sym.lift(f(*syms))
+    return linearize(root, k, getattr(f, "__name__", "f"))
+
+
+def linearize(root, k, name="f"):
+    """Expression DAG over ``k`` operands -> Program (peephole rewrites, structural CSE, catalogue / size checks)."""
     root = _simplify(root)
     ops, ia, ib, consts = [], [], [], []
     memo = {}
@@ -318,7 +323,26 @@ def _compile_scalar(f, nargs, const_args):
         else:
             ops.append(OPCODES["add"]); ia.append(r); ib.append(const_index(0.0))
             # a constant function still needs operand 0 to define the shape
-    return Program(k, ops, ia, ib, consts, getattr(f, "__name__", "f"))
+    return Program(k, ops, ia, ib, consts, name)
+
+
+_OPNAME = {v: n for n, v in OPCODES.items() if not n.endswith(("_end", "_begin"))}
+
+
+def symbolic(prog, syms):
+    """The value of ``prog`` on symbolic operands ``syms`` (one Sym per program operand) as an expression DAG — used to
+    compose the programs of adjacent broadcast Branches into one (ewfusion.py)."""
+    vals = list(syms)
+    if len(vals) != prog.nargs:
+        raise ValueError("symbolic: operand count mismatch")
+
+    def slot(i):
+        return vals[i] if i >= 0 else Sym("const", value=float(prog.consts[-i - 1]))
+    for op, a, b in zip(prog.ops, prog.a, prog.b):
+        name = _OPNAME[op]
+        binary = OPCODES["add"] <= op < OPCODES["binary_end"]
+        vals.append(Sym("op", op=name, a=slot(a), b=slot(b) if binary else None))
+    return vals[-1] if prog.ops else vals[0]
 
 
 def _make_catalogue():

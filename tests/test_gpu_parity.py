@@ -1362,3 +1362,130 @@ def test_value_dependent_lambdas(nb, orc, dtype):
     check_case(nb, orc, lambda ns, a: ns.broadcast(comp(ns), a), [x], rng.standard_normal((37, 29)), dtype, sc)
     # inside a reduction
     check_case(nb, orc, lambda ns, a: ns.sum(leaky(ns), a), [x], None, dtype, sc)
+
+
+# ---------------------------------------------------------------------------------------------
+# tape-level fusion of adjacent broadcast Branches (ewfusion.py)
+# ---------------------------------------------------------------------------------------------
+def _with_ew_fusion(nb, on, fn):
+    from nabla_jl_b200 import ewfusion
+    old = ewfusion.ENABLED
+    ewfusion.ENABLED = on
+    try:
+        return fn()
+    finally:
+        ewfusion.ENABLED = old
+
+
+def test_adjacent_broadcast_fusion_matches_unfused_and_oracle(nb, orc, ctx):
+    """The same tapes with and without the fusion: equal to rounding (the composed program evaluates the same
+    primitives; only the order in which a slot receives its contributions can change), both equal to the oracle —
+    chains, a value with two consumers (must be materialised), the same Node twice, broadcast operands, reductions over
+    chains, array seeds, pre-filled slots."""
+    rng = np.random.default_rng(31)
+    A, Bm = rng.standard_normal((23, 17)), rng.standard_normal((23, 17))
+    bcol, brow = rng.standard_normal(23), rng.standard_normal((1, 17))
+    Y = (rng.random((23, 17)) > 0.5) * 1.0
+
+    def chain(ns, a, b, c):          # three adjacent broadcasts + a reduction over the chain
+        t = ns.broadcast(ns.tanh, ns.broadcast(ns.add, a, c))
+        u = ns.broadcast(ns.mul, t, ns.broadcast(ns.exp, b))
+        return ns.sum(ns.broadcast(ns.log, ns.broadcast(ns.add, ns.broadcast(ns.abs2, u), 1e-3)))
+
+    def two_consumers(ns, a, b, c):  # `t` feeds two Branches: it gets its own sensitivity slot
+        t = ns.broadcast(ns.tanh, ns.broadcast(ns.add, a, c))
+        return ns.sum(ns.broadcast(ns.mul, t, b)) + ns.sum(ns.abs2, t)
+
+    def same_twice(ns, a, b, c):     # σ .* σ (examples/vae.jl:85) inside a chain
+        s = ns.broadcast(ns.exp, ns.broadcast(ns.mul, a, 0.3))
+        return ns.sum(ns.broadcast(ns.log, ns.broadcast(ns.mul, s, s))) + ns.sum(ns.broadcast(ns.add, b, c))
+
+    def loglik(ns, a, b, c):         # the log-likelihood chain of examples/mlp.jl:68-73
+        f = ns.broadcast(lambda x: 1.0 / (1.0 + ns.exp(-x)), ns.broadcast(ns.add, a, c))
+        p = ns.broadcast(ns.div, f, ns.sum(f, dims=1))
+        t1 = ns.broadcast(ns.mul, Y, ns.broadcast(ns.log, ns.broadcast(ns.add, p, 1e-15)))
+        t2 = ns.broadcast(ns.mul, ns.broadcast(ns.sub, 1.0, Y), ns.broadcast(ns.log, ns.broadcast(ns.sub, 1.0 + 1e-15, p)))
+        return ns.sum(ns.broadcast(ns.add, t1, t2)) + 0.0 * ns.sum(b)
+
+    def array_out(ns, a, b, c):      # array-valued result with an explicit seed, unbroadcast over rows
+        return ns.broadcast(ns.mul, ns.broadcast(ns.tanh, ns.broadcast(ns.add, a, brow)), ns.broadcast(ns.add, b, c))
+
+    for build, ybar in ((chain, None), (two_consumers, None), (same_twice, None), (loglik, None),
+                        (array_out, rng.standard_normal((23, 17)))):
+        xs = [A, Bm, bcol]
+        for on in (True, False):
+            _with_ew_fusion(nb, on, lambda: check_case(nb, orc, build, xs, ybar))
+        fused = _with_ew_fusion(nb, True, lambda: run_both(nb, orc, build, xs, ybar))
+        plain = _with_ew_fusion(nb, False, lambda: run_both(nb, orc, build, xs, ybar))
+        np.testing.assert_allclose(fused[0], plain[0], rtol=1e-13)
+        for a, b in zip(fused[1], plain[1]):
+            np.testing.assert_allclose(a, b, rtol=1e-12, atol=1e-13 * np.max(np.abs(b)))
+
+
+def test_adjacent_broadcast_fusion_cuts_launches_of_c1_and_c4(nb, orc, ctx):
+    """C1 (examples/mlp.jl) and C4 (examples/vae.jl) at a small batch: fewer kernel launches per evaluation with the
+    fusion, gradients equal to the unfused sweep and to the oracle; also inside a CUDA-graph capture."""
+    import nabla_jl_b200.workloads as wl
+    W, b, X, Y = wl.mlp_inputs((784, 500, 300, 10), 256, np.float64, seed=0)
+    Xd, Yd = ctx.asarray(X), ctx.asarray(Y)
+    vp, VX, noise = wl.vae_inputs(B=256, seed=3)
+    VXd, Nd = ctx.asarray(VX), ctx.asarray(noise)
+    for name, obj, oobj, params in (
+            ("mlp", wl.mlp_objective(nb, Xd, Yd, 1e-3, 3), wl.mlp_objective(orc, X, Y, 1e-3, 3), [*W, *b]),
+            ("vae", wl.vae_objective(nb, VXd, Nd, 1e-3, 60000 / 256, 10), wl.vae_objective(orc, VX, noise, 1e-3, 60000 / 256, 10),
+             list(vp))):
+        dparams = [ctx.asarray(p) for p in params]
+        ref = oobj and orc.nabla(oobj)(*params)
+        counts, grads = {}, {}
+        for on in (False, True):
+            def run():
+                nb.nabla(obj)(*dparams)                      # warm: programs compiled, pool sized
+                n0 = ctx.stats()["kernel_launches"]
+                g = nb.nabla(obj)(*dparams)
+                g = [x.numpy() for x in g]
+                return ctx.stats()["kernel_launches"] - n0, g
+            counts[on], grads[on] = _with_ew_fusion(nb, on, run)
+        assert counts[True] < 0.8 * counts[False], f"{name}: {counts}"
+        for a, r, o in zip(grads[True], grads[False], ref):
+            np.testing.assert_allclose(a, r, rtol=1e-11, atol=1e-12 * np.max(np.abs(r)))
+            close(a, o)
+        cap = _with_ew_fusion(nb, True, lambda: nb.CapturedGradient(obj, dparams, ctx))
+        _, g = cap()
+        ctx.sync()
+        for a, o in zip(g, ref):
+            close(a.numpy(), o)
+        cap.close()
+
+
+@pytest.mark.parametrize("dtype", [np.float64, np.float32])
+def test_fused_two_op_primitives(nb, orc, dtype):
+    """un(bin(a, b)) lambdas — `tanh.(A .+ b)`, `log.(f .+ eps)`, `exp.(a .* b)` … — run as one fused primitive of the
+    single-primitive kernels (csrc/ops.cuh nb_fop): every supported pair, array / column / scalar-constant second
+    operands (flat, tall and per-column mappings), large enough for the vectorised kernels, fresh and pre-filled
+    slots, against the oracle."""
+    rng = np.random.default_rng(41)
+    m, n = 256, 96
+    un = {"tanh": (-2, 2), "exp": (-2, 2), "log": (0.5, 3), "logistic": (-3, 3), "sqrt": (0.5, 3), "abs2": (-2, 2)}
+    for uname, (lo, hi) in un.items():
+        for bname in ("add", "sub", "mul"):
+            # operands chosen so that bin(a, b) lies in the domain of un
+            if bname == "add":
+                a, b = rng.uniform(lo / 2, hi / 2, (m, n)), rng.uniform(lo / 2, hi / 2, (m, n))
+            elif bname == "sub":
+                a, b = rng.uniform(hi * 0.75, hi, (m, n)), rng.uniform(0, hi * 0.75 - max(lo, 0), (m, n))
+                if lo < 0:
+                    a, b = rng.uniform(lo / 2, hi / 2, (m, n)), rng.uniform(lo / 2, hi / 2, (m, n))
+            else:
+                s = np.sqrt(hi)
+                a, b = rng.uniform(np.sqrt(max(lo, 0.25)), s, (m, n)), rng.uniform(np.sqrt(max(lo, 0.25)), s, (m, n))
+            f = lambda ns, u=uname, bn=bname: (lambda x, y: getattr(ns, u)(getattr(ns, bn)(x, y)))
+            ybar = rng.standard_normal((m, n))
+            sc = 4.0 if dtype == np.float32 else 1.0
+            check_case(nb, orc, lambda ns, x, y: ns.broadcast(f(ns), x, y), [a, b], ybar, dtype, sc)
+            check_case(nb, orc, lambda ns, x, y: ns.broadcast(f(ns), x, y), [a, b[:, 0]], ybar, dtype, sc)      # bias column
+            check_case(nb, orc, lambda ns, x, y: ns.broadcast(f(ns), x, y), [a, b[:1, :]], ybar, dtype, sc)    # row vector
+            c = float(b[0, 0])
+            check_case(nb, orc, lambda ns, x: ns.broadcast(lambda t: getattr(ns, uname)(getattr(ns, bname)(t, c)), x),
+                       [a], ybar, dtype, sc)
+            check_case(nb, orc, lambda ns, x, y: ns.sum(f(ns), x) if False else ns.sum(ns.broadcast(f(ns), x, y)), [a, b], None,
+                       dtype, sc)
