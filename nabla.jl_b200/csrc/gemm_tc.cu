@@ -65,6 +65,7 @@ constexpr int BM = 128;
 constexpr int NTHREADS = 384;
 constexpr int EPI_WARP0 = 4;
 constexpr int EPI_THREADS = 256;
+constexpr int EPI_WARPS = EPI_THREADS / 32;  // the accumulator is released by ONE arrive per warp (see the fold loops)
 constexpr int REGS_WG0 = 80, REGS_EPI = 208;  // 128*80 + 256*208 <= 384*168
 
 // Operand kinds.  Every staged row is 128 bytes (one swizzle row), so tile byte sizes are kind-independent.
@@ -703,7 +704,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_THREADS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], EPI_WARPS); }
     for (int q = 0; q < SCHED_SLOTS; ++q) { mbar_init(&sfull[q], 1); mbar_init(&sempty[q], 1 + EPI_THREADS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -870,7 +871,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
           tc_fence_after();
           a64.fold(tmem_base + (uint32_t)(a * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16), g.tab_scale[c], c == 0);
           tc_fence_before();
-          mbar_arrive(&tempty[a]);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tempty[a]);
           if (++a == 2) { a = 0; aph ^= 1; }
         }
         a64.store(g, (int64_t)tm * BM + q * 32 + lane, (int64_t)tn * BN + half * (BN / 2));
@@ -881,7 +883,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
         tc_fence_after();
         acc.fold(tmem_base + (uint32_t)(a * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16), kb0 == 0);
         tc_fence_before();
-        mbar_arrive(&tempty[a]);  // the accumulator is free as soon as it is in registers
+        // one arrive per WARP: with short K chunks the fold is a latency chain between two MMA chunks, and 256
+        // (pair kernel: 512, half of them remote) serialised arrives on one mbarrier were a visible part of it
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty[a]);  // the accumulator is free as soon as it is in registers
         if (++a == 2) { a = 0; aph ^= 1; }
       }
       acc.store(g, (int64_t)tm * BM + q * 32 + lane, (int64_t)tn * BN + half * (BN / 2), tn * 2 + half, lane);
@@ -906,7 +911,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
 //   full[s]   (leader)      : both producers' TMA bytes (cta_group::2 loads signal the leader's barrier)
 //   empty[s]  (both CTAs)   : tcgen05.commit multicast to the pair
 //   tfull[a]  (both CTAs)   : tcgen05.commit multicast — each CTA drains its own TMEM half
-//   tempty[a] (leader)      : 256 epilogue threads (the peer's arrive remotely)
+//   tempty[a] (leader)      : one arrive per epilogue warp of BOTH CTAs (the peer's arrive remotely)
 // =================================================================================================
 constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;  // clears the CTA-rank bit of a shared::cluster address
 
@@ -1040,7 +1045,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_THREADS); }
+    for (int a = 0; a < 2; ++a) { mbar_init(&tfull[a], 1); mbar_init(&tempty[a], 2 * EPI_WARPS); }
     // consumers of a slot: leader MMA thread + peer producer + the epilogue threads of both CTAs
     for (int q = 0; q < SCHED_SLOTS; ++q) { mbar_init(&sfull[q], 1); mbar_init(&sempty[q], 2 + 2 * EPI_THREADS); }
     mbar_init(sempty + SCHED_SLOTS + 4, 1);  // dbg_bar
@@ -1206,7 +1211,8 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
         tc_fence_after();
         acc.fold(tmem_base + (uint32_t)(a * BN + half * (BN / 2)) + ((uint32_t)(q * 32) << 16), kb0 == 0);
         tc_fence_before();
-        mbar_arrive_cta(&tempty[a], 0);  // the leader's barrier collects both CTAs' epilogues
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cta(&tempty[a], 0);  // the leader's barrier collects both CTAs' epilogue warps
         if (++a == 2) { a = 0; aph ^= 1; }
       }
       acc.store(g, (int64_t)tm * 256 + (int64_t)rank * 128 + q * 32 + lane, (int64_t)tn * BN + half * (BN / 2),

@@ -1478,14 +1478,16 @@ def test_fused_two_op_primitives(nb, orc, dtype):
             else:
                 s = np.sqrt(hi)
                 a, b = rng.uniform(np.sqrt(max(lo, 0.25)), s, (m, n)), rng.uniform(np.sqrt(max(lo, 0.25)), s, (m, n))
-            f = lambda ns, u=uname, bn=bname: (lambda x, y: getattr(ns, u)(getattr(ns, bn)(x, y)))
+            def outer(ns, t, u=uname):   # (the oracle has no `logistic` primitive: examples/mlp.jl:42 writes it out)
+                return 1.0 / (1.0 + ns.exp(-t)) if u == "logistic" else getattr(ns, u)(t)
+            f = lambda ns, bn=bname: (lambda x, y: outer(ns, getattr(ns, bn)(x, y)))
             ybar = rng.standard_normal((m, n))
             sc = 4.0 if dtype == np.float32 else 1.0
             check_case(nb, orc, lambda ns, x, y: ns.broadcast(f(ns), x, y), [a, b], ybar, dtype, sc)
             check_case(nb, orc, lambda ns, x, y: ns.broadcast(f(ns), x, y), [a, b[:, 0]], ybar, dtype, sc)      # bias column
             check_case(nb, orc, lambda ns, x, y: ns.broadcast(f(ns), x, y), [a, b[:1, :]], ybar, dtype, sc)    # row vector
             c = float(b[0, 0])
-            check_case(nb, orc, lambda ns, x: ns.broadcast(lambda t: getattr(ns, uname)(getattr(ns, bname)(t, c)), x),
+            check_case(nb, orc, lambda ns, x: ns.broadcast(lambda t: outer(ns, getattr(ns, bname)(t, c)), x),
                        [a], ybar, dtype, sc)
             check_case(nb, orc, lambda ns, x, y: ns.sum(f(ns), x) if False else ns.sum(ns.broadcast(f(ns), x, y)), [a, b], None,
                        dtype, sc)
