@@ -91,7 +91,10 @@ class Leaf(Node):
     """``Leaf(tape, val)`` (core.jl:48-57).  Host values are moved to HBM once, here."""
 
     def __init__(self, tape, val, ctx=None):
-        self.val = as_device(val, ctx)
+        # the reference's Leaf wraps ANY value (core.jl:48-57); only arrays and real numbers move to HBM, anything
+        # else (a callable, a tuple, a string flag) is kept as it is and simply never receives a sensitivity
+        numeric = isinstance(val, (DevArray, BroadcastView, np.ndarray, numbers.Real, list)) and not isinstance(val, bool)
+        self.val = as_device(val, ctx) if numeric else val
         self.tape = tape
         self.pos = len(tape) + 1
         tape.push(self)
@@ -121,6 +124,17 @@ class Branch(Node):
 
     def __repr__(self):
         return f"Branch{{{self.val!r}}} f={self.f.name}"
+
+
+class Output(Node):
+    """The live output Node ``∇(f; get_output=true)`` returns: same value and position as the Node on the tape, and
+    the only strong reference to that tape (dropping it releases every forward value at once)."""
+
+    def __init__(self, y, tape):
+        self.val, self.pos, self.tape = y.val, y.pos, tape
+
+    def __repr__(self):
+        return f"Output{{{self.val!r}}}"
 
 
 class Arg:
@@ -161,6 +175,8 @@ def oneslike(x):
 
 def zeroslike(x):
     x = unbox(x)
+    if not isinstance(x, (DevArray, BroadcastView)):
+        return None      # a non-numeric argument (kept as it is by Leaf) has no sensitivity
     return x.ctx.zeros(x.shape, x.dtype)
 
 
@@ -201,6 +217,9 @@ class Primitive:
         if not nodes:
             res = self.forward(*args, **kwargs)
             return res[0] if self.returns_saved else res
+        for nd in nodes[1:]:
+            if nd.tape is not nodes[0].tape:   # the reference "fails silently" here (docs/src/index.md:88): be loud
+                raise ValueError("Nodes of different Tapes in one call: every Leaf of a computation must share one Tape")
         return Branch(self, args, nodes[0].tape, **kwargs)
 
 
@@ -275,6 +294,7 @@ def propagate(fwd_tape, rvs_tape, on_final=None):
 
     ``on_final(leaf_pos, slot)`` (optional, not in the reference) is called as soon as a Leaf's
     sensitivity can no longer change — used to start its allreduce while the sweep continues."""
+    rvs_tape._fwd = fwd_tape      # (rules that look across Branches — ewfusion.py — find the forward tape here)
     finals = {}
     if on_final is not None:
         for leaf_pos, p in last_contribution_positions(fwd_tape, len(rvs_tape)).items():
@@ -335,8 +355,18 @@ def nabla(f_or_node, ybar=None, *, get_output=False):
         # counting return every forward value and intermediate sensitivity to the device pool as
         # soon as this call returns, instead of whenever Python's cyclic collector runs (which made
         # successive evaluations overlap in memory and hit cudaMalloc).  `y` stays a valid Node.
-        t.tape.clear()
-        return (y, out) if get_output else out
+        # Tape -> Node -> Tape is a reference cycle: it is broken here so that reference counting returns every forward
+        # value and intermediate sensitivity to the device pool as soon as the caller lets go, instead of whenever
+        # Python's cyclic collector runs (successive evaluations would overlap in memory and hit cudaMalloc).  With
+        # get_output the caller receives y as a LIVE Node (core.jl:214-229: it can be passed to ∇(y, ȳ) again): a
+        # detached twin of y that owns the tape, while the nodes on the tape drop their back references.
+        if not get_output or not isinstance(y, Node):
+            t.tape.clear()
+            return (y, out) if get_output else out
+        for node in t.tape:
+            node.tape = None
+        yo = Output(y, t)
+        return yo, out
 
     return gradient_fn
 

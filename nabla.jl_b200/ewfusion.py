@@ -128,7 +128,8 @@ def _consumers(y, rvs):
     if c is None:
         from .core import Branch, Node
         c = {}
-        for node in y.tape.tape[:len(rvs)]:
+        fwd = getattr(rvs, "_fwd", None) or y.tape
+        for node in fwd.tape[:len(rvs)]:
             if isinstance(node, Branch):
                 for a in node.args:
                     if isinstance(a, Node):
