@@ -152,15 +152,17 @@ def _mr_fused(y, ybar, rvs):
             d_tape[xid - 1] = BroadcastView(base, dev[0].shape)
             return
     y_saved = None if reduce else y.val
+    y_dropped = False
     if y_saved is not None and ewfusion.lazy_of(y_saved) is not None:
         y_saved = None     # the value itself was never materialised (its consumers were fused): the kernel re-evaluates f
+        y_dropped = True   # ... from the operands, so every operand is read
     kdev = dev
     if any(d.pending is not None for d in dev) or (y_saved is not None and y_saved.pending is not None):
         # hand the kernel only what the partials read: a deferred forward value (W*X, W*X .+ b) that nothing
         # reads is never launched
         wanted = [k for k, j in enumerate(dev_pos) if isinstance(y.args[j + 1], Node)]
         reads = fusion.pullback_reads(prog, wanted)
-        if reads is not None:
+        if reads is not None and not (y_dropped and reads[1]):
             read_ops, read_y = reads
             if not read_y:
                 y_saved = None
