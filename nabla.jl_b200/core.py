@@ -126,12 +126,15 @@ class Branch(Node):
         return f"Branch{{{self.val!r}}} f={self.f.name}"
 
 
-class Output(Node):
-    """The live output Node ``∇(f; get_output=true)`` returns: same value and position as the Node on the tape, and
-    the only strong reference to that tape (dropping it releases every forward value at once)."""
+class Output(Branch):
+    """The live output Node ``∇(f; get_output=true)`` returns (a Branch, as in the reference: test/core.jl:171-173): same
+    value, function, arguments and position as the Branch on the tape, and the only strong reference to that tape
+    (dropping it releases every forward value at once)."""
 
-    def __init__(self, y, tape):
+    def __init__(self, y, tape):   # (not Branch.__init__: nothing is evaluated or recorded)
         self.val, self.pos, self.tape = y.val, y.pos, tape
+        self.f, self.args, self.kwargs = getattr(y, "f", None), getattr(y, "args", ()), getattr(y, "kwargs", {})
+        self.saved = getattr(y, "saved", None)
 
     def __repr__(self):
         return f"Output{{{self.val!r}}}"

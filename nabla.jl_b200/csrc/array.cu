@@ -40,6 +40,7 @@ extern "C" {
 
 int32_t nb_copy2d(nb_ctx* ctx, int64_t rows, int64_t cols, const void* src, int64_t src_off, int64_t ld_src,
                   void* dst, int64_t dst_off, int64_t ld_dst, int32_t dtype, int32_t accumulate) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, rows >= 0 && cols >= 0 && src_off >= 0 && dst_off >= 0, NB_ERR_INVALID, "nb_copy2d: negative extent");
   NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
@@ -63,6 +64,7 @@ int32_t nb_copy2d(nb_ctx* ctx, int64_t rows, int64_t cols, const void* src, int6
 }
 
 int32_t nb_gather(nb_ctx* ctx, int64_t n, const void* src, const int64_t* idx_dev, void* dst, int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && (n == 0 || (src && idx_dev && dst)), NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
   if (n == 0) return NB_OK;
@@ -76,6 +78,7 @@ int32_t nb_gather(nb_ctx* ctx, int64_t n, const void* src, const int64_t* idx_de
 }
 
 int32_t nb_scatter_add(nb_ctx* ctx, int64_t n, const void* src, const int64_t* idx_dev, void* dst, int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && (n == 0 || (src && idx_dev && dst)), NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
   if (n == 0) return NB_OK;

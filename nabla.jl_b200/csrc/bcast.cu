@@ -1183,6 +1183,7 @@ int32_t nb_prog_destroy(nb_prog* p) {
 
 int32_t nb_bcast_fwd(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const nb_tensor* args,
                      const nb_tensor* out) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && args && out, NB_ERR_INVALID, "NULL argument");
   Call C{};
   C.prog = prog; C.nargs = nargs; C.args = args; C.pullback = false; C.nout = 1;
@@ -1199,6 +1200,7 @@ int32_t nb_bcast_fwd(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const nb_t
 
 int32_t nb_bcast_reduce(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const nb_tensor* args,
                         double scale, const nb_tensor* out, int32_t accumulate) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && args && out, NB_ERR_INVALID, "NULL argument");
   Call C{};
   C.prog = prog; C.nargs = nargs; C.args = args; C.pullback = false; C.nout = 1;
@@ -1209,6 +1211,7 @@ int32_t nb_bcast_reduce(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const n
 int32_t nb_bcast_pullback(nb_ctx* ctx, const nb_prog* prog, const nb_tensor* ybar,
                           const nb_tensor* y_saved, int32_t nargs, const nb_tensor* args,
                           uint32_t want_mask, const nb_tensor* outs, uint32_t accumulate_mask) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && args && outs, NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, nargs >= 1 && nargs <= NB_MAX_ARGS, NB_ERR_INVALID, "bad operand count");
   Call C{};
@@ -1239,6 +1242,7 @@ int32_t nb_bcast_pullback(nb_ctx* ctx, const nb_prog* prog, const nb_tensor* yba
 }
 
 int32_t nb_fill(nb_ctx* ctx, void* dst, int32_t dtype, uint64_t count, double value) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && (dst || !count), NB_ERR_INVALID, "NULL argument");
   if (!count) return NB_OK;
   nb_note_write(ctx, dst);
@@ -1255,6 +1259,7 @@ int32_t nb_fill(nb_ctx* ctx, void* dst, int32_t dtype, uint64_t count, double va
 // 'T': out[j] = sum_i A[i,j]*x[i] is the KEEP_COLS pattern (k_wcol): both stream A once at HBM rate.
 int32_t nb_gemv(nb_ctx* ctx, char tA, int64_t m, int64_t n, double alpha, const void* A,
                 int64_t lda, const void* x, double beta, void* y, int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && A && x && y, NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, lda >= m, NB_ERR_SHAPE, "nb_gemv: leading dimension too small (DimensionMismatch)");
   const bool tr = tA == 'T' || tA == 't' || tA == 'C' || tA == 'c';
@@ -1288,6 +1293,7 @@ int32_t nb_gemv(nb_ctx* ctx, char tA, int64_t m, int64_t n, double alpha, const 
 // A = alpha*x*y' + beta*A (outer product): the elementwise pattern with two broadcast operands
 int32_t nb_ger(nb_ctx* ctx, int64_t m, int64_t n, double alpha, const void* x, const void* y,
                double beta, void* A, int64_t lda, int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && A && x && y, NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, lda >= m, NB_ERR_SHAPE, "nb_ger: leading dimension too small (DimensionMismatch)");
   if (m > 0 && n > 0) {  // k = 1 product: the small-K kernel of gemm_skinny.cu (any lda, any beta)

@@ -66,6 +66,7 @@ int32_t nb_comm_unique_id(uint8_t id_out[128]) {
 }
 
 int32_t nb_comm_init(nb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id_in[128]) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && id_in, NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, nranks >= 1 && rank >= 0 && rank < nranks, NB_ERR_INVALID, "bad rank/nranks");
   NB_REQUIRE(ctx, api().ok, NB_ERR_COMM, "libnccl.so.2 could not be loaded");
@@ -84,6 +85,7 @@ int32_t nb_comm_init(nb_ctx* ctx, int32_t nranks, int32_t rank, const uint8_t id
 
 int32_t nb_allreduce_sum(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const int64_t* counts,
                          int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && (n_bufs == 0 || (bufs && counts)), NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
   if (ctx->nranks == 1 && !ctx->nccl_comm) return NB_OK;  // single rank: the sum is the identity
@@ -128,6 +130,7 @@ static int32_t reduce_on(nb_ctx* ctx, cudaStream_t st, int32_t n_bufs, void* con
 
 int32_t nb_allreduce_sum_async(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, const int64_t* counts,
                                int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && (n_bufs == 0 || (bufs && counts)), NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
   if (ctx->nranks == 1 && !ctx->nccl_comm) return NB_OK;
@@ -146,6 +149,7 @@ int32_t nb_allreduce_sum_async(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, c
 }
 
 int32_t nb_comm_join(nb_ctx* ctx) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   if (!ctx->comm_pending) return NB_OK;
   NB_CUDA_OK(ctx, cudaEventRecord(ctx->ev_join, ctx->comm_stream));

@@ -65,6 +65,14 @@ static inline int32_t nb_fail(nb_ctx* ctx, int32_t code, const std::string& msg)
   return code;
 }
 
+// Every entry point makes the context's device current for the calling thread first: kernel launches, cudaMalloc and
+// cudaFuncSetAttribute act on the CURRENT device, one host thread may drive contexts on several GPUs, and other
+// libraries in the process (the host's own CUDA code) may have switched devices in between.  cudaSetDevice to the
+// device that is already current is a thread-local compare inside the runtime.
+static inline void nb_enter(nb_ctx* ctx) {
+  if (ctx) cudaSetDevice(ctx->device);
+}
+
 #define NB_CUDA_OK(ctx, expr)                                                            \
   do {                                                                                   \
     cudaError_t _e = (expr);                                                             \

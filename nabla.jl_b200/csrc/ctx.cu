@@ -29,6 +29,7 @@ static void trim_locked(nb_ctx* ctx) {
 }
 
 int32_t nb_pool_alloc(nb_ctx* ctx, size_t nbytes, void** out) {
+  nb_enter(ctx);
   size_t cls = size_class(nbytes ? nbytes : 1);
   std::lock_guard<std::mutex> lk(ctx->mu);
   void* p = nullptr;
@@ -187,6 +188,7 @@ int32_t nb_sweep_begin(nb_ctx* ctx) {
 }
 
 int32_t nb_sync(nb_ctx* ctx) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return NB_OK;
@@ -235,6 +237,7 @@ int32_t nb_refcount(nb_ctx* ctx, void* buf, int32_t* out) {
 }
 
 int32_t nb_h2d(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   if (!nbytes) return NB_OK;
   nb_note_write(ctx, dst);
@@ -244,6 +247,7 @@ int32_t nb_h2d(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
 }
 
 int32_t nb_d2h_async(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   if (!nbytes) return NB_OK;
   NB_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyDeviceToHost, ctx->stream));
@@ -259,6 +263,7 @@ int32_t nb_d2h(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
 }
 
 int32_t nb_d2d(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   if (!nbytes) return NB_OK;
   nb_note_write(ctx, dst);
@@ -286,6 +291,7 @@ int32_t nb_host_free(void* p) {
 
 // ---- graphs ---------------------------------------------------------------------------------
 int32_t nb_graph_begin(nb_ctx* ctx) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, !ctx->capturing, NB_ERR_INVALID, "nb_graph_begin: already capturing");
   NB_CUDA_OK(ctx, cudaSetDevice(ctx->device));
@@ -300,6 +306,7 @@ int32_t nb_graph_begin(nb_ctx* ctx) {
 }
 
 int32_t nb_graph_end(nb_ctx* ctx, nb_graph** out) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && out, NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, ctx->capturing, NB_ERR_INVALID, "nb_graph_end: not capturing");
   nb_split_cache_clear(ctx);
@@ -331,6 +338,7 @@ int32_t nb_graph_end(nb_ctx* ctx, nb_graph** out) {
 }
 
 int32_t nb_graph_launch(nb_ctx* ctx, nb_graph* g) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && g && g->exec, NB_ERR_INVALID, "NULL argument");
   nb_split_cache_clear(ctx);
   NB_CUDA_OK(ctx, cudaGraphLaunch(g->exec, ctx->stream));
@@ -372,6 +380,7 @@ int32_t nb_event_create(void** out) {
 }
 
 int32_t nb_event_record(nb_ctx* ctx, void* ev) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && ev, NB_ERR_INVALID, "NULL argument");
   NB_CUDA_OK(ctx, cudaEventRecord((cudaEvent_t)ev, ctx->stream));
   return NB_OK;

@@ -138,6 +138,7 @@ extern "C" {
 int32_t nb_gemm(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k, double alpha,
                 const void* A, int64_t lda, const void* B, int64_t ldb, double beta, void* C,
                 int64_t ldc, int32_t dtype, int32_t math_mode) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, (is_t(tAc) || is_n(tAc)) && (is_t(tBc) || is_n(tBc)), NB_ERR_INVALID,
              "nb_gemm: transpose flags must be 'N', 'T' or 'C'");
@@ -185,6 +186,7 @@ int32_t nb_gemm(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k
 int32_t nb_gemm_fused(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k, double alpha,
                       const void* A, int64_t lda, const void* B, int64_t ldb, void* C, int64_t ldc,
                       int32_t dtype, int32_t math_mode, const nb_gemm_epilogue* epi) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, (is_t(tAc) || is_n(tAc)) && (is_t(tBc) || is_n(tBc)), NB_ERR_INVALID,
              "nb_gemm_fused: transpose flags must be 'N', 'T' or 'C'");
@@ -219,6 +221,7 @@ int32_t nb_op_partial_needs(int32_t op, int32_t wrt) { return nb_partial_needs(o
 
 int32_t nb_transpose(nb_ctx* ctx, int64_t m, int64_t n, const void* in, int64_t ld_in, void* out,
                      int64_t ld_out, int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx && (in || !(m * n)) && (out || !(m * n)), NB_ERR_INVALID, "NULL argument");
   NB_REQUIRE(ctx, ld_in >= m && ld_out >= n, NB_ERR_SHAPE, "nb_transpose: leading dimension too small");
   if (m == 0 || n == 0) return NB_OK;

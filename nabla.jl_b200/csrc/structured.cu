@@ -91,6 +91,7 @@ extern "C" {
 
 int32_t nb_tri(nb_ctx* ctx, int32_t op, int32_t diag, int64_t n, const void* src, int64_t ld_src, void* dst,
                int64_t ld_dst, int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, op >= 0 && op <= 5 && diag >= 0 && diag <= 2, NB_ERR_INVALID, "nb_tri: bad op/diag");
   NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
@@ -108,6 +109,7 @@ int32_t nb_tri(nb_ctx* ctx, int32_t op, int32_t diag, int64_t n, const void* src
 
 int32_t nb_trsm(nb_ctx* ctx, char side, char ul, char ta, char diag, int64_t m, int64_t n, double alpha,
                 const void* A, int64_t lda, void* B, int64_t ldb, int32_t dtype) {
+  nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, dtype == NB_F32 || dtype == NB_F64, NB_ERR_INVALID, "bad dtype");
   const bool left = side == 'L' || side == 'l', right = side == 'R' || side == 'r';

@@ -1491,3 +1491,38 @@ def test_fused_two_op_primitives(nb, orc, dtype):
                        [a], ybar, dtype, sc)
             check_case(nb, orc, lambda ns, x, y: ns.sum(f(ns), x) if False else ns.sum(ns.broadcast(f(ns), x, y)), [a, b], None,
                        dtype, sc)
+
+
+def test_two_contexts_on_two_gpus_in_one_process(nb):
+    """One host thread driving a context on each of two GPUs (the Julia host model is one ctx per task): every entry
+    point selects its context's device, and per-device kernel attributes (the > 48 KB shared memory of the GEMM
+    kernels) are set on both.  Skipped on a one-GPU box."""
+    import ctypes as C
+    n = C.c_int32()
+    nb._lib.lib().nb_device_count(C.byref(n))
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    rng = np.random.default_rng(5)
+    ctxs = [nb.Context(device=0), nb.Context(device=1)]
+    try:
+        outs = []
+        for dtype in (np.float32, np.float64):
+            A = rng.standard_normal((1024, 768)).astype(dtype)
+            B = rng.standard_normal((768, 1536)).astype(dtype)
+            res = []
+            for c in ctxs:       # interleave the two devices call by call
+                res.append((c.asarray(A), c.asarray(B), c.empty((1024, 1536), dtype)))
+            from nabla_jl_b200 import kernels as K
+            for (a, b, o) in res:
+                K.gemm("N", "N", 1.0, a, b, 0.0, o, 1024, 1536, 768)
+            for (a, b, o) in res:
+                K.bcast_fwd(nb.compile_scalar(nb.tanh, 1), [o], o)
+            ref = np.tanh(A.astype(np.float64) @ B.astype(np.float64))
+            for (_, _, o) in res:
+                err = np.linalg.norm(o.numpy() - ref) / np.linalg.norm(ref)
+                assert err < (1e-4 if dtype == np.float32 else 1e-12), err
+                outs.append(o)
+        del outs, res
+    finally:
+        for c in ctxs:
+            c.close()
