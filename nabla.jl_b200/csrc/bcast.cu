@@ -1066,7 +1066,7 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
         if ((needs & 4) && !C.ysaved) lean_mode = -1;  // would have to recompute y: general kernel
       }
       if (lean_mode >= 0) {
-        P.load_mask = (P.is_const[0] ? 0 : 1) | (P.is_const[1] ? 0 : 2);
+        P.lean_mask = (P.is_const[0] ? 0 : 1) | (P.is_const[1] ? 0 : 2);
         P.has_y = C.ysaved != nullptr;
       }
     }

@@ -68,14 +68,14 @@ struct LeanPack {
   // recompute flag: the partial needs y but no saved forward value was passed -> needs a and b
   __device__ __forceinline__ void load(const MRP& P, const Extra&, int64_t r, int64_t c) {
     if constexpr ((NEED & 1) != 0) {
-      if (P.load_mask & 1) lean_ld<T, V>(P.arg[0], r, c, a);
+      if (P.lean_mask & 1) lean_ld<T, V>(P.arg[0], r, c, a);
       else {
 #pragma unroll
         for (int i = 0; i < V; ++i) a[i] = T(P.cval[0]);
       }
     }
     if constexpr ((NEED & 2) != 0) {
-      if (P.load_mask & 2) lean_ld<T, V>(P.arg[1], r, c, b);
+      if (P.lean_mask & 2) lean_ld<T, V>(P.arg[1], r, c, b);
       else {
 #pragma unroll
         for (int i = 0; i < V; ++i) b[i] = T(P.cval[1]);

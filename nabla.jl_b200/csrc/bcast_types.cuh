@@ -29,7 +29,11 @@ struct MRP {
   int32_t nout;
   int32_t pullback;
   int32_t op;        // fast path opcode
-  int32_t load_mask; // which operands are actually read
+  int32_t load_mask; // which operands are actually read (general kernels: FastEv)
+  int32_t lean_mask; // lean kernels: bit s = operand s is an array (not a baked-in constant); WHICH operands are read is
+                     // fixed at compile time there (LeanNeeds).  Kept apart from load_mask: a launch that qualifies for
+                     // the lean kernels can still end on a general one (rows <= 32), whose loads must stay limited to
+                     // what the partials read — an operand nothing reads may be a shape-only stand-in (fusion.Shadow)
   int32_t has_ybar, has_y, need_y;
   int32_t vec_ok;    // all contiguous operands 16B-aligned with compatible strides
   int32_t slot_off;  // GenEvS: byte offset of the interpreter's slot storage in dynamic shared memory

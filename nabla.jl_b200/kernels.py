@@ -90,8 +90,15 @@ def bcast_pullback(prog, ybar, y_saved, args, outs, accumulate):
     ybt = C.byref(yb.tensor()) if yb is not None else None
     yst = C.byref(y_saved.tensor()) if y_saved is not None else None
     with _timed(ctx, "bcast_pullback", 0, "B"):
-        check(ctx.L.nb_bcast_pullback(ctx.h, _prog_handle(prog, ctx), ybt, yst, len(args),
-                                      _pack([a.tensor() for a in args]), want, _pack(ts), acc), ctx.h)
+        try:
+            check(ctx.L.nb_bcast_pullback(ctx.h, _prog_handle(prog, ctx), ybt, yst, len(args),
+                                          _pack([a.tensor() for a in args]), want, _pack(ts), acc), ctx.h)
+        except _lib.NablaCudaError as e:   # say WHICH launch failed: program, operand and output shapes
+            e.args = (f"{e.args[0]} [nb_bcast_pullback: ops={getattr(prog, 'ops', None)} a={getattr(prog, 'a', None)} "
+                      f"b={getattr(prog, 'b', None)} args={[(tuple(a.shape), a.dtype.name) for a in args]} "
+                      f"ybar={None if yb is None else tuple(yb.shape)} y_saved={None if y_saved is None else tuple(y_saved.shape)} "
+                      f"outs={[None if o is None else tuple(o.shape) for o in outs]} acc={accumulate}]",)
+            raise
     return outs
 
 
