@@ -633,7 +633,9 @@ def run_gpu(args):
     for _ in range(2):
         step_e2e()
     barrier()
+    l0 = ctx.stats()["kernel_launches"]
     ms_e2e = max_over_ranks(timed_region(ctx, step_e2e, args.steps))
+    launches_e2e = ctx.stats()["kernel_launches"] - l0
     barrier()
     e2e_g = None
     if not args.no_e2e_grads:
@@ -733,7 +735,7 @@ def run_gpu(args):
         "pool": {"cuda_mallocs_in_timed_regions": int(mallocs), "high_water_GB": ctx.stats()["pool_high_water"] / 1e9},
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "evals/s",
                 "h2d_bytes_per_step": int(sum(p.nbytes for p in pinned)), "d2h_bytes_per_step": int(yp.nbytes),
-                "ms_per_step": ms_e2e / args.steps},
+                "ms_per_step": ms_e2e / args.steps, "gpu_launches": int(launches_e2e)},
         "e2e_with_gradients": e2e_g,
         "parity": parity,
         "notes": ("operand splits (hi/lo 16-bit copies of W, X and the activations) are cached per source array and "

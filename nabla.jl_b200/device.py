@@ -85,6 +85,28 @@ class Context:
             d.flush()
         self._deferred = live
 
+    def flush_readers_of(self, arr):
+        """Launch the deferred work that still READS ``arr`` (it is about to be overwritten).  Everything else stays
+        deferred: a pending product nobody has asked for yet (an intermediate of the previous evaluation the caller
+        still holds, a sensitivity it never read) must not be launched just because a new batch is copied in."""
+        if not self._deferred:
+            return
+        root = arr._base or arr
+
+        def reads(x, depth=0):
+            if not isinstance(x, DevArray):
+                return False
+            if x is root or x._base is root:
+                return True
+            p = x.pending
+            return p is not None and not p.done and depth < 64 and any(reads(o, depth + 1) for o in p.operands())
+
+        for r in list(self._deferred):
+            d = r()
+            if d is not None and not d.done and any(reads(o) for o in d.operands()):
+                d.flush()
+        self._deferred = [r for r in self._deferred if r() is not None and not r().done]
+
     def stats(self):
         s = _lib.nb_stats()
         check(self.L.nb_ctx_stats(self.h, C.byref(s)), self.h)
@@ -292,7 +314,7 @@ class DevArray:
             a = np.asfortranarray(a)
         if a.shape != self.shape:
             raise ValueError(f"DimensionMismatch: {a.shape} vs {self.shape}")
-        self.ctx.flush_deferred()  # a deferred launch may still read this buffer
+        self.ctx.flush_readers_of(self)  # a deferred launch may still read this buffer
         if self.nbytes:
             # pageable source: the copy is complete (staged) when the call returns
             check(self.ctx.L.nb_h2d(self.ctx.h, self.ptr, a.ctypes.data, self.nbytes), self.ctx.h)
@@ -303,7 +325,7 @@ class DevArray:
         """Asynchronous H2D from pinned host memory on the ctx stream (no host synchronisation)."""
         if pinned.nbytes != self.nbytes:
             raise ValueError(f"DimensionMismatch: {pinned.shape} vs {self.shape}")
-        self.ctx.flush_deferred()
+        self.ctx.flush_readers_of(self)
         check(self.ctx.L.nb_h2d(self.ctx.h, self.ptr, pinned.ptr, self.nbytes), self.ctx.h)
         return self
 

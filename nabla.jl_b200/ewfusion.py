@@ -50,6 +50,9 @@ class LazyEw:
     def has_side_outputs(self):
         return False
 
+    def operands(self):
+        return list(self.leaves or ())
+
     def flush(self):
         if self.done:
             return
@@ -146,6 +149,29 @@ def _chainable(a, d, rvs, cons):
             and lazy_of(d) is not None and cons.get(a.pos, 0) == 1 and rvs.tape[a.pos - 1] is UNDEF)
 
 
+def _leaf(d, a, leaves, nodes, index):
+    from .core import Node
+    k = index.get(id(d))
+    if k is None:
+        k = index[id(d)] = len(leaves)
+        leaves.append(d)
+        nodes.append(a if isinstance(a, Node) else None)
+    return Sym.arg(k)
+
+
+def _expr(branch, rvs, cons, leaves, nodes, index):
+    """Expression of ``branch``'s value over the leaves: chainable operands are expanded recursively."""
+    p, dv, dp = branch.saved[0], branch.saved[1], branch.saved[2]
+    syms = []
+    for k, j in enumerate(dp):
+        a = branch.args[j + 1]
+        if _chainable(a, dv[k], rvs, cons):
+            syms.append(_expr(a, rvs, cons, leaves, nodes, index))
+        else:
+            syms.append(_leaf(dv[k], a, leaves, nodes, index))
+    return symbolic(p, syms)
+
+
 def chain_pullback(y, ybar, rvs, own, alias_ok=None):
     """Fused pullback of Branch ``y`` together with every chainable Branch below it.  Returns False when nothing is
     chainable or the composition does not fit (the caller then runs the ordinary per-Branch pullback)."""
@@ -157,27 +183,10 @@ def chain_pullback(y, ybar, rvs, own, alias_ok=None):
     if not any(_chainable(y.args[j + 1], dev[k], rvs, cons) for k, j in enumerate(dev_pos)):
         return False
     leaves, nodes, index = [], [], {}
-
-    def leaf(d, a):
-        k = index.get(id(d))
-        if k is None:
-            k = index[id(d)] = len(leaves)
-            leaves.append(d)
-            nodes.append(a if isinstance(a, Node) else None)
-        return Sym.arg(k)
-
-    def expr(branch):
-        p, dv, dp = branch.saved[0], branch.saved[1], branch.saved[2]
-        syms = []
-        for k, j in enumerate(dp):
-            a = branch.args[j + 1]
-            if _chainable(a, dv[k], rvs, cons):
-                syms.append(expr(a))
-            else:
-                syms.append(leaf(dv[k], a))
-        return symbolic(p, syms)
-
-    root = expr(y)
+    # (module-level recursion, not a nested closure calling itself: a self-referencing closure is a reference cycle
+    #  that keeps the reverse tape — and every deferred launch hanging off its slots — alive until the cyclic collector
+    #  runs, long after the sweep)
+    root = _expr(y, rvs, cons, leaves, nodes, index)
     if len(leaves) > NB_MAX_ARGS:
         return False
     try:

@@ -157,6 +157,10 @@ class Deferred:
     def has_side_outputs(self):
         return self.rowsum_ref is not None
 
+    def operands(self):
+        """The arrays the pending launch reads."""
+        return [x for x in (self.A, self.B, self.bias, self.ysaved) if x is not None]
+
     # -- launch --
     def flush(self):
         if self.done:
