@@ -19,7 +19,7 @@
 //                               handles outputs that keep rows (reduce over cols), e.g. bias grads
 //   k_wcol   rows  > 32         one warp per column; handles outputs that keep cols (reduce over
 //                               rows), e.g. `f ./ sum(f, dims=1)` with many rows
-//   k_short  rows <= 32         one thread per column (10 x B output layers)
+//   k_short  rows <= 32         lanes = (row, column) pairs (10 x B output layers)
 //   k_nd     >2 collapsed dims  generic fallback, one thread per output element
 #include "ops.cuh"
 #include "bcast_types.cuh"
@@ -480,79 +480,72 @@ __global__ void __launch_bounds__(256) k_wcol(const MRP P, const nb_prog G) {
   }
 }
 
-// ---- k_short: rows <= 32, one thread per column; all output modes ----------------------------
-// dynamic smem: (#KEEP_ROWS outputs) * rows * blockDim.x accumulators + 32
+// ---- k_short: rows <= 32; all output modes ----------------------------------------------------
+// A warp covers 32 / RP columns at a time, RP = the power of two >= rows: lane -> (row = lane % RP, column = lane / RP).
+// (One thread per column left a 10 x 4096 array — the output layer of examples/mlp.jl — with 4096 threads on the whole
+// part, each walking its column serially: 20-38 us of pure latency per launch for 40 K elements.)  Column sums
+// (KEEP_COLS) are xor-shuffle trees inside the RP lanes, row sums (KEEP_ROWS) per-thread registers combined through
+// shared memory in a fixed order, OM_ALL a block sum: deterministic.
+// dynamic smem: blockDim.x + 32 accumulators (+ the interpreter's slots)
 template <typename T, template <typename, int> class EvT>
-__global__ void __launch_bounds__(128) k_short(const MRP P, const nb_prog G) {
+__global__ void __launch_bounds__(128) k_short(const MRP P, const nb_prog G, int rp) {
   using Ev = EvT<T, 1>;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   T* smem = reinterpret_cast<T*>(smem_raw);
   const int tid = threadIdx.x, BT = blockDim.x;
   const int rows = (int)P.rows;
   const T scale = T(P.scale);
-  int kr_slot[Ev::MAXOUT];
-  int nkr = 0;
+  const int r = tid & (rp - 1), cl = tid / rp, cpb = BT / rp;
+  const bool rok = r < rows;
+  T* red = smem + BT;
+  T acc[Ev::MAXOUT];   // KEEP_ROWS: this thread's row; OM_ALL: everything it saw
 #pragma unroll
-  for (int k = 0; k < Ev::MAXOUT; ++k) {
-    kr_slot[k] = -1;
-    if (k < P.nout && P.out[k].active && P.out[k].mode == OM_KEEP_ROWS) kr_slot[k] = nkr++;
-  }
-  for (int i = tid; i < nkr * rows * BT; i += BT) smem[i] = T(0);
-  T* red = smem + nkr * rows * BT;
-  T all_acc[Ev::MAXOUT];
+  for (int k = 0; k < Ev::MAXOUT; ++k) acc[k] = T(0);
+  const int64_t stride = (int64_t)gridDim.x * cpb;
+  for (int64_t c0 = (int64_t)blockIdx.x * cpb; c0 < P.cols; c0 += stride) {   // (uniform trip count per block)
+    const int64_t c = c0 + cl;
+    const bool ok = rok && c < P.cols;
+    T o[Ev::MAXOUT][1];
 #pragma unroll
-  for (int k = 0; k < Ev::MAXOUT; ++k) all_acc[k] = T(0);
-  __syncthreads();
-  const int64_t stride = (int64_t)gridDim.x * BT;
-  for (int64_t c = (int64_t)blockIdx.x * BT + tid; c < P.cols; c += stride) {
-    T col_acc[Ev::MAXOUT];
-#pragma unroll
-    for (int k = 0; k < Ev::MAXOUT; ++k) col_acc[k] = T(0);
-    for (int r = 0; r < rows; ++r) {
-      T o[Ev::MAXOUT][1];
-      Ev::run(P, G, r, c, 1, o);
-#pragma unroll
-      for (int k = 0; k < Ev::MAXOUT; ++k) {
-        if (k >= P.nout || !P.out[k].active) continue;
-        const int mode = P.out[k].mode;
-        const T val = o[k][0];
-        if (mode == OM_ELEM) {
-          T* dst = (T*)P.out[k].p + r * P.out[k].rs + c * P.out[k].cs;
-          *dst = P.out[k].acc ? *dst + val * scale : val * scale;
-        } else if (mode == OM_KEEP_COLS) {
-          col_acc[k] += val;
-        } else if (mode == OM_KEEP_ROWS) {
-          smem[(kr_slot[k] * rows + r) * BT + tid] += val;
-        } else {
-          all_acc[k] += val;
-        }
-      }
-    }
+    for (int k = 0; k < Ev::MAXOUT; ++k) o[k][0] = T(0);
+    if (ok) Ev::run(P, G, r, c, 1, o);
 #pragma unroll
     for (int k = 0; k < Ev::MAXOUT; ++k) {
-      if (k >= P.nout || !P.out[k].active || P.out[k].mode != OM_KEEP_COLS) continue;
-      T* dst = (T*)P.out[k].p + c * P.out[k].cs;
-      *dst = P.out[k].acc ? *dst + col_acc[k] * scale : col_acc[k] * scale;
+      if (k >= P.nout || !P.out[k].active) continue;
+      const int mode = P.out[k].mode;
+      T val = ok ? o[k][0] : T(0);
+      if (mode == OM_ELEM) {
+        if (ok) {
+          T* dst = (T*)P.out[k].p + r * P.out[k].rs + c * P.out[k].cs;
+          *dst = P.out[k].acc ? *dst + val * scale : val * scale;
+        }
+      } else if (mode == OM_KEEP_COLS) {
+        for (int sft = rp >> 1; sft > 0; sft >>= 1) val += __shfl_xor_sync(0xffffffffu, val, sft);
+        if (r == 0 && c < P.cols) {
+          T* dst = (T*)P.out[k].p + c * P.out[k].cs;
+          *dst = P.out[k].acc ? *dst + val * scale : val * scale;
+        }
+      } else {
+        acc[k] += val;
+      }
     }
   }
-  __syncthreads();
-  // KEEP_ROWS: each warp reduces (output,row) pairs over the block's threads
-  const int lane = tid & 31, w = tid >> 5, nw = BT >> 5;
 #pragma unroll
   for (int k = 0; k < Ev::MAXOUT; ++k) {
-    if (kr_slot[k] < 0) continue;
-    for (int r = w; r < rows; r += nw) {
-      T s = T(0);
-      for (int t = lane; t < BT; t += 32) s += smem[(kr_slot[k] * rows + r) * BT + t];
-      s = warp_sum(s);
-      if (lane == 0) ((T*)P.out[k].partial)[(int64_t)blockIdx.x * rows + r] = s;
+    if (k >= P.nout || !P.out[k].active) continue;
+    if (P.out[k].mode == OM_KEEP_ROWS) {
+      __syncthreads();
+      smem[tid] = acc[k];
+      __syncthreads();
+      if (tid < rows) {
+        T s = T(0);
+        for (int j = 0; j < cpb; ++j) s += smem[j * rp + tid];
+        ((T*)P.out[k].partial)[(int64_t)blockIdx.x * rows + tid] = s;
+      }
+    } else if (P.out[k].mode == OM_ALL) {
+      T s = block_sum<T>(acc[k], red);
+      if (tid == 0) ((T*)P.out[k].partial)[blockIdx.x] = s;
     }
-  }
-#pragma unroll
-  for (int k = 0; k < Ev::MAXOUT; ++k) {
-    if (k >= P.nout || !P.out[k].active || P.out[k].mode != OM_ALL) continue;
-    T s = block_sum<T>(all_acc[k], red);
-    if (tid == 0) ((T*)P.out[k].partial)[blockIdx.x] = s;
   }
 }
 
@@ -767,38 +760,26 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
   }
 
   if (P.rows <= 32) {
-    // one thread per column; KEEP_ROWS accumulators live in shared memory, so at most a few such
-    // outputs per launch (48 KB budget)
+    // lanes = (row, column) pairs, RP = power of two >= rows (k_short)
     const int BT = 128;
-    int64_t blocks = (P.cols + BT - 1) / BT;
-    const int64_t cap = (int64_t)sms * 8;
+    int rp = 1;
+    while (rp < P.rows) rp <<= 1;
+    const int cpb = BT / rp;
+    int64_t blocks = (P.cols + cpb - 1) / cpb;
+    const int64_t cap = (int64_t)sms * 16;
     if (blocks > cap) blocks = cap;
-    const size_t per_kr = (size_t)P.rows * BT * sizeof(T);
-    const int max_kr = (int)((48 * 1024 - 32 * sizeof(T)) / per_kr);
-    int k0 = 0;
-    while (k0 < P.nout) {
-      int nkr = 0, k1 = k0;
-      for (; k1 < P.nout; ++k1) {
-        if (P.out[k1].mode == OM_KEEP_ROWS) {
-          if (nkr == max_kr) break;
-          ++nkr;
-        }
-      }
-      for (int k = 0; k < P.nout; ++k) P.out[k].active = (k >= k0 && k < k1);
-      for (int k = k0; k < k1; ++k) {
-        int32_t rc = NB_OK;
-        if (P.out[k].mode == OM_KEEP_ROWS) rc = alloc_partial(k, blocks, P.rows);
-        if (P.out[k].mode == OM_ALL) rc = alloc_partial(k, blocks, 1);
-        if (rc != NB_OK) return rc;
-      }
-      const size_t smem = with_slots(k_short<T, Ev>, nkr * per_kr + 32 * sizeof(T), BT, 1);
-      k_short<T, Ev><<<(unsigned)blocks, BT, smem, st>>>(P, G);
-      NB_LAUNCH_CHECK(ctx);
-      int32_t rc = finish();
+    if (blocks < 1) blocks = 1;
+    for (int k = 0; k < P.nout; ++k) {
+      P.out[k].active = 1;
+      int32_t rc = NB_OK;
+      if (P.out[k].mode == OM_KEEP_ROWS) rc = alloc_partial(k, blocks, P.rows);
+      if (P.out[k].mode == OM_ALL) rc = alloc_partial(k, blocks, 1);
       if (rc != NB_OK) return rc;
-      k0 = k1;
     }
-    return NB_OK;
+    const size_t smem = with_slots(k_short<T, Ev>, (BT + 32) * sizeof(T), BT, 1);
+    k_short<T, Ev><<<(unsigned)blocks, BT, smem, st>>>(P, G, rp);
+    NB_LAUNCH_CHECK(ctx);
+    return finish();
   }
 
   // rows > 32: KEEP_COLS outputs go to the warp-per-column kernel, everything else to k_tall
