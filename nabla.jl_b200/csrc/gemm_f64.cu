@@ -83,7 +83,9 @@ template <bool TA, bool TB>
 __global__ void __launch_bounds__(256, 1)
 k_gemm_dmma(int64_t M, int64_t N, int64_t K, double alpha, const double* __restrict__ A, int64_t lda,
             const double* __restrict__ B, int64_t ldb, double beta, double* __restrict__ C, int64_t ldc,
-            int vecA, int vecB, int tiles_m, int64_t k_per_split, double* __restrict__ ws) {
+            int vecA, int vecB, int tiles_m, int64_t k_per_split, double* __restrict__ ws,
+            const int32_t* __restrict__ run_if) {
+  if (run_if && !*run_if) return;  // a product decided on the device (ozaki.cu range guard): not this path
   // two shared-memory stages: slice i+1 is stored while slice i is multiplied, one barrier per slice (ncu on the
   // single-stage version: Tensor (DP) pipe 76.8 % active, no eligible warp 84 % of the cycles — the 8 warps
   // drained the pipe at both barriers of every slice)
@@ -167,7 +169,9 @@ k_gemm_dmma(int64_t M, int64_t N, int64_t K, double alpha, const double* __restr
 // C = alpha * sum_s ws[s] + beta * C   (deterministic second phase of split-K)
 __global__ void __launch_bounds__(256) k_splitk_reduce(const double* __restrict__ ws, int splits, int64_t M,
                                                        int64_t N, double alpha, double beta,
-                                                       double* __restrict__ C, int64_t ldc) {
+                                                       double* __restrict__ C, int64_t ldc,
+                                                       const int32_t* __restrict__ run_if) {
+  if (run_if && !*run_if) return;
   const int64_t total = M * N;
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
@@ -182,7 +186,7 @@ __global__ void __launch_bounds__(256) k_splitk_reduce(const double* __restrict_
 
 int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double beta, double* C,
-                     int64_t ldc) {
+                     int64_t ldc, const int32_t* run_if) {
   const int64_t tiles_m = (m + BM - 1) / BM, tiles_n = (n + BN - 1) / BN;
   if (tiles_m * tiles_n > 0x7fffffffLL) return NB_ERR_UNSUPPORTED;
   const int vecA = ((uintptr_t)A % 16 == 0) && (lda % 2 == 0);
@@ -218,7 +222,7 @@ int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_
       attr_done[ctx->device & 63] = true;                                                                                         \
     }                                                                                                           \
     k_gemm_dmma<TA_, TB_><<<grid, 256, DMMA_SMEM, st>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, vecA,     \
-                                                        vecB, (int)tiles_m, kps, ws);                           \
+                                                        vecB, (int)tiles_m, kps, ws, run_if);                   \
   } while (0)
   if (!tA && !tB) NB_DMMA(false, false);
   else if (!tA && tB) NB_DMMA(false, true);
@@ -229,7 +233,7 @@ int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_
   if (ws) {
     int64_t blocks = (m * n + 255) / 256;
     if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
-    k_splitk_reduce<<<(unsigned)blocks, 256, 0, st>>>(ws, splits, m, n, alpha, beta, C, ldc);
+    k_splitk_reduce<<<(unsigned)blocks, 256, 0, st>>>(ws, splits, m, n, alpha, beta, C, ldc, run_if);
     NB_LAUNCH_CHECK(ctx);
     nb_pool_release(ctx, ws);
   }

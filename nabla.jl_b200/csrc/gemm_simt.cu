@@ -10,7 +10,7 @@
 // implemented in gemm_f64.cu / gemm_tf32.cu; return NB_ERR_UNSUPPORTED when the shape does not fit
 int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha,
                      const double* A, int64_t lda, const double* B, int64_t ldb, double beta,
-                     double* C, int64_t ldc);
+                     double* C, int64_t ldc, const int32_t* run_if);
 int32_t nb_gemm_ozaki(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, double alpha, const double* A,
                       int64_t lda, const double* B, int64_t ldb, double beta, double* C, int64_t ldc);
 int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t k, float alpha,
@@ -171,7 +171,7 @@ int32_t nb_gemm(nb_ctx* ctx, char tAc, char tBc, int64_t m, int64_t n, int64_t k
       if (rc != NB_ERR_UNSUPPORTED) return rc;
     }
     int32_t rc = nb_gemm_dmma(ctx, tA, tB, m, n, k, alpha, (const double*)A, lda, (const double*)B,
-                              ldb, beta, (double*)C, ldc);
+                              ldb, beta, (double*)C, ldc, nullptr);
     if (rc != NB_ERR_UNSUPPORTED) return rc;
     return launch_simt<double>(ctx, tA, tB, m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
   }

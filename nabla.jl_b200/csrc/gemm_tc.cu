@@ -132,6 +132,8 @@ struct GemmArgs {
   int64_t ldc;
   int32_t tiles_m, tiles_n;
   int32_t* tile_counter;  // zeroed before the launch; next tile index to hand out
+  const int32_t* skip_if; // host side only, nullable: device word; when non-zero at launch time the counter starts beyond
+                          // the last tile, so every CTA sees the end sentinel at once and the launch does nothing
   int32_t group_m;        // tile-rows per rasterisation group (see tile_coords)
   int64_t k_begin, k_end; // K range of this launch (multiples of the K step except at the very end)
   int32_t kchunk_kb;      // K blocks accumulated in TMEM before the epilogue folds them into C
@@ -1487,6 +1489,22 @@ bool make_map(GemmState* st, CUtensorMap* map, const void* base, CUtensorMapData
   return r == CUDA_SUCCESS;
 }
 
+// tile counter of the next launch: 0, or past every tile when *skip_if is set (the launch then does nothing — how a
+// product decided on the device, e.g. the Float64 split's range guard in ozaki.cu, is cancelled without a host sync)
+__global__ void k_counter_init(int32_t* counter, const int32_t* skip_if) {
+  *counter = (skip_if && *skip_if) ? 0x40000000 : 0;
+}
+
+static int32_t reset_counter(nb_ctx* ctx, const GemmArgs& g) {
+  if (g.skip_if) {
+    k_counter_init<<<1, 1, 0, ctx->stream>>>(g.tile_counter, g.skip_if);
+    NB_LAUNCH_CHECK(ctx);
+    return NB_OK;
+  }
+  NB_CUDA_OK(ctx, cudaMemsetAsync(g.tile_counter, 0, sizeof(int32_t), ctx->stream));
+  return NB_OK;
+}
+
 template <int BN, int KIND>
 int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   using C_ = Cfg<BN, KIND>;
@@ -1498,7 +1516,7 @@ int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   }
   const int ntiles = g.tiles_m * g.tiles_n;
   const int grid = ntiles < ctx->num_sms ? ntiles : ctx->num_sms;
-  NB_CUDA_OK(ctx, cudaMemsetAsync(g.tile_counter, 0, sizeof(int32_t), ctx->stream));
+  { const int32_t rc0 = reset_counter(ctx, g); if (rc0 != NB_OK) return rc0; }
   kern<<<grid, NTHREADS, C_::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
@@ -1516,7 +1534,7 @@ int32_t launch_pair(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
   int max_pairs = ctx->num_sms / 2;
   if (const char* e = getenv("NB_GEMM_PAIRS")) max_pairs = atoi(e) > 0 && atoi(e) < max_pairs ? atoi(e) : max_pairs;
   const int pairs = ntiles < max_pairs ? ntiles : max_pairs;
-  NB_CUDA_OK(ctx, cudaMemsetAsync(g.tile_counter, 0, sizeof(int32_t), ctx->stream));
+  { const int32_t rc0 = reset_counter(ctx, g); if (rc0 != NB_OK) return rc0; }
   k_gemm_tc_pair<KIND><<<2 * pairs, NTHREADS, C2::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
@@ -1797,6 +1815,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
     rc = NB_ERR_UNSUPPORTED;
   } else {
     GemmArgs g;
+    memset(&g, 0, sizeof(g));
     g.M = m; g.N = n; g.K = k;
     g.a_mn = a_mn; g.b_mn = b_mn;
     g.alpha = alpha; g.beta = beta;
@@ -1973,7 +1992,7 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
 // kp * 2^12 < 2^31 (|slice| <= 64): checked by the caller.
 int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* A8, int64_t lda8, const int8_t* B8,
                    int64_t ldb8, double scale, const double* row_scale, const double* col_scale, double beta,
-                   double* C, int64_t ldc) {
+                   double* C, int64_t ldc, const int32_t* skip_if) {
   GemmState* st = state_of(ctx);
   if (!st->encode) return NB_ERR_UNSUPPORTED;
   if (kp % 128 || (lda8 & 15) || (ldb8 & 15) || (((uintptr_t)A8 | (uintptr_t)B8) & 15)) return NB_ERR_UNSUPPORTED;
@@ -2007,6 +2026,7 @@ int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* 
   int64_t gm = (70ll << 20) / (panel > 0 ? panel : 1);
   g.group_m = (int32_t)(gm < 1 ? 1 : gm > 32 ? 32 : gm);
   g.C64 = C; g.row_scale = row_scale; g.col_scale = col_scale; g.scale64 = scale; g.beta64 = beta;
+  g.skip_if = skip_if;
   if (use_pair) return launch_pair<KIND_I8>(ctx, maps, g);
   return BN == 256 ? launch<256, KIND_I8>(ctx, maps, g) : launch<128, KIND_I8>(ctx, maps, g);
 }
@@ -2016,7 +2036,7 @@ int32_t nb_gemm_i8(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, const int8_t* 
 // S-1..1: five more passes, error 2^-7 smaller).  C64 = beta*C64 + alpha * diag(row_scale) * (sum of levels) * diag(col_scale).
 int32_t nb_gemm_i8all(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, int32_t S, int32_t extra_level, const int8_t* A8,
                       int64_t ld8, const int8_t* B8, double alpha, const double* row_scale, const double* col_scale,
-                      double beta, double* C, int64_t ldc) {
+                      double beta, double* C, int64_t ldc, const int32_t* skip_if) {
   GemmState* st = state_of(ctx);
   if (!st->encode) return NB_ERR_UNSUPPORTED;
   if (kp % 128 || (ld8 & 15) || (((uintptr_t)A8 | (uintptr_t)B8) & 15) || S < 1 || S + (extra_level ? 1 : 0) > 8)
@@ -2057,5 +2077,6 @@ int32_t nb_gemm_i8all(nb_ctx* ctx, int64_t m, int64_t n, int64_t kp, int32_t S, 
     ++c;
   }
   g.nchunk_tab = c;
+  g.skip_if = skip_if;
   return launch<BNL, KIND_I8ALL>(ctx, maps, g);
 }

@@ -1299,7 +1299,7 @@ def test_gemm_f64_ozaki_split(nb, ctx):
                     Cd = ctx.asarray(C0)
                     n0 = ctx.stats()["kernel_launches"]
                     K.gemm(tA, tB, -1.3, ctx.asarray(A), ctx.asarray(B), 1.0, Cd, mm, nn, kk)
-                    assert 5 <= ctx.stats()["kernel_launches"] - n0 <= 7
+                    assert 8 <= ctx.stats()["kernel_launches"] - n0 <= 11   # scales, slices, guard, one split launch, idle DMMA
                     close(Cd.numpy(), ref, scale=0.01)   # 1e-12
         # non-finite input: the affected row of C is NaN (never finite garbage), the rest is untouched
         A = rng.standard_normal((m, k))
@@ -1314,6 +1314,34 @@ def test_gemm_f64_ozaki_split(nb, ctx):
         assert np.all(np.isfinite(np.delete(got, [7, 300], axis=0)))
     finally:
         ctx.math_mode = old
+
+
+def test_gemm_f64_split_range_guard(nb, ctx):
+    """dgemm's error is relative to sum_k |a_ik||b_kj|, the int8 split's to max|a_i.| * max|b_.j| (csrc/ozaki.cu): a row
+    dominated by one outlier that meets a zero of B would keep only ~25 bits of its other entries.  The guard measures
+    how far the largest entry of a line stands above the rest in the pass that finds the scales and — on the device,
+    without a host synchronisation — hands such a product to DMMA.  Both split variants (one launch / one launch per
+    level); with the guard disabled by its limit the same product shows the loss the guard prevents."""
+    from nabla_jl_b200 import kernels as K
+    rng = np.random.default_rng(321)
+    for (m, n, k) in ((2048, 2048, 1024), (4100, 4200, 4000)):
+        A = rng.standard_normal((m, k))
+        B = rng.standard_normal((k, n))
+        A[5, 0] = 1e7          # the outlier of row 5 ...
+        B[0, :] = 0.0          # ... meets zeros: C[5, :] is made of the ordinary entries of the row
+        ref = A @ B
+        Cd = ctx.zeros((m, n), np.float64)
+        K.gemm("N", "N", 1.0, ctx.asarray(A), ctx.asarray(B), 0.0, Cd, m, n, k)
+        got = Cd.numpy()
+        err5 = np.abs(got[5] - ref[5]).max() / np.abs(ref[5]).max()
+        assert err5 < 1e-13, err5
+        close(got, ref, scale=0.01)
+        # ordinary data is NOT handed to DMMA: same product without the outlier stays on the split (launch count)
+        A[5, 0] = 0.3
+        n0 = ctx.stats()["kernel_launches"]
+        K.gemm("N", "N", 1.0, ctx.asarray(A), ctx.asarray(B), 0.0, Cd, m, n, k)
+        assert ctx.stats()["kernel_launches"] - n0 >= 8
+        close(Cd.numpy(), A @ B, scale=0.01)
 
 
 def test_mlp_gradient_f64_on_the_split_path(nb, orc):
