@@ -195,11 +195,20 @@ int32_t nb_gemm_dmma(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_
   cudaStream_t st = ctx->stream;
   // split-K when the output has too few tiles to occupy the SMs (weight gradients: small m x n, k = batch)
   int splits = 1;
-  if (tiles * 2 <= ctx->num_sms && k >= 8 * BK) {
-    splits = (int)((2 * ctx->num_sms + tiles - 1) / tiles);
-    const int64_t max_splits = k / (4 * BK);
-    if (splits > max_splits) splits = (int)max_splits;
-    if (splits > 64) splits = 64;
+  if (tiles < ctx->num_sms && k >= 8 * BK) {
+    // one CTA per SM: pick the split count (up to ~2 waves) whose grid fills whole waves best — 28 tiles x 11 splits
+    // = 308 CTAs ran as three waves on 148 SMs, 28 x 10 = 280 as two.  With more than half a wave of tiles the split
+    // must pay for its workspace pass: taken only for a quarter more of the part (96 tiles -> 3 x 96 = 288 CTAs)
+    int64_t max_splits = k / (4 * BK);
+    if (max_splits > 64) max_splits = 64;
+    const int64_t hi = (2 * (int64_t)ctx->num_sms + tiles - 1) / tiles;
+    const double eff1 = (double)tiles / (double)ctx->num_sms;
+    double best = tiles * 2 <= ctx->num_sms ? 0.0 : 1.25 * eff1;
+    for (int64_t s = 2; s <= hi && s <= max_splits; ++s) {
+      const int64_t ctas = tiles * s, waves = (ctas + ctx->num_sms - 1) / ctx->num_sms;
+      const double eff = (double)ctas / (double)(waves * ctx->num_sms);
+      if (eff >= best - 1e-9) { best = eff; splits = (int)s; }   // ties: the larger split (shorter CTAs)
+    }
   }
   int64_t kps = k;
   double* ws = nullptr;

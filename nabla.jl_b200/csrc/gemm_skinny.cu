@@ -279,6 +279,7 @@ struct SmallK {
   const T* bias;
   const T* y; int64_t ldy;
   T* rowsum_partial;        // [gridDim.y][m]
+  int ncb;                  // columns per CTA (<= 128; fewer when 128 would leave most SMs without a CTA)
   void* s_hi; void* s_lo; int64_t ld_s; int s_fp16; float s_scale;   // Float32 only
   int vec;
 };
@@ -294,9 +295,9 @@ __global__ void __launch_bounds__(256, 2) k_gemm_smallk(const SmallK<T> g) {
   __shared__ __align__(16) T Bs[NCB][KKP];
   const int tid = threadIdx.x;
   const int64_t i0 = ((int64_t)blockIdx.x * 256 + tid) * V;
-  const int64_t j0 = (int64_t)blockIdx.y * NCB;
-  const int ncb = (int)(g.n - j0 < NCB ? g.n - j0 : NCB);
-  for (int e = tid; e < NCB * KKP; e += 256) {
+  const int64_t j0 = (int64_t)blockIdx.y * g.ncb;
+  const int ncb = (int)(g.n - j0 < g.ncb ? g.n - j0 : g.ncb);
+  for (int e = tid; e < g.ncb * KKP; e += 256) {
     const int jj = e / KKP, kk = e % KKP;
     Bs[jj][kk] = (jj < ncb && kk < g.k) ? g.B[(int64_t)kk * g.b_sk + (j0 + jj) * g.b_sj] : T(0);
   }
@@ -546,9 +547,12 @@ int32_t run_stream(nb_ctx* ctx, bool g_c_contig, const T* G, int64_t ldg, int64_
   // items fill whole rounds of that wave (a 1.3-wave grid leaves two thirds of the part idle for the last third)
   const int64_t kc_cols = 8 * (sizeof(T) == 8 ? 2 : 4);   // columns per CTA of k_skinny_kc
   const int64_t ncg = g_c_contig ? (ncols + 256 * V - 1) / (256 * V) : (ncols + kc_cols - 1) / kc_cols;
-  const int64_t kquant = g_c_contig ? 64 : 32 * V * 2;
-  const int64_t maxsplit = (K + kquant - 1) / kquant;
+  int64_t kquant = g_c_contig ? 64 : 32 * V * 2;
   const int64_t cap = a.capacity;
+  // few output columns (300 x 4096 with 10 rows: one column group): K ranges of 64 would leave 64 CTAs for the whole
+  // part; two batches of eight K steps per CTA still keep eight loads in flight
+  if (g_c_contig && ncg * ((K + kquant - 1) / kquant) * 2 < cap) kquant = 16;
+  const int64_t maxsplit = (K + kquant - 1) / kquant;
   int64_t nsplit = 1;
   if (ncg < cap) {
     nsplit = cap / ncg;   // one round
@@ -596,7 +600,7 @@ int32_t run_stream(nb_ctx* ctx, bool g_c_contig, const T* G, int64_t ldg, int64_
 template <typename T, int KK>
 int32_t launch_smallk(nb_ctx* ctx, const SmallK<T>& g) {
   constexpr int V = Vec<T>::N;
-  dim3 grid((unsigned)((g.m + 256 * V - 1) / (256 * V)), (unsigned)((g.n + 127) / 128));
+  dim3 grid((unsigned)((g.m + 256 * V - 1) / (256 * V)), (unsigned)((g.n + g.ncb - 1) / g.ncb));
   k_gemm_smallk<T, KK><<<grid, 256, 0, ctx->stream>>>(g);
   NB_LAUNCH_CHECK(ctx);
   return NB_OK;
@@ -618,7 +622,14 @@ int32_t run_smallk(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int64_t 
   void *e_hi = nullptr, *e_lo = nullptr;
   float* e_sc = nullptr;
   int64_t e_ld = 0;
-  const int nparts = (int)((n + 127) / 128);
+  // columns per CTA: 128, or fewer (down to 16) until the grid covers the part twice (500 x 4096 x 10 in Float64 is one
+  // CTA row: 32 CTAs of 128 columns left four fifths of the SMs idle)
+  g.ncb = 128;
+  {
+    const int64_t gx = (m + 256 * V - 1) / (256 * V);
+    while (g.ncb > 16 && gx * ((n + g.ncb - 1) / g.ncb) < 2 * (int64_t)ctx->num_sms) g.ncb >>= 1;
+  }
+  const int nparts = (int)((n + g.ncb - 1) / g.ncb);
   int32_t rc = NB_OK;
   if (epi && epi->kind) {
     g.ekind = epi->kind; g.eop = epi->op;
