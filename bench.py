@@ -141,6 +141,8 @@ def defaults_for(args):
         args.dtype = "f32" if args.workload == "wide_mlp" else "f64"
     if args.scaling == "weak":
         args.batch = args.per_gpu_batch * max(1, args.gpus)
+    if args.capture is None:
+        args.capture = args.workload != "wide_mlp"
     return args
 
 
@@ -688,6 +690,10 @@ def run_gpu(args):
             d[1] += 1
             d[3].append(t)
     roof = None
+    phase_ms = {}
+    for tag, work, unit, t in recs:
+        if unit == "ms":
+            phase_ms[tag] = phase_ms.get(tag, 0.0) + t
     gemm_ms_total = sum(v[0] for v in by_tag.values())
     if by_tag:
         flop = sum(v[2] * v[1] for v in by_tag.values())
@@ -732,6 +738,13 @@ def run_gpu(args):
         "TFLOP/s_algorithmic": wk.flops(B) / (ms_step * 1e-3) / 1e12,
         "clocks": clocks, "gpu_launches": int(launches), "host_enqueue_ms_per_step": host_ms / args.steps,
         "non_gemm_ms_per_step": (ms_prof - gemm_ms_total) / args.steps,
+        "step_breakdown_ms": {"gemm": gemm_ms_total / args.steps,
+                              "shared_sweep": phase_ms.get("shared_sweep", 0.0) / args.steps,
+                              "join_wait": phase_ms.get("join_wait", 0.0) / args.steps,
+                              "other": (ms_prof - gemm_ms_total - phase_ms.get("shared_sweep", 0.0)
+                                        - phase_ms.get("join_wait", 0.0)) / args.steps,
+                              "note": "CUDA-event brackets on the sweep stream in the eager profiling region; join_wait = "
+                                      "the part of the NCCL exchange not hidden behind the sweep"},
         "pool": {"cuda_mallocs_in_timed_regions": int(mallocs), "high_water_GB": ctx.stats()["pool_high_water"] / 1e9},
         "e2e": {"value": 1e3 / (ms_e2e / args.steps), "unit": "evals/s",
                 "h2d_bytes_per_step": int(sum(p.nbytes for p in pinned)), "d2h_bytes_per_step": int(yp.nbytes),
@@ -788,7 +801,10 @@ def main():
     ap.add_argument("--per-gpu-batch", type=int, default=8192, help="--scaling weak: columns per GPU")
     ap.add_argument("--dtype", default=None, choices=["f32", "f64"])
     ap.add_argument("--math", default="default", choices=["default", "fp16x3", "bf16x3", "3xtf32", "tf32", "fp32"])
-    ap.add_argument("--capture", action="store_true", help="replay the whole per-rank step as one CUDA graph")
+    ap.add_argument("--capture", action="store_true", default=None,
+                    help="replay the whole per-rank step as one CUDA graph (default for the small, launch-bound "
+                         "workloads vae / mlp; the wide MLP runs eager: its step is 99 %% GEMM time)")
+    ap.add_argument("--no-capture", dest="capture", action="store_false")
     ap.add_argument("--cpu-cols", type=int, default=1024, help="columns per CPU-oracle sample (wide MLP)")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-extra", action="store_true")

@@ -183,7 +183,7 @@ class OverlappedShardedGradient:
     # -- one step, enqueued on the context (and communicator) streams ---------------------------------------------
     def _enqueue(self, keep_tapes=False):
         from .core import UNDEF, own, propagate, reverse_tape
-        from .kernels import bcast_fwd
+        from .kernels import _timed, bcast_fwd
         comm, ctx = self.comm, self.ctx
         G = comm.nranks
         # ---- sweep A: shared term, seeded with 1/G
@@ -191,18 +191,19 @@ class OverlappedShardedGradient:
         y2v = None
         tapes = []
         if self.f_shared is not None:
-            t2 = Tape()
-            leaves2 = [Leaf(t2, p) for p in self.params]
-            y2 = self.f_shared(*leaves2)
-            if isinstance(y2, Node):
-                y2v = unbox(y2)
-                rt2 = propagate(t2, reverse_tape(y2, ctx.full(y2v.shape, 1.0 / G, y2v.dtype)))
-                for i, l in enumerate(leaves2):
-                    if rt2.isassigned(l):
-                        pre[i] = own(unthunk(rt2.raw(l)))
-                tapes.append((t2, rt2))
-                if not keep_tapes:
-                    t2.tape.clear()
+            with _timed(ctx, "shared_sweep", 0, "ms"):      # (CUDA-event bracket while bench.py profiles the step)
+                t2 = Tape()
+                leaves2 = [Leaf(t2, p) for p in self.params]
+                y2 = self.f_shared(*leaves2)
+                if isinstance(y2, Node):
+                    y2v = unbox(y2)
+                    rt2 = propagate(t2, reverse_tape(y2, ctx.full(y2v.shape, 1.0 / G, y2v.dtype)))
+                    for i, l in enumerate(leaves2):
+                        if rt2.isassigned(l):
+                            pre[i] = own(unthunk(rt2.raw(l)))
+                    tapes.append((t2, rt2))
+                    if not keep_tapes:
+                        t2.tape.clear()
         # ---- sweep B: data term accumulates into the pre-filled slots; allreduce of every final leaf slot overlapped
         t = Tape()
         leaves = [Leaf(t, p) for p in self.params]
@@ -230,7 +231,8 @@ class OverlappedShardedGradient:
                 rest.append(grads[l.pos])
         comm.allreduce_sum_async([yd] + rest)
         out = [grads[l.pos] if l.pos in grads else zeroslike(l) for l in leaves]
-        comm.join()
+        with _timed(ctx, "join_wait", 0, "ms"):           # what of the exchange is NOT hidden behind the sweep
+            comm.join()
         if y2v is not None:
             ytot = ctx.empty((), yd.dtype)
             bcast_fwd(_ADD_PROG, [yd, y2v], ytot)
