@@ -138,13 +138,26 @@ int32_t nb_allreduce_sum_async(nb_ctx* ctx, int32_t n_bufs, void* const* bufs, c
   // (inside nb_graph_begin/end the fork below pulls the communicator stream into the capture; NCCL collectives are
   //  capturable, and nb_comm_join — required before nb_graph_end — joins it back)
   if (!ctx->comm_stream) {
-    NB_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    // highest priority: the persistent GEMM launches of the sweep take every SM, so a collective can only start when
+    // CTAs retire — its CTAs must then win the freed SMs against the next product's
+    int prio_lo = 0, prio_hi = 0;
+    NB_CUDA_OK(ctx, cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+    NB_CUDA_OK(ctx, cudaStreamCreateWithPriority(&ctx->comm_stream, cudaStreamNonBlocking, prio_hi));
     NB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
     NB_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming));
   }
   NB_CUDA_OK(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
   NB_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->comm_stream, ctx->ev_fork, 0));
   ctx->comm_pending = true;
+  {
+    int64_t bytes = 0;
+    for (int i = 0; i < n_bufs; ++i) bytes += counts[i] * (dtype == NB_F64 ? 8 : 4);
+    // OFF by default (NB_COMM_CUT_BYTES=<bytes> turns it on): measured on 4 and 8 B200s the exchange then hides behind
+    // the sweep (join wait 1.21 -> 0.61 ms at N = 8) but its CTAs — each one blocks a whole CTA PAIR of the GEMM —
+    // slow the overlapped product by as much (profiles/README.md, round 2): NCCL's SM time is paid either way
+    static const int64_t cut_bytes = getenv("NB_COMM_CUT_BYTES") ? atoll(getenv("NB_COMM_CUT_BYTES")) : 0;
+    if (cut_bytes > 0 && bytes >= cut_bytes) ctx->cut_next_gemm = true;
+  }
   return reduce_on(ctx, ctx->comm_stream, n_bufs, bufs, counts, dtype);
 }
 

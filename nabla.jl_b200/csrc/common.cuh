@@ -45,6 +45,9 @@ struct nb_ctx {
   cudaStream_t comm_stream = nullptr;      // overlapped reductions (nb_allreduce_sum_async)
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   bool comm_pending = false;
+  bool cut_next_gemm = false;  // a large collective was just issued: the next tensor-core product ends its first launch
+                               // after ONE wave of tiles, so the NCCL kernel finds free SMs a tile time later instead
+                               // of after the whole persistent launch (gemm_tc.cu launch ranges)
   // tcgen05 GEMM staging (gemm_tf32.cu)
   void* gemm_state = nullptr;
 };

@@ -132,6 +132,8 @@ struct GemmArgs {
   int64_t ldc;
   int32_t tiles_m, tiles_n;
   int32_t* tile_counter;  // zeroed before the launch; next tile index to hand out
+  int32_t tile_begin, tile_end;  // this launch hands out tiles [tile_begin, tile_end) of the rasterised order
+                                 // (tile_end = 0: all) — a product can be cut at any tile boundary at no extra traffic
   const int32_t* skip_if; // host side only, nullable: device word; when non-zero at launch time the counter starts beyond
                           // the last tile, so every CTA sees the end sentinel at once and the launch does nothing
   int32_t group_m;        // tile-rows per rasterisation group (see tile_coords)
@@ -701,7 +703,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ CUten
   volatile int32_t* sched_tile = (volatile int32_t*)(tmem_slot + 2);  // [SCHED_SLOTS]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int ntiles = g.tiles_m * g.tiles_n;
+  const int ntiles = g.tile_end > 0 ? g.tile_end : g.tiles_m * g.tiles_n;
   const int nkb = (int)((g.k_end - g.k_begin + BK - 1) / BK);
 
   if (warp == 0 && lane == 0) {
@@ -1042,7 +1044,7 @@ k_gemm_tc_pair(const __grid_constant__ CUtensorMap mA0, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();
   const bool leader = rank == 0;
-  const int ntiles = g.tiles_m * g.tiles_n;  // pair tiles (256 x 256)
+  const int ntiles = g.tile_end > 0 ? g.tile_end : g.tiles_m * g.tiles_n;  // pair tiles (256 x 256)
   const int nkb = (int)((g.k_end - g.k_begin + BK - 1) / BK);
 
   if (warp == 0 && lane == 0) {
@@ -1491,13 +1493,13 @@ bool make_map(GemmState* st, CUtensorMap* map, const void* base, CUtensorMapData
 
 // tile counter of the next launch: 0, or past every tile when *skip_if is set (the launch then does nothing — how a
 // product decided on the device, e.g. the Float64 split's range guard in ozaki.cu, is cancelled without a host sync)
-__global__ void k_counter_init(int32_t* counter, const int32_t* skip_if) {
-  *counter = (skip_if && *skip_if) ? 0x40000000 : 0;
+__global__ void k_counter_init(int32_t* counter, const int32_t* skip_if, int32_t start) {
+  *counter = (skip_if && *skip_if) ? 0x40000000 : start;
 }
 
 static int32_t reset_counter(nb_ctx* ctx, const GemmArgs& g) {
-  if (g.skip_if) {
-    k_counter_init<<<1, 1, 0, ctx->stream>>>(g.tile_counter, g.skip_if);
+  if (g.skip_if || g.tile_begin) {
+    k_counter_init<<<1, 1, 0, ctx->stream>>>(g.tile_counter, g.skip_if, g.tile_begin);
     NB_LAUNCH_CHECK(ctx);
     return NB_OK;
   }
@@ -1514,7 +1516,7 @@ int32_t launch(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
     NB_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C_::SMEM));
     attr_done[ctx->device & 63] = true;
   }
-  const int ntiles = g.tiles_m * g.tiles_n;
+  const int ntiles = (g.tile_end > 0 ? g.tile_end : g.tiles_m * g.tiles_n) - g.tile_begin;
   const int grid = ntiles < ctx->num_sms ? ntiles : ctx->num_sms;
   { const int32_t rc0 = reset_counter(ctx, g); if (rc0 != NB_OK) return rc0; }
   kern<<<grid, NTHREADS, C_::SMEM, ctx->stream>>>(maps[0], maps[1], maps[2], maps[3], g);
@@ -1530,7 +1532,7 @@ int32_t launch_pair(nb_ctx* ctx, const CUtensorMap maps[4], const GemmArgs& g) {
     NB_CUDA_OK(ctx, cudaFuncSetAttribute(k_gemm_tc_pair<KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C2::SMEM));
     attr_done[ctx->device & 63] = true;
   }
-  const int ntiles = g.tiles_m * g.tiles_n;
+  const int ntiles = (g.tile_end > 0 ? g.tile_end : g.tiles_m * g.tiles_n) - g.tile_begin;
   int max_pairs = ctx->num_sms / 2;
   if (const char* e = getenv("NB_GEMM_PAIRS")) max_pairs = atoi(e) > 0 && atoi(e) < max_pairs ? atoi(e) : max_pairs;
   const int pairs = ntiles < max_pairs ? ntiles : max_pairs;
@@ -1942,10 +1944,30 @@ int32_t nb_gemm_tcgen05(nb_ctx* ctx, bool tA, bool tB, int64_t m, int64_t n, int
       int64_t gm = panel_budget / (panel > 0 ? panel : 1);
       g.group_m = (int32_t)(gm < 1 ? 1 : gm > 32 ? 32 : gm);
       if (const char* e = getenv("NB_GEMM_GROUP_M")) g.group_m = atoi(e) > 0 ? atoi(e) : g.group_m;
-      if (use_pair) rc = launch_pair<KIND_BF16X3>(ctx, maps, g);
-      else if (kind == KIND_BF16X3) rc = BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
-      else if (kind == KIND_3XTF32) rc = BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
-      else rc = BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);
+      auto go = [&]() -> int32_t {
+        if (use_pair) return launch_pair<KIND_BF16X3>(ctx, maps, g);
+        if (kind == KIND_BF16X3) return BN == 256 ? launch<256, KIND_BF16X3>(ctx, maps, g) : launch<128, KIND_BF16X3>(ctx, maps, g);
+        if (kind == KIND_3XTF32) return BN == 256 ? launch<256, KIND_3XTF32>(ctx, maps, g) : launch<128, KIND_3XTF32>(ctx, maps, g);
+        return BN == 256 ? launch<256, KIND_TF32>(ctx, maps, g) : launch<128, KIND_TF32>(ctx, maps, g);
+      };
+      // A large collective was issued just before this product (comm.cu): its NCCL kernel can only start when CTAs
+      // retire, and a persistent launch holds every SM until its last tile.  The first launch therefore ends after ONE
+      // wave of tiles (they start together and take the same time, so nothing idles at that boundary), the collective's
+      // CTAs take the SMs they need there (high-priority stream) and the second launch runs the remaining tiles.
+      const int all_tiles = g.tiles_m * g.tiles_n;
+      const int wave = use_pair ? ctx->num_sms / 2 : ctx->num_sms;
+      if (ctx->cut_next_gemm && kb == 0) {
+        ctx->cut_next_gemm = false;
+        if (all_tiles >= 3 * wave) {
+          g.tile_begin = 0; g.tile_end = wave;
+          rc = go();
+          g.tile_begin = wave; g.tile_end = all_tiles;
+          if (rc == NB_OK) rc = go();
+          g.tile_begin = 0; g.tile_end = 0;
+          continue;
+        }
+      }
+      rc = go();
     }
     if (unfuse && rc == NB_OK) {
       const int vec = (((uintptr_t)C & 15) == 0) && (ldc % 4 == 0) && (!g.epi.s_hi || g.epi.ld_s % 4 == 0) &&

@@ -222,14 +222,17 @@ class OverlappedShardedGradient:
             grads[leaf_pos] = g
             comm.allreduce_sum_async([g])
 
+        # the objective's exchange goes first (a copy: the forward value itself may still be read by a pullback), so
+        # that it is not one more latency-bound collective behind the last weight sensitivity
+        yd = unbox(y).copy() if G > 1 else unbox(y)
+        comm.allreduce_sum_async([yd])
         propagate(t, rt, on_final=on_final)
-        yd = unbox(y)
         rest = []
         for l in leaves:            # parameters only the shared term touches: G copies of g/G
             if l.pos not in grads and rt.tape[l.pos - 1] is not UNDEF:
                 grads[l.pos] = unthunk(rt.raw(l.pos))
                 rest.append(grads[l.pos])
-        comm.allreduce_sum_async([yd] + rest)
+        comm.allreduce_sum_async(rest)
         out = [grads[l.pos] if l.pos in grads else zeroslike(l) for l in leaves]
         with _timed(ctx, "join_wait", 0, "ms"):           # what of the exchange is NOT hidden behind the sweep
             comm.join()

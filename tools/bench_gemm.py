@@ -32,7 +32,7 @@ if os.environ.get("SHAPES"):
     shapes = {k: v for k, v in shapes.items() if any(k.lower().startswith(x) for x in sel)}
 TAIL = int(os.environ.get("TAIL", "0"))  # report only the last TAIL reps (power-capped steady state)
 for mode in modes:
-    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "bf16x3": nb.MATH_BF16X3, "f64": nb.MATH_DEFAULT}[mode]
+    ctx.math_mode = {"3xtf32": nb.MATH_3XTF32, "tf32": nb.MATH_TF32, "fp32": nb.MATH_FP32, "bf16x3": nb.MATH_BF16X3, "fp16x3": nb.MATH_FP16X3, "f64": nb.MATH_DEFAULT}[mode]
     for name, fn in shapes.items():
         for _ in range(2):
             fn()
