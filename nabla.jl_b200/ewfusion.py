@@ -172,6 +172,17 @@ def _expr(branch, rvs, cons, leaves, nodes, index):
     return symbolic(p, syms)
 
 
+def _full_shape(arrays):
+    """Broadcast shape of the operands (trailing singleton dimensions dropped like Julia's)."""
+    nd = max((len(a.shape) for a in arrays), default=0)
+    full = [1] * nd
+    for a in arrays:
+        for i, e in enumerate(a.shape):
+            if e != 1:
+                full[i] = e
+    return tuple(full)
+
+
 def chain_pullback(y, ybar, rvs, own, alias_ok=None):
     """Fused pullback of Branch ``y`` together with every chainable Branch below it.  Returns False when nothing is
     chainable or the composition does not fit (the caller then runs the ordinary per-Branch pullback)."""
@@ -204,6 +215,13 @@ def chain_pullback(y, ybar, rvs, own, alias_ok=None):
         else:
             outs[k], acc[k] = own(slot), True
         d_tape[a.pos - 1] = outs[k]
+    # the root Branch's own forward value, when it was materialised, is the saved y of the composed program: the kernels
+    # take f' from it where f' is a function of y alone (tanh.(A .+ b): 1 - y^2 instead of a second tanh)
+    y_saved = None
+    if not reduce and scale == 1.0:
+        v = y.val
+        if isinstance(v, DevArray) and v.pending is None and tuple(v.shape) == tuple(_full_shape(leaves)):
+            y_saved = v
     if any(o is not None for o in outs):
-        K.bcast_pullback(pc, ybar, None, leaves, outs, acc)
+        K.bcast_pullback(pc, ybar, y_saved, leaves, outs, acc)
     return True
