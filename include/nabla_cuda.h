@@ -28,7 +28,7 @@ extern "C" {
 
 #define NB_ABI_VERSION 1
 #define NB_MAX_DIMS 4
-#define NB_MAX_ARGS 6      /* operands of one broadcast call (the reference caps map at 10) */
+#define NB_MAX_ARGS 10     /* operands of one broadcast / map call (the reference generates map for up to ten: functional.jl:10-18) */
 #define NB_MAX_INSTR 32    /* instructions of one scalar program */
 #define NB_MAX_CONSTS 16
 

@@ -359,7 +359,7 @@ import SpecialFunctions
 const SF = SpecialFunctions
 "`step(x) = x > 0 ? 1 : 0` (NB_OP_STEP)"
 step(x::Real) = x > 0 ? one(x) : zero(x)
-const NB_MAX_ARGS, NB_MAX_INSTR, NB_MAX_CONSTS = 6, 32, 16
+const NB_MAX_ARGS, NB_MAX_INSTR, NB_MAX_CONSTS = 10, 32, 16
 
 # function => nb_op (include/nabla_cuda.h; the values are ABI).  The list is test/runtests.jl:28-52.
 const UNARY_OPS = Dict{Any,Int32}(

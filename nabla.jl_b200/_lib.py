@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("NABLA_CUDA_LIB") or os.path.join(_HERE, "libnabla_cud
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "nabla_cuda.h")
 
 NB_MAX_DIMS = 4
-NB_MAX_ARGS = 6
+NB_MAX_ARGS = 10
 NB_MAX_INSTR = 32
 NB_MAX_CONSTS = 16
 NB_F32, NB_F64 = 0, 1

@@ -125,7 +125,7 @@ struct FastEv {
 
 template <typename T, int V>
 struct GenEv {
-  static constexpr int MAXOUT = NB_MAX_ARGS;
+  static constexpr int MAXOUT = NB_MAX_OUTS;
   static __device__ __forceinline__ void run(const MRP& P, const nb_prog& G, int64_t r, int64_t c,
                                              int nvalid, T (&o)[MAXOUT][V]) {
     T x[NB_MAX_ARGS][V], yb[V];
@@ -176,7 +176,7 @@ struct GenEv {
 //     accumulating — the first contribution to every adjoint (nb_prog::rflags, computed once on the host).
 template <typename T, int V>
 struct GenEvS {
-  static constexpr int MAXOUT = NB_MAX_ARGS;
+  static constexpr int MAXOUT = NB_MAX_OUTS;
   using VT = typename std::conditional<V == 1, T, typename VecOf<T>::type>::type;
 
   static __device__ __forceinline__ void run(const MRP& P, const nb_prog& G, int64_t r, int64_t c,
@@ -212,8 +212,10 @@ struct GenEvS {
       load_vals<T, V>(P.arg[k].p, r * P.arg[k].rs + c * P.arg[k].cs, P.arg[k].rs != 0, nvalid, vok, last);
       st(k, last);
     }
-    // forward
+    // forward (in a pullback only the values some computed partial reads: nb_prog::fwd_skip)
+    const uint32_t skip = P.pullback ? G.fwd_skip : 0u;
     for (int i = 0; i < n; ++i) {
+      if (skip >> i & 1u) continue;
       T a[V], b[V];
       get(G.a[i], a);
       if (G.hop[i] >= NB_HOP_ADD && G.hop[i] != NB_HOP_COLD_UN) get(G.b[i], b);
@@ -652,9 +654,9 @@ struct Call {
   const nb_tensor* ysaved;   // nullable
   bool pullback;
   int nout;
-  const nb_tensor* outs[NB_MAX_ARGS];
-  int out_wrt[NB_MAX_ARGS];  // operand index each output differentiates (pullback)
-  bool out_acc[NB_MAX_ARGS];
+  const nb_tensor* outs[NB_MAX_OUTS];
+  int out_wrt[NB_MAX_OUTS];  // operand index each output differentiates (pullback)
+  bool out_acc[NB_MAX_OUTS];
   double scale;
 };
 
@@ -849,7 +851,7 @@ int32_t launch_all(nb_ctx* ctx, MRP& P, const nb_prog& G, int ngroups, int lean_
 static int32_t run_call(nb_ctx* ctx, const Call& C) {
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   NB_REQUIRE(ctx, C.nargs >= 1 && C.nargs <= NB_MAX_ARGS, NB_ERR_INVALID, "bad operand count");
-  NB_REQUIRE(ctx, C.nout >= 1 && C.nout <= NB_MAX_ARGS, NB_ERR_INVALID, "bad output count");
+  NB_REQUIRE(ctx, C.nout >= 1 && C.nout <= NB_MAX_OUTS, NB_ERR_INVALID, "bad output count");
   const int32_t dt = C.outs[0]->dtype;
   NB_REQUIRE(ctx, dt == NB_F32 || dt == NB_F64, NB_ERR_INVALID, "bad dtype");
   std::vector<const nb_tensor*> parts;
@@ -1068,13 +1070,23 @@ static int32_t run_call(nb_ctx* ctx, const Call& C) {
       }
       P.has_y = P.need_y;
     }
+    // a composite pullback runs on a copy of the program specialised for the operands this launch differentiates
+    nb_prog Gs;
+    const nb_prog* Gp = &G;
+    if (!fast && C.pullback && G.n_instr > 1) {
+      Gs = G;
+      uint32_t wanted = 0;
+      for (int k = 0; k < C.nout; ++k) wanted |= 1u << C.out_wrt[k];
+      nb_prog_derive(Gs, wanted);
+      Gp = &Gs;
+    }
     // otherwise: shared-memory interpreter when the slots of a 256-thread CTA fit
     const bool use_s = (size_t)2 * (G.nargs + G.n_instr) * 16 * 256 <= GEN_SMEM_LIMIT && !getenv("NB_GEN_LOCAL");
     if (dt == NB_F32) return fast ? launch_all<float, FastEv>(ctx, P, G, ng, lean_mode)
-                           : use_s ? launch_all<float, GenEvS>(ctx, P, G, ng, pmode, true)
+                           : use_s ? launch_all<float, GenEvS>(ctx, P, *Gp, ng, pmode, true)
                                    : launch_all<float, GenEv>(ctx, P, G, ng, pmode, true);
     return fast ? launch_all<double, FastEv>(ctx, P, G, ng, lean_mode)
-         : use_s ? launch_all<double, GenEvS>(ctx, P, G, ng, pmode, true)
+         : use_s ? launch_all<double, GenEvS>(ctx, P, *Gp, ng, pmode, true)
                  : launch_all<double, GenEv>(ctx, P, G, ng, pmode, true);
   }
 
@@ -1198,9 +1210,9 @@ int32_t nb_bcast_pullback(nb_ctx* ctx, const nb_prog* prog, const nb_tensor* yba
   Call C{};
   C.prog = prog; C.nargs = nargs; C.args = args; C.pullback = true; C.scale = 1.0;
   C.ybar = ybar; C.ysaved = y_saved;
-  // fast path handles <= 2 outputs per launch; generic up to NB_MAX_ARGS
+  // fast path handles <= 2 outputs per launch; generic up to NB_MAX_OUTS
   const bool fast = !prog || prog->n_instr <= 1;
-  const int per = fast ? 2 : NB_MAX_ARGS;
+  const int per = fast ? 2 : NB_MAX_OUTS;
   int k = 0;
   while (k < nargs) {
     C.nout = 0;

@@ -95,7 +95,9 @@ struct ProgPack {
       }
     }
     T last[N][V];
+    const uint32_t skip = MODE != LM_FWD ? G.fwd_skip : 0u;   // values no computed partial reads (nb_prog_derive)
     for (int i = 0; i < nfwd; ++i) {
+      if (skip >> i & 1u) continue;
       const int hop = G.hop[i], op = G.op[i], ia = G.a[i], ib = G.b[i];
       const bool bin = hop >= NB_HOP_ADD && hop != NB_HOP_COLD_UN;
 #pragma unroll

@@ -22,6 +22,8 @@ struct OutS {
   void* partial;
 };
 
+// sensitivities one launch of the general kernels produces (a pullback that wants more runs several launches)
+#define NB_MAX_OUTS 6
 #define NB_FAST_NIN 2
 struct MRP {
   int64_t rows, cols;
@@ -42,7 +44,7 @@ struct MRP {
   double scale;
   Opnd arg[NB_MAX_ARGS];
   Opnd ybar, ys;
-  OutS out[NB_MAX_ARGS];
+  OutS out[NB_MAX_OUTS];
 };
 
 template <typename T> struct VecOf;

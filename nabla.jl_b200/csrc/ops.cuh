@@ -21,6 +21,8 @@ struct nb_prog {
   uint8_t hop[NB_MAX_INSTR];     // dense dispatch index (NB_HOP_*): the switch becomes a jump table
   uint8_t rflags[NB_MAX_INSTR];  // NB_RF_* : what the reverse step of instruction i reads and how it writes
   uint32_t arg_live;             // bit k: operand k reaches the result (otherwise its sensitivity is zero)
+  uint32_t fwd_skip;             // pullback mode: bit i = the VALUE of instruction i is read by no partial that is
+                                 // computed (nor needed to compute one that is): the forward pass skips it
   // the program selects between branches (NB_OP_MASK / NB_OP_MASKN): a zero adjoint then contributes exactly zero
   // (0 * Inf from the branch NOT taken must not reach the result: ForwardDiff never evaluates its derivative)
   uint32_t guard;
@@ -547,8 +549,12 @@ __device__ __forceinline__ void nb_prog_grad(const nb_prog& P, const T* vals, T*
   }
 }
 
-// Fill the derived fields of a validated program (host, nb_prog_create).
-inline void nb_prog_derive(nb_prog& P) {
+// Fill the derived fields of a validated program (host).  nb_prog_create derives them for "every operand wanted"; a
+// pullback launch of a composite program re-derives them on a copy for the operands it actually differentiates
+// (`wanted`, bit k = operand k): adjoints are propagated only along paths that reach a wanted operand, and forward
+// values no remaining partial reads are not computed — in `x .* log.(f .+ eps)` with x a constant (the data of
+// examples/vae.jl:79) the sensitivity of f needs x and f + eps, never the logarithm.
+inline void nb_prog_derive(nb_prog& P, uint32_t wanted = 0xFFFFFFFFu) {
   auto hop_of = [](int op) -> uint8_t {
     switch (op) {
       case NB_OP_IDENTITY: return NB_HOP_IDENTITY; case NB_OP_NEG: return NB_HOP_NEG;
@@ -562,29 +568,46 @@ inline void nb_prog_derive(nb_prog& P) {
   const int n = P.n_instr, na = P.nargs;
   bool live[NB_MAX_INSTR] = {false};
   bool written[NB_MAX_SLOTS] = {false};
+  bool reach[NB_MAX_SLOTS] = {false};     // the slot is a wanted operand or is computed from one
+  bool need_val[NB_MAX_SLOTS] = {false};  // the slot's forward value is read in pullback mode
+  for (int k = 0; k < na; ++k) reach[k] = (wanted >> k & 1u) != 0;
+  for (int i = 0; i < n; ++i) {
+    const bool bin = nb_op_is_binary(P.op[i]);
+    const int a = P.a[i], b = bin ? P.b[i] : -1;
+    reach[na + i] = (a >= 0 && reach[a]) || (b >= 0 && reach[b]);
+  }
   if (n > 0) live[n - 1] = true;
   for (int i = n - 1; i >= 0; --i) {
     P.hop[i] = hop_of(P.op[i]);
     P.rflags[i] = 0;
-    if (!live[i]) continue;
+    if (!live[i] || !reach[na + i]) continue;
     const bool bin = nb_op_is_binary(P.op[i]);
     const int a = P.a[i], b = bin ? P.b[i] : -1;
+    const bool ca = a >= 0 && reach[a], cb = bin && b >= 0 && reach[b];
     uint8_t f = NB_RF_LIVE;
     int needs = 0;
-    if (a >= 0) { f |= NB_RF_SLOT_A; needs |= nb_partial_needs(P.op[i], 0); }
-    if (bin && b >= 0) { f |= NB_RF_SLOT_B; needs |= nb_partial_needs(P.op[i], 1); }
-    if (needs & 1) f |= NB_RF_NEED_A;
-    if (needs & 2) f |= NB_RF_NEED_B;
-    if (needs & 4) f |= NB_RF_NEED_Y;
-    if (a >= 0) {
+    if (ca) { f |= NB_RF_SLOT_A; needs |= nb_partial_needs(P.op[i], 0); }
+    if (cb) { f |= NB_RF_SLOT_B; needs |= nb_partial_needs(P.op[i], 1); }
+    if (needs & 1) { f |= NB_RF_NEED_A; if (a >= 0) need_val[a] = true; }
+    if (needs & 2) { f |= NB_RF_NEED_B; if (b >= 0) need_val[b] = true; }
+    if (needs & 4) { f |= NB_RF_NEED_Y; need_val[na + i] = true; }
+    if (ca) {
       if (!written[a]) { f |= NB_RF_FIRST_A; written[a] = true; }
       if (a >= na) live[a - na] = true;
     }
-    if (bin && b >= 0 && b != a) {
+    if (cb && b != a) {
       if (!written[b]) { f |= NB_RF_FIRST_B; written[b] = true; }
       if (b >= na) live[b - na] = true;
     }
     P.rflags[i] = f;
+  }
+  // a value that is read needs its own operands' values
+  P.fwd_skip = 0;
+  for (int i = n - 1; i >= 0; --i) {
+    if (!need_val[na + i]) { P.fwd_skip |= 1u << i; continue; }
+    const bool bin = nb_op_is_binary(P.op[i]);
+    if (P.a[i] >= 0) need_val[P.a[i]] = true;
+    if (bin && P.b[i] >= 0) need_val[P.b[i]] = true;
   }
   P.guard = 0;
   for (int i = 0; i < n; ++i)

@@ -28,6 +28,7 @@ from .device import BroadcastView, DevArray
 from .scalar import Sym, linearize, symbolic
 
 MAX_ELEMS = int(os.environ.get("NB_EW_FUSE_MAX", str(1 << 22)))
+MAX_LEAVES = min(6, NB_MAX_ARGS)   # composed programs: more operands than this no longer fit the shared-memory interpreter
 ENABLED = os.environ.get("NB_EW_FUSE", "1") != "0"
 
 
@@ -96,7 +97,7 @@ def compose(prog, dev):
             syms.append(leaf(d))
         else:
             syms.append(symbolic(L.prog, [leaf(x) for x in L.leaves]))
-    if len(leaves) > NB_MAX_ARGS:
+    if len(leaves) > MAX_LEAVES:
         return None
     try:
         return linearize(symbolic(prog, syms), len(leaves), "fused"), leaves
@@ -198,7 +199,7 @@ def chain_pullback(y, ybar, rvs, own, alias_ok=None):
     #  that keeps the reverse tape — and every deferred launch hanging off its slots — alive until the cyclic collector
     #  runs, long after the sweep)
     root = _expr(y, rvs, cons, leaves, nodes, index)
-    if len(leaves) > NB_MAX_ARGS:
+    if len(leaves) > MAX_LEAVES:
         return False
     try:
         pc = linearize(root, len(leaves), "fused")

@@ -377,6 +377,16 @@ def test_map_and_literal_pow_known_answers(nb, orc):
                rng.standard_normal((4, 6)))
     with pytest.raises(nb.DimensionMismatch):
         nb.map_(nb.add, nb.Leaf(nb.Tape(), a), np.ones(4))
+    # ten operands, the most the reference generates `map` for (functional.jl:10-18): every one a Node, so the pullback
+    # wants ten sensitivities (more than one launch of the general kernels produces)
+    ops10 = [rng.standard_normal((4, 6)) for _ in range(10)]
+    f10 = lambda ns, *v: ns.map_(lambda a0, a1, a2, a3, a4, a5, a6, a7, a8, a9:
+                                 a0 * a1 + a2 * a3 - a4 * a5 + ns.sin(a6) * a7 + a8 / (2.0 + a9 * a9), *v)
+    check_case(nb, orc, f10, ops10, rng.standard_normal((4, 6)))
+    f10b = lambda ns, *v: ns.broadcast(lambda a0, a1, a2, a3, a4, a5, a6, a7, a8, a9:
+                                       (a0 + a1 + a2) * (a3 + a4) + a5 * a6 + a7 + a8 * a9, *v)
+    mixed = [rng.standard_normal(sh) for sh in ((4, 6), (4,), (1, 6), (4, 6), (4, 1), (4, 6), (1, 6), (4,), (4, 6), (4, 6))]
+    check_case(nb, orc, f10b, mixed, rng.standard_normal((4, 6)))
 
 
 def test_empty_and_error_cases(nb, ctx):
