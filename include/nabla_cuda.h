@@ -56,7 +56,11 @@ typedef enum nb_dtype { NB_F32 = 0, NB_F64 = 1 } nb_dtype;
  * Float64: exact FP64 FMA on the DMMA path for small products, exact int8 slice products on tcgen05 (Ozaki split)
  * for m*n*k >= 3e9 — its error is ~2^-49 relative to max|row of A| * max|col of B| (4e-14 norm-wise measured), NOT
  * relative to |A||B| element-wise like dgemm: rows or columns with a very large dynamic range lose low-order bits of
- * their small entries.  NB_MATH_FP32 (or NB_F64_OZAKI=0) keeps every Float64 product on DMMA. */
+ * their small entries.  A range guard measures, in the pass that finds the row / column scales, how far the largest
+ * entry of a line stands above the others (peak = max * (K-1) / (sum - max)); when peak_A * peak_B exceeds
+ * NB_OZAKI_PEAK_LIMIT (default 2^24, i.e. ordinary entries of a line would keep fewer than 25 bits; 4096 = strict,
+ * 0 = off) the product runs on DMMA instead — decided on the device, no host synchronisation.
+ * NB_MATH_FP32 (or NB_F64_OZAKI=0) keeps every Float64 product on DMMA. */
 typedef enum nb_math_mode {
   NB_MATH_DEFAULT = 0,  /* f32: NB_MATH_FP16X3; f64: DMMA / Ozaki split by size */
   NB_MATH_TF32 = 1,     /* f32: single-pass kind::tf32 on tcgen05 (~8e-4 relative error) */

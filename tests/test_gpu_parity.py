@@ -1328,7 +1328,7 @@ def test_gemm_f64_ozaki_split(nb, ctx):
 
 def test_gemm_f64_split_range_guard(nb, ctx):
     """dgemm's error is relative to sum_k |a_ik||b_kj|, the int8 split's to max|a_i.| * max|b_.j| (csrc/ozaki.cu): a row
-    dominated by one outlier that meets a zero of B would keep only ~25 bits of its other entries.  The guard measures
+    dominated by one outlier (1e9 here) that meets a zero of B would keep only ~19 bits of its other entries.  The guard measures
     how far the largest entry of a line stands above the rest in the pass that finds the scales and — on the device,
     without a host synchronisation — hands such a product to DMMA.  Both split variants (one launch / one launch per
     level); with the guard disabled by its limit the same product shows the loss the guard prevents."""
@@ -1337,7 +1337,7 @@ def test_gemm_f64_split_range_guard(nb, ctx):
     for (m, n, k) in ((2048, 2048, 1024), (4100, 4200, 4000)):
         A = rng.standard_normal((m, k))
         B = rng.standard_normal((k, n))
-        A[5, 0] = 1e7          # the outlier of row 5 ...
+        A[5, 0] = 1e9          # the outlier of row 5 ...
         B[0, :] = 0.0          # ... meets zeros: C[5, :] is made of the ordinary entries of the row
         ref = A @ B
         Cd = ctx.zeros((m, n), np.float64)
