@@ -714,15 +714,16 @@ def run_gpu(args):
                          f"MEASURED_PEAKS has no int8 figure) / {npass} int8 passes per Float64 product (Ozaki split, "
                          f"{slices} slices); small products on DMMA")
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+        tpath = os.path.join(ROOT, "profiles", "r2_gemm_traffic.json")
         if args.workload == "wide_mlp" and args.dtype == "f32" and n == 1 and B == 32768 and os.path.exists(tpath):
             t = json.load(open(tpath))["per_gemm_call"]["NN_8192x32768x8192"]
             traffic = t["dram_read_bytes"] + t["dram_write_bytes"]
         nl = sum(v[1] for v in by_tag.values())
         roof = {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "traffic": traffic,
-                "traffic_note": "DRAM bytes per GEMM launch (8192x32768x8192, same kernel) from one ncu capture, "
-                                "profiles/r1_gemm_traffic.json; algorithmic bytes 2.42e9" if traffic else None,
+                "traffic_note": "DRAM bytes of one forward 8192x32768x8192 launch of the same kernel (FP16x3, 128-long K "
+                                "chunks) from one ncu --set full capture, profiles/r2_gemm_traffic.json; algorithmic "
+                                "bytes 2.42e9" if traffic else None,
                 "kernel": "nb_gemm / nb_gemm_fused (dense GEMM sensitivities: forward A*B, Abar=Ybar*B', Bbar=A'*Ybar)",
                 "peak_note": peak_note, "tensor_work_frac": passes * achieved / peak,
                 "launches": nl, "share_of_step": gemm_ms_total / ms_prof,
