@@ -185,6 +185,13 @@ int32_t nb_host_free(void* p);
 int32_t nb_prog_create(int32_t nargs, int32_t n_instr, const int32_t* ops, const int32_t* a,
                        const int32_t* b, int32_t n_consts, const double* consts, nb_prog** out);
 int32_t nb_prog_destroy(nb_prog* prog);
+/* What a pullback launch of `prog` computes when it differentiates the operands in `wanted_mask` (bit k = operand k;
+ * host only, no device work).  fmad evaluates the whole function on duals once per operand (core.jl:285-301); the
+ * device propagates adjoints only along paths that reach a wanted operand and skips forward values no remaining
+ * partial reads.  Bit i of *live_instr: instruction i takes part in the reverse pass; bit i of *fwd_skip: its value is
+ * not computed; bit k of *arg_live: operand k reaches the result (otherwise its sensitivity is zero). */
+int32_t nb_prog_pullback_plan(const nb_prog* prog, uint32_t wanted_mask, uint32_t* live_instr, uint32_t* fwd_skip,
+                              uint32_t* arg_live);
 
 /* ---- family (1): broadcast forward / pullback fused with unbroadcast ----------------------- */
 /* out = f.(args...)   — primal of Branch(broadcast, (f, args...)): functional.jl:48-51, core.jl:89 */

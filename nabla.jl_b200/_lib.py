@@ -91,6 +91,7 @@ _SIGS = {
     "nb_prog_create": ([_i32, _i32, C.POINTER(_i32), C.POINTER(_i32), C.POINTER(_i32), _i32,
                         C.POINTER(_dbl), _pp], _i32),
     "nb_prog_destroy": ([_p], _i32),
+    "nb_prog_pullback_plan": ([_p, C.c_uint32, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)], _i32),
     "nb_bcast_fwd": ([_p, _p, _i32, _tp, _tp], _i32),
     "nb_bcast_pullback": ([_p, _p, _tp, _tp, _i32, _tp, _u32, _tp, _u32], _i32),
     "nb_bcast_reduce": ([_p, _p, _i32, _tp, _dbl, _tp, _i32], _i32),

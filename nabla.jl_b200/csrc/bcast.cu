@@ -1191,6 +1191,19 @@ int32_t nb_bcast_fwd(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const nb_t
   return run_call(ctx, C);
 }
 
+int32_t nb_prog_pullback_plan(const nb_prog* prog, uint32_t wanted_mask, uint32_t* live_instr, uint32_t* fwd_skip,
+                              uint32_t* arg_live) {
+  if (!prog || !live_instr || !fwd_skip || !arg_live) return nb_fail(nullptr, NB_ERR_INVALID, "nb_prog_pullback_plan: NULL argument");
+  nb_prog g = *prog;
+  nb_prog_derive(g, wanted_mask);
+  *live_instr = 0;
+  for (int i = 0; i < g.n_instr; ++i)
+    if (g.rflags[i] & NB_RF_LIVE) *live_instr |= 1u << i;
+  *fwd_skip = g.fwd_skip;
+  *arg_live = g.arg_live;
+  return NB_OK;
+}
+
 int32_t nb_bcast_reduce(nb_ctx* ctx, const nb_prog* prog, int32_t nargs, const nb_tensor* args,
                         double scale, const nb_tensor* out, int32_t accumulate) {
   nb_enter(ctx);

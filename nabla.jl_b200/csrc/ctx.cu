@@ -190,6 +190,10 @@ int32_t nb_sweep_begin(nb_ctx* ctx) {
 int32_t nb_sync(nb_ctx* ctx) {
   nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
+  // (a synchronisation inside nb_graph_begin / nb_graph_end would invalidate the capture with an opaque CUDA error)
+  NB_REQUIRE(ctx, !ctx->capturing, NB_ERR_INVALID,
+             "nb_sync: the context is capturing a CUDA graph — the captured function read a device value on the host or "
+             "uploaded pageable host data (an index vector, a NumPy operand); create such operands before the capture");
   NB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return NB_OK;
 }
@@ -240,6 +244,14 @@ int32_t nb_h2d(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
   nb_enter(ctx);
   NB_REQUIRE(ctx, ctx, NB_ERR_INVALID, "ctx is NULL");
   if (!nbytes) return NB_OK;
+  if (ctx->capturing) {   // only pinned memory can be the source of a captured copy
+    cudaPointerAttributes at{};
+    const bool pinned = cudaPointerGetAttributes(&at, src) == cudaSuccess && at.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    NB_REQUIRE(ctx, pinned, NB_ERR_INVALID,
+               "nb_h2d: pageable host memory cannot be copied inside a CUDA-graph capture (an index vector or a NumPy "
+               "operand created by the captured function): upload it before the capture or use pinned memory");
+  }
   nb_note_write(ctx, dst);
   NB_CUDA_OK(ctx, cudaMemcpyAsync(dst, src, nbytes, cudaMemcpyHostToDevice, ctx->stream));
   ctx->stats.h2d_bytes += nbytes;
@@ -256,6 +268,8 @@ int32_t nb_d2h_async(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
 }
 
 int32_t nb_d2h(nb_ctx* ctx, void* dst, const void* src, uint64_t nbytes) {
+  NB_REQUIRE(ctx, !ctx || !ctx->capturing, NB_ERR_INVALID,
+             "nb_d2h: the context is capturing a CUDA graph — a device value cannot be read on the host there");
   int32_t rc = nb_d2h_async(ctx, dst, src, nbytes);
   if (rc != NB_OK) return rc;
   NB_CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));

@@ -752,6 +752,25 @@ def test_graph_capture_replays_sweep(nb, ctx):
     assert cap.launches_per_replay > 0
 
 
+def test_capture_rejects_host_uploads_with_a_clear_error(nb, ctx):
+    """A captured function that uploads pageable host data (the index vector of `getindex`) or reads a device value on
+    the host cannot be recorded: the library says so instead of surfacing CUDA's stream-capture error, ends the
+    capture cleanly, and the context keeps working."""
+    from nabla_jl_b200._lib import NablaCudaError
+    x = ctx.asarray(np.arange(1.0, 7.0))
+    f = lambda v: nb.sum(nb.getindex(v, [2, 3, 3]))
+    (g_eager,) = nb.nabla(f)(x)
+    expected = g_eager.numpy()
+    with pytest.raises(NablaCudaError, match="captur"):
+        nb.CapturedGradient(f, [x], ctx)
+    g = lambda v: nb.sum(nb.broadcast(nb.mul, v, float(nb.to_host(nb.sum(v)))))   # host read inside the function
+    with pytest.raises(NablaCudaError, match="captur"):
+        nb.CapturedGradient(g, [x], ctx)
+    (g_again,) = nb.nabla(f)(x)
+    np.testing.assert_array_equal(g_again.numpy(), expected)
+    np.testing.assert_array_equal(expected, [0.0, 1.0, 2.0, 0.0, 0.0, 0.0])
+
+
 @pytest.mark.parametrize("mode,tol", [("bf16x3", 3e-5), ("3xtf32", 2e-5), ("tf32", 3e-3), ("fp32", 2e-5)])
 def test_gemm_tensor_core_modes(nb, ctx, mode, tol):
     """Float32 GEMM on tcgen05 (kind::tf32) for all four transposes, ragged M/N/K tails, alpha/beta.

@@ -490,6 +490,124 @@ def test_pullback_reads():
     assert fusion.pullback_reads(comp, [0]) is None
 
 
+def _pullback_plan(P, wanted):
+    """C side: nb_prog_pullback_plan of the traced program -> (live_instr, fwd_skip, arg_live) bit masks."""
+    L = _lib.lib()
+    n = len(P.ops)
+    I = ctypes.c_int32 * max(n, 1)
+    D = ctypes.c_double * max(len(P.consts), 1)
+    h = ctypes.c_void_p()
+    assert L.nb_prog_create(P.nargs, n, I(*P.ops), I(*P.a), I(*P.b), len(P.consts), D(*P.consts), ctypes.byref(h)) == 0
+    live, skip, alive = ctypes.c_uint32(), ctypes.c_uint32(), ctypes.c_uint32()
+    assert L.nb_prog_pullback_plan(h, wanted, ctypes.byref(live), ctypes.byref(skip), ctypes.byref(alive)) == 0
+    L.nb_prog_destroy(h)
+    return live.value, skip.value, alive.value
+
+
+def _pullback_plan_py(P, wanted):
+    """Independent restatement: which instructions a pullback for the operands in `wanted` runs in reverse, and which
+    forward values it has to compute (everything a computed partial reads, plus what those values are computed from)."""
+    from nabla_jl_b200 import fusion
+    na, n = P.nargs, len(P.ops)
+    binary = lambda op: _lib.OPCODES["add"] <= op < _lib.OPCODES["binary_end"]
+    operands = lambda i: [P.a[i]] + ([P.b[i]] if binary(P.ops[i]) else [])
+    reach = [bool(wanted >> k & 1) for k in range(na)]
+    for i in range(n):
+        reach.append(any(s >= 0 and reach[s] for s in operands(i)))
+    live, need, written = [False] * n, [False] * (na + n), set()
+    if n:
+        live[n - 1] = True
+    for i in range(n - 1, -1, -1):
+        if not (live[i] and reach[na + i]):
+            live[i] = False
+            continue
+        for side, s in enumerate(operands(i)):
+            if s < 0 or not reach[s]:
+                continue
+            bits = fusion.partial_needs(P.ops[i], side)
+            if bits & 1 and P.a[i] >= 0:
+                need[P.a[i]] = True
+            if bits & 2 and binary(P.ops[i]) and P.b[i] >= 0:
+                need[P.b[i]] = True
+            if bits & 4:
+                need[na + i] = True
+            written.add(s)
+            if s >= na:
+                live[s - na] = True
+    skip = 0
+    for i in range(n - 1, -1, -1):
+        if not need[na + i]:
+            skip |= 1 << i
+            continue
+        for s in operands(i):
+            if s >= 0:
+                need[s] = True
+    live_mask = sum(1 << i for i in range(n) if live[i])
+    alive = sum(1 << k for k in range(na) if k in written or n == 0)
+    return live_mask, skip, alive
+
+
+def test_pullback_plan_skips_what_no_partial_reads():
+    """examples/vae.jl:79 / mlp.jl:73: the log-likelihood term `x * log(f + eps) + (1 - x) * log(1 + eps - f)` with `x`
+    data.  The sensitivity of `f` needs x and the two arguments of the logarithms — never the logarithms: the pullback
+    launch for f alone skips them (fmad's duals evaluate everything, core.jl:285-301); asked for x as well it cannot."""
+    eps = 1e-12
+    P = nb.compile_scalar(lambda x, f: x * nb.log(f + eps) + (1.0 - x) * nb.log(1.0 + eps - f), 2)
+    logs = [i for i, op in enumerate(P.ops) if op == _lib.OPCODES["log"]]
+    assert len(logs) == 2
+    live, skip, alive = _pullback_plan(P, 0b10)          # wanted: f (operand 1)
+    assert all(skip >> i & 1 for i in logs) and alive == 0b10
+    assert all(live >> i & 1 for i in logs)               # the adjoint still flows THROUGH log (its partial reads a)
+    live_x, skip_x, alive_x = _pullback_plan(P, 0b01)    # wanted: x — d/dx = log(..) - log(..): the values are needed
+    assert not any(skip_x >> i & 1 for i in logs) and alive_x == 0b01
+    assert not any(live_x >> i & 1 for i in logs)         # ... but no adjoint goes through the logarithms towards f
+    _, skip_all, alive_all = _pullback_plan(P, 0b11)
+    assert not any(skip_all >> i & 1 for i in logs) and alive_all == 0b11
+    assert skip_all & ~skip == 0 and skip_all != skip             # wanting more never skips more
+    # an operand that does not reach the result has no sensitivity
+    Q = nb.compile_scalar(lambda a, b: nb.tanh(a) + 0.0 * b, 2)
+    assert _pullback_plan(Q, 0b11)[2] in (0b01, 0b11)
+
+
+def test_pullback_plan_matches_its_restatement_on_random_programs():
+    """nb_prog_derive (csrc/ops.cuh) against an independent Python restatement: for random traced programs and every
+    subset of wanted operands the reverse instructions, the skipped forward values and the live operands are equal."""
+    import numpy as np
+    rng = np.random.default_rng(77)
+    un = [nb.tanh, nb.sin, nb.exp, nb.log, nb.sqrt, nb.abs2, lambda v: -v, lambda v: 1.0 / (1.0 + nb.exp(-v))]
+
+    def gen(depth, nargs):
+        r = rng.random()
+        if depth == 0 or r < 0.2:
+            k = int(rng.integers(nargs))
+            return lambda xs: xs[k]
+        if r < 0.3:
+            c = float(np.round(rng.uniform(0.5, 2), 2))
+            return lambda xs: c
+        if r < 0.6:
+            f, sub = un[int(rng.integers(len(un)))], gen(depth - 1, nargs)
+            return lambda xs: f(sub(xs) + 0 * xs[0])
+        l, rr, kind = gen(depth - 1, nargs), gen(depth - 1, nargs), int(rng.integers(4))
+        return lambda xs: (l(xs) + rr(xs), l(xs) - rr(xs), l(xs) * rr(xs), l(xs) / (2.0 + rr(xs)))[kind]
+
+    done = 0
+    for _ in range(300):
+        nargs = int(rng.integers(1, 5))
+        expr = gen(4, nargs)
+        try:
+            P = nb.compile_scalar(lambda *xs: expr(list(xs)), nargs)
+        except (nb.UnsupportedOp, TypeError):
+            continue
+        if len(P.ops) < 2:
+            continue
+        for wanted in range(1, 1 << nargs):
+            assert _pullback_plan(P, wanted) == _pullback_plan_py(P, wanted), (P.ops, P.a, P.b, wanted)
+        done += 1
+        if done == 120:
+            break
+    assert done == 120
+
+
 def test_ozaki_split_scheme_in_numpy():
     """The Float64-on-int8 scheme of csrc/ozaki.cu restated in NumPy (no GPU): power-of-two row/column scales,
     S signed 7-bit slices by q = rint(128 x), x <- 128 x - q, slices concatenated along K (A in order, B
