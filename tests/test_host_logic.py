@@ -608,6 +608,62 @@ def test_pullback_plan_matches_its_restatement_on_random_programs():
     assert done == 120
 
 
+def test_copy_into_an_array_flushes_only_the_launches_that_read_it():
+    """Host logic behind DevArray.copy_from_pinned / copy_from_host (device.Context.flush_readers_of): a deferred launch
+    must run before a buffer it READS is overwritten — directly, through a view, or through an operand that is itself
+    still pending — and nothing else may be launched (a pending product nobody asked for would otherwise run on every
+    new batch: the end-to-end step once took twice the resident one for exactly this reason).  No GPU: stand-in
+    objects with the attributes the method touches."""
+    import weakref
+    import numpy as np
+    from nabla_jl_b200.device import Context, DevArray
+
+    ctx = Context.__new__(Context)
+    ctx._deferred = []
+
+    def arr(base=None):
+        a = DevArray.__new__(DevArray)
+        a.ctx, a._ptr, a.shape, a.dtype = None, None, (2, 2), np.dtype(np.float64)
+        a.shared, a.adjvec, a._base, a.pending, a._tensor = False, False, base, None, None
+        return a
+
+    class Pending:
+        def __init__(self, reads, out):
+            self.reads, self.done, self.flushed = list(reads), False, 0
+            out.pending = self
+            ctx._deferred.append(weakref.ref(self))
+
+        def operands(self):
+            return list(self.reads)
+
+        def flush(self):
+            self.done = True
+            self.flushed += 1
+
+    X, Y, W = arr(), arr(), arr()
+    Xview = arr(base=X)
+    z1, z2, z3, z4 = arr(), arr(), arr(), arr()
+    p1 = Pending([W, X], z1)          # reads X directly
+    p2 = Pending([W, Xview], z2)      # reads a view of X
+    p3 = Pending([W, z1], z3)         # reads z1: once p1 has run, z1 is an ordinary buffer and p3 no longer depends on X
+    p4 = Pending([W, Y], z4)          # does not read X
+    ctx.flush_readers_of(X)
+    assert (p1.flushed, p2.flushed, p3.flushed, p4.flushed) == (1, 1, 0, 0)
+    assert [r() for r in ctx._deferred] == [p3, p4]
+    ctx.flush_readers_of(Xview)       # writing through a view is writing the base: nothing of X is pending any more
+    assert (p3.flushed, p4.flushed) == (0, 0)
+    ctx.flush_readers_of(Y)
+    assert p4.flushed == 1 and [r() for r in ctx._deferred] == [p3]
+    # a launch that reads X only THROUGH a value that is still pending must run (it would force that value later,
+    # after X has changed)
+    ctx._deferred = []
+    u1, u2 = arr(), arr()
+    q2 = Pending([W, u1], u2)         # registered first, reads u1 ...
+    q1 = Pending([W, X], u1)          # ... which is pending and reads X
+    ctx.flush_readers_of(X)
+    assert (q1.flushed, q2.flushed) == (1, 1) and ctx._deferred == []
+
+
 def test_ozaki_split_scheme_in_numpy():
     """The Float64-on-int8 scheme of csrc/ozaki.cu restated in NumPy (no GPU): power-of-two row/column scales,
     S signed 7-bit slices by q = rint(128 x), x <- 128 x - q, slices concatenated along K (A in order, B
