@@ -664,6 +664,42 @@ def test_copy_into_an_array_flushes_only_the_launches_that_read_it():
     assert (q1.flushed, q2.flushed) == (1, 1) and ctx._deferred == []
 
 
+def test_composed_programs_equal_the_branches_they_replace(orc):
+    """Tape-level fusion of adjacent broadcast Branches (ewfusion.py) composes the programs of consecutive dot calls
+    with scalar.symbolic + scalar.linearize.  Property: for random chains `g.(f.(x, y), z)` the composed program,
+    run by the Python restatement of the device interpreter, gives the value and the operand sensitivities of the two
+    Branches evaluated one after the other (functional.jl:48-51 tapes them separately; the chain rule joins them)."""
+    import numpy as np
+    from nabla_jl_b200.scalar import Sym, linearize, symbolic
+    rng = np.random.default_rng(99)
+    inner = [lambda a, b: nb.tanh(a + b), lambda a, b: a * b + 0.5, lambda a, b: nb.exp(-a * a) - b,
+             lambda a, b: a / (2.0 + b * b), lambda a, b: nb.sin(a) * nb.cos(b)]
+    outer = [lambda u, c: nb.log(u * u + 1.5) * c, lambda u, c: u * c + u, lambda u, c: nb.tanh(u) - c * c,
+             lambda u, c: 1.0 / (1.0 + nb.exp(-u)) + c, lambda u, c: nb.sqrt(u * u + c * c + 0.1)]
+    for fi in inner:
+        for go in outer:
+            Pf, Pg = nb.compile_scalar(fi, 2), nb.compile_scalar(go, 2)
+            # leaves (x, y, z): g's first operand is the lazy value f(x, y), its second the leaf z
+            root = symbolic(Pg, [symbolic(Pf, [Sym.arg(0), Sym.arg(1)]), Sym.arg(2)])
+            Pc = linearize(root, 3, "fused")
+            x, y, z = (rng.uniform(-1.2, 1.2, 9) for _ in range(3))
+            u, (ux, uy) = _run_program(orc, Pf, [x, y])
+            v, (vu, vz) = _run_program(orc, Pg, [u, z])
+            w, (wx, wy, wz) = _run_program(orc, Pc, [x, y, z])
+            np.testing.assert_allclose(w, v, rtol=1e-13, atol=1e-13)
+            np.testing.assert_allclose(wx, vu * ux, rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(wy, vu * uy, rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(wz, vz, rtol=1e-12, atol=1e-13)
+            # the same operand on both levels (sigma .* sigma style reuse): one leaf, contributions add up
+            root2 = symbolic(Pg, [symbolic(Pf, [Sym.arg(0), Sym.arg(1)]), Sym.arg(0)])
+            Pd = linearize(root2, 2, "fused")
+            w2, (w2x, w2y) = _run_program(orc, Pd, [x, y])
+            v2, (v2u, v2c) = _run_program(orc, Pg, [u, x])
+            np.testing.assert_allclose(w2, v2, rtol=1e-13, atol=1e-13)
+            np.testing.assert_allclose(w2x, v2u * ux + v2c, rtol=1e-12, atol=1e-13)
+            np.testing.assert_allclose(w2y, v2u * uy, rtol=1e-12, atol=1e-13)
+
+
 def test_ozaki_split_scheme_in_numpy():
     """The Float64-on-int8 scheme of csrc/ozaki.cu restated in NumPy (no GPU): power-of-two row/column scales,
     S signed 7-bit slices by q = rint(128 x), x <- 128 x - q, slices concatenated along K (A in order, B
