@@ -241,8 +241,9 @@ class OracleTimer:
     Small configurations (VAE, MLP at batch 4096: 0.1-0.4 s per evaluation) are timed whole.  The wide MLP at batch
     32768 (tens of seconds and ~40 GB per evaluation) is timed as  t(B) = t_shared + t_data(B): the batch-independent
     shared term (prior over 207.8 M parameters) is timed on its own, the data term — whose cost is proportional to the
-    number of columns — at ``cols`` columns per step and, once, at 2x and 4x that to measure the linearity the
-    extrapolation relies on (reported as ``fit``)."""
+    number of columns — at 4 x ``cols`` columns per step (4096 by default: the per-column cost has converged there,
+    at 1024 it is ~15 % higher) and, once, at ``cols``, 2x and 4x ``cols`` (best of two each) to measure the linearity
+    the extrapolation relies on (reported as ``fit``)."""
 
     def __init__(self, wk, args, dtype):
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
@@ -253,6 +254,7 @@ class OracleTimer:
         self.cols = self.B if self.whole else args.cpu_cols
         ncols = self.B if self.whole else min(self.B, 4 * self.cols)
         self.params, self.data = wk.inputs(ncols, dtype)
+        self.step_cols = ncols      # columns of the per-step sample
         self.t_shared = None
         self.fit = None
 
@@ -268,7 +270,7 @@ class OracleTimer:
             return
         fs = orc.nabla(wk.shared_objective(orc, self.B))
         self.t_shared = _best(lambda: fs(*self.params), 3)
-        pts = [(c, self._data_seconds(c)) for c in (self.cols, 2 * self.cols, 4 * self.cols) if c <= self.data[0].shape[1]]
+        pts = [(c, self._data_seconds(c, 2)) for c in (self.cols, 2 * self.cols, 4 * self.cols) if c <= self.data[0].shape[1]]
         xs, ys = np.array([p[0] for p in pts], float), np.array([p[1] for p in pts], float)
         slope = float(np.sum(xs * ys) / np.sum(xs * xs))       # through the origin: the data term is linear in B
         resid = float(np.max(np.abs(ys - slope * xs) / ys))
@@ -281,13 +283,13 @@ class OracleTimer:
         if self.whole:
             f = orc.nabla(wk.full_objective(orc, self.data, self.B))
             return _best(lambda: f(*self.params), 1)
-        return self.t_shared + self._data_seconds(self.cols) * (self.B / self.cols)
+        return self.t_shared + self._data_seconds(self.step_cols) * (self.B / self.step_cols)
 
     def sample_text(self):
         if self.whole:
             return f"NumPy oracle, whole evaluation at B={self.B} per step (not extrapolated)"
-        return (f"NumPy oracle: shared (prior) term timed whole + data term timed at {self.cols} columns per step, "
-                f"scaled by {self.B}/{self.cols} (the data term is linear in the batch: measured at "
+        return (f"NumPy oracle: shared (prior) term timed whole + data term timed at {self.step_cols} columns per step, "
+                f"scaled by {self.B}/{self.step_cols} (the data term is linear in the batch: measured at "
                 f"{self.fit['cols']} columns, max residual {self.fit['max_rel_residual']:.1%}); extrapolated")
 
 
